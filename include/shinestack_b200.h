@@ -1,0 +1,169 @@
+/*
+ * shinestack_b200.h -- C ABI of libshinestack_b200.so: a B200-native (sm_100a CUDA) implementation of
+ * the Laplacian-pyramid focus-stacking hot path of lucalista/shinestacker.
+ *
+ * The reference is pure Python; its "FFI" for this path is the stack-algo protocol that
+ * FocusStack / FocusStackBunch call (reference src/shinestacker/algorithms/stack.py:23,29,47,108 and
+ * base_stack_algo.py:9-42).  Each entry point below names the reference interface it replaces.  The
+ * reference-side binding is the ctypes shim in shinestacker_b200/pyramid.py.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * ss_status; nothing throws across the ABI; ss_last_error() returns a thread-local message.  Frames are
+ * H x W x 3 interleaved BGR, 8 or 16 bits per sample, exactly what cv2.imread delivers to
+ * PyramidStack.focus_stack (reference pyramid.py:158,172).  All calls on one handle must come from one
+ * thread at a time (the reference host calls its stack_algo synchronously, stack.py:29).
+ */
+#ifndef SHINESTACK_B200_H
+#define SHINESTACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ss_handle ss_handle;
+
+typedef enum ss_status {
+    SS_OK = 0,
+    SS_ERR_INVALID_OPTION = -1, /* reference: InvalidOptionError (base_stack_algo.py:18-22)          */
+    SS_ERR_SHAPE = -2,          /* reference: ShapeError (utils.py:60-61)                            */
+    SS_ERR_BIT_DEPTH = -3,      /* reference: BitDepthError (utils.py:62-63)                         */
+    SS_ERR_CUDA = -4,           /* CUDA runtime / driver failure (no reference equivalent)           */
+    SS_ERR_NO_DEVICE = -5,      /* no sm_100 device: the product never falls back to a CPU path      */
+    SS_ERR_STATE = -6,          /* call sequence violated (e.g. finish before any frame)             */
+    SS_ERR_NOMEM = -7,
+    SS_ERR_COMM = -8            /* multi-GPU exchange failure                                        */
+} ss_status;
+
+/* Constructor arguments of PyramidStack (reference pyramid.py:114-123) + the frame geometry that the
+ * reference derives from the first file (pyramid.py:158-165) + placement. */
+typedef struct ss_config {
+    int32_t width;             /* W, pixels                                                         */
+    int32_t height;            /* H, pixels                                                         */
+    int32_t bytes_per_sample;  /* 1 (uint8) or 2 (uint16)                                           */
+    int32_t min_size;          /* PyramidStack(min_size=32): levels = int(log2(min(H,W)/min_size))  */
+    int32_t kernel_size;       /* PyramidStack(kernel_size=5): base-level entropy/variance window   */
+    double gen_kernel;         /* PyramidStack(gen_kernel=0.4): Burt-Adelson 'a'                    */
+    int32_t float_bits;        /* PyramidStack(float_type): 32 ('float-32'); 64 is rejected         */
+    int32_t device;            /* CUDA device ordinal                                               */
+    int32_t max_frames;        /* capacity of the device-resident frame store (>= frames pushed)    */
+    int32_t batch_frames;      /* frames fused per kernel-chain launch (0 = default)                */
+    int32_t frame_index_base;  /* global index of this handle's first frame (multi-GPU sharding)    */
+    int32_t resident_frames;   /* device frame slots (0 = 2*batch_frames ring; >= frames pushed keeps
+                                  the whole stack in HBM so that ss_rerun_resident can be used)       */
+    int32_t reserved[4];
+} ss_config;
+
+/* Library / build identification. */
+const char *ss_version(void);
+/* Thread-local description of the last error on this thread. */
+const char *ss_last_error(void);
+/* Number of CUDA devices with compute capability 10.x visible to the process (may be 0). */
+int ss_device_count(void);
+
+/* Replaces PyramidStack.__init__ + the first-file set-up in focus_stack (pyramid.py:114-123,158-165).
+ * Fails with SS_ERR_NO_DEVICE when no sm_100 GPU is present. */
+int ss_create(const ss_config *cfg, ss_handle **out);
+void ss_destroy(ss_handle *h);
+/* Forget all frames / running state so the same handle can fuse another stack of the same geometry
+ * (FocusStackBunch reuses one stack_algo for every bunch, stack.py:94-97). */
+int ss_reset(ss_handle *h);
+
+/* Geometry queries: number of Laplacian levels L actually built (pyramid.py:127-131,165) and the size
+ * of level l (0..L; L is the base level). */
+int ss_num_levels(const ss_handle *h);
+int ss_level_size(const ss_handle *h, int level, int32_t *height, int32_t *width);
+
+/* Pinned host staging memory for callers that want zero-copy-speed uploads (optional). */
+int ss_host_alloc(void **ptr, size_t bytes);
+int ss_host_free(void *ptr);
+
+/* Replaces one iteration of the second loop of focus_stack (pyramid.py:170-177: read_img +
+ * process_single_image): hands one host frame to the device.  The copy is asynchronous; the frame
+ * memory must stay valid until the next ss_sync/ss_finish_* call.  Frames must be pushed in stack
+ * order; when batch_frames frames are pending their kernel chain (pyramid build + energy + running
+ * arg-max select, pyramid.py:125-139 and :48-55) is launched behind the copy. */
+int ss_push_frame(ss_handle *h, const void *bgr, size_t row_pitch_bytes);
+/* Same, for a frame that already lives in device memory (device pointer, same layout). */
+int ss_push_frame_device(ss_handle *h, const void *d_bgr, size_t row_pitch_bytes);
+/* Block until all pushed work has completed. */
+int ss_sync(ss_handle *h);
+/* Block only until every pushed frame has reached the device (host buffers may then be reused). */
+int ss_sync_copies(ss_handle *h);
+
+/* Replaces fuse_pyramids' base step up to the histogram (pyramid.py:95-101,67): flushes pending frames,
+ * computes each frame's truncated gray base level and its histogram.  counts receives
+ * n_frames x num_values int64 entries (num_values = 256 or 65536); may be NULL. */
+int ss_finish_begin(ss_handle *h, int64_t *counts);
+/* Replaces get_fused_base + collapse + astype (pyramid.py:102-111,57-64,179).  log_prob is the table
+ * np.log(probabilities) of PyramidBase.entropy (pyramid.py:68-77), n_frames x num_values float32,
+ * computed by the host with numpy so that it is bit-identical to the reference; NULL makes the library
+ * compute it with C logf (documented last-ulp differences versus numpy).  out_bgr receives the fused
+ * H x W x 3 image in the input sample type. */
+int ss_finish_end(ss_handle *h, const float *log_prob, void *out_bgr, size_t out_row_pitch_bytes);
+/* Convenience: ss_finish_begin + ss_finish_end(log_prob = NULL). */
+int ss_finish(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
+
+/* The integer depth maps (np.argmax results, pyramid.py:51 and :104-105; not returned by the reference
+ * API but named by the north-star): level 0..L-1 = per-level Laplacian arg-max; level L = base-level
+ * entropy arg-max; level L+1 = base-level deviation arg-max.  int32 frame indices (global, i.e.
+ * including frame_index_base), height x width of that level, written to host memory. */
+int ss_get_argmax(ss_handle *h, int level, int32_t *out);
+/* Fused Laplacian level l (l < L) or fused base (l == L) as H_l x W_l x 3 float32 BGR (tests). */
+int ss_get_fused_level(ss_handle *h, int level, float *out);
+
+/* Device-side time of the kernel chain in milliseconds, measured with CUDA events on the library's
+ * compute stream: accumulated since the last ss_reset (all batches + finish). */
+int ss_kernel_time_ms(ss_handle *h, float *ms);
+/* Optional per-launch CUDA-event timing of the fused level kernels: enable, run, then read the summed
+ * device time and launch count of one level's kernel (bench.py's roofline figure). */
+int ss_set_profiling(ss_handle *h, int on);
+int ss_level_kernel_time_ms(ss_handle *h, int level, float *total_ms, int32_t *launches);
+/* Number of kernel launches since the last ss_reset. */
+int ss_launch_count(ss_handle *h, int64_t *launches);
+
+/* ---- multi-GPU exchange (frames of one stack sharded over ranks) ------------
+ * After ss_finish_begin on every rank, the per-level running state (energy, global frame index,
+ * winning coefficients) and the base-level planes are merged so that the root rank holds the state
+ * of the whole stack.  The library exposes the packed device buffers; the caller runs the collective
+ * (NCCL through torch.distributed in bench.py) and then calls ss_finish_end on the root. */
+/* Packs (energy_bits << 32 | ~global_index) keys for every level into one device buffer; returns its
+ * device address and element count. */
+int ss_exchange_keys(ss_handle *h, uint64_t **d_keys, size_t *count);
+/* After the keys were max-reduced across ranks: zero every coefficient this rank did not win and
+ * return the packed float32 coefficient buffer (device address, element count) for a sum-reduce. */
+int ss_exchange_mask_losers(ss_handle *h, float **d_coeffs, size_t *count);
+/* On the root after both reductions: unpack winners' indices from the reduced keys. */
+int ss_exchange_adopt(ss_handle *h);
+
+/* Re-run the kernel chain over the frames still resident in HBM (requires resident_frames >= frames
+ * pushed).  Used by bench.py for the "inputs already in HBM" throughput. */
+int ss_rerun_resident(ss_handle *h);
+/* The two halves of ss_finish_end, separately callable so that a multi-GPU exchange can run between
+ * them: base-level entropy/deviation arg-max on this rank's frames; then base blend + collapse +
+ * conversion + download. */
+int ss_finish_select_base(ss_handle *h, const float *log_prob);
+int ss_finish_collapse(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
+/* Time of the i-th timed segment (one per launched batch, then histogram, base select, collapse). */
+int ss_segment_time_ms(ss_handle *h, int i, float *ms);
+
+/* ---- test hooks: host arrays out of / through the product kernels, each checked against the
+ * reference method it replaces ------------------------------------------------------------------- */
+/* Running best energy of level l (after a 1-frame stack: convolve(square(gray(lap))), reference
+ * pyramid.py:49-50), H_l x W_l float32. */
+int ss_get_best_energy(ss_handle *h, int level, float *out);
+/* g_level of one frame as 3 float32 planes (PyramidBase.reduce_layer, pyramid.py:27-32): for
+ * level < L the frame index counts within the most recent batch, for level == L it is absolute. */
+int ss_get_gauss_level(ss_handle *h, int level, int frame, float *out_planes);
+/* One collapse step through the product's collapse kernel (reference pyramid.py:59-63, i.e.
+ * expand_layer pyramid.py:34-41 cropped, + layer): planes in, planes out; layer may be NULL (pure
+ * expand). */
+int ss_test_collapse_step(const float *img_planes, int h2, int w2, const float *layer_planes, int h,
+                          int w, double gen_kernel, float *out_planes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHINESTACK_B200_H */

@@ -251,7 +251,7 @@ SO_API void so_base_gray(const float *b, const float *g, const float *r, size_t 
 SO_API void so_entropy_map(const int32_t *gray, int h, int w, int ksize, const float *log_p,
                            float *out)
 {
-    const int pad = (ksize - 1) / 2, n = ksize * ksize;
+    const int pad = (ksize - 1) / 2, side = 2 * pad + 1, n = side * side;  /* len(arange(-pad, pad+1)), pyramid.py:18,120 */
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < h; ++y) {
         float buf[1024];
@@ -271,7 +271,7 @@ SO_API void so_entropy_map(const int32_t *gray, int h, int w, int ksize, const f
  * pairwise_sum( (f32(v) - mean)^2 ) / f32(n). */
 SO_API void so_deviation_map(const int32_t *gray, int h, int w, int ksize, float *out)
 {
-    const int pad = (ksize - 1) / 2, n = ksize * ksize;
+    const int pad = (ksize - 1) / 2, side = 2 * pad + 1, n = side * side;  /* len(arange(-pad, pad+1)), pyramid.py:18,120 */
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < h; ++y) {
         float buf[1024];

@@ -1,0 +1,15 @@
+"""shinestacker_b200 -- B200-native (sm_100a CUDA) focus-stacking core.
+
+Drop-in ``stack_algo`` for lucalista/shinestacker's ``FocusStack`` / ``FocusStackBunch``
+(reference src/shinestacker/algorithms/stack.py:14-113):
+
+    from shinestacker import StackJob, FocusStack
+    from shinestacker_b200 import PyramidStack          # instead of shinestacker's PyramidStack
+    job.add_action(FocusStack("stack", PyramidStack(), ...))
+"""
+from .pyramid import PyramidStack, PyramidBase  # noqa: F401
+from .exceptions import (FocusStackError, InvalidOptionError, ImageLoadError, BitDepthError,  # noqa: F401
+                         ShapeError, RunStopException, NativeLibraryError)
+
+__all__ = ["PyramidStack", "PyramidBase", "FocusStackError", "InvalidOptionError", "ImageLoadError",
+           "BitDepthError", "ShapeError", "RunStopException", "NativeLibraryError"]

@@ -1,0 +1,110 @@
+"""ctypes binding of libshinestack_b200.so (C ABI: include/shinestack_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``python -m shinestacker_b200.build``.
+If it is missing or cannot be loaded the import of this module raises: there is no CPU fallback.
+"""
+import ctypes
+import os
+
+from .exceptions import NativeLibraryError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshinestack_b200.so")
+
+
+class SsConfig(ctypes.Structure):
+    """struct ss_config (include/shinestack_b200.h)."""
+    _fields_ = [
+        ("width", ctypes.c_int32),
+        ("height", ctypes.c_int32),
+        ("bytes_per_sample", ctypes.c_int32),
+        ("min_size", ctypes.c_int32),
+        ("kernel_size", ctypes.c_int32),
+        ("gen_kernel", ctypes.c_double),
+        ("float_bits", ctypes.c_int32),
+        ("device", ctypes.c_int32),
+        ("max_frames", ctypes.c_int32),
+        ("batch_frames", ctypes.c_int32),
+        ("frame_index_base", ctypes.c_int32),
+        ("resident_frames", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 4),
+    ]
+
+
+SS_OK = 0
+SS_ERR_INVALID_OPTION = -1
+SS_ERR_SHAPE = -2
+SS_ERR_BIT_DEPTH = -3
+SS_ERR_CUDA = -4
+SS_ERR_NO_DEVICE = -5
+SS_ERR_STATE = -6
+SS_ERR_NOMEM = -7
+SS_ERR_COMM = -8
+
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_i = ctypes.c_int
+
+# name -> (restype, argtypes); every symbol declared in include/shinestack_b200.h
+SIGNATURES = {
+    "ss_version": (ctypes.c_char_p, []),
+    "ss_last_error": (ctypes.c_char_p, []),
+    "ss_device_count": (_i, []),
+    "ss_create": (_i, [ctypes.POINTER(SsConfig), ctypes.POINTER(_vp)]),
+    "ss_destroy": (None, [_vp]),
+    "ss_reset": (_i, [_vp]),
+    "ss_num_levels": (_i, [_vp]),
+    "ss_level_size": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "ss_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "ss_host_free": (_i, [_vp]),
+    "ss_push_frame": (_i, [_vp, _vp, _sz]),
+    "ss_push_frame_device": (_i, [_vp, _vp, _sz]),
+    "ss_sync": (_i, [_vp]),
+    "ss_sync_copies": (_i, [_vp]),
+    "ss_finish_begin": (_i, [_vp, _vp]),
+    "ss_finish_end": (_i, [_vp, _vp, _vp, _sz]),
+    "ss_finish": (_i, [_vp, _vp, _sz]),
+    "ss_get_argmax": (_i, [_vp, _i, _vp]),
+    "ss_get_fused_level": (_i, [_vp, _i, _vp]),
+    "ss_kernel_time_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "ss_set_profiling": (_i, [_vp, _i]),
+    "ss_level_kernel_time_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)]),
+    "ss_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),
+    "ss_exchange_keys": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    "ss_exchange_mask_losers": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    "ss_exchange_adopt": (_i, [_vp]),
+    "ss_rerun_resident": (_i, [_vp]),
+    "ss_finish_select_base": (_i, [_vp, _vp]),
+    "ss_finish_collapse": (_i, [_vp, _vp, _sz]),
+    "ss_segment_time_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float)]),
+    "ss_get_best_energy": (_i, [_vp, _i, _vp]),
+    "ss_get_gauss_level": (_i, [_vp, _i, _i, _vp]),
+    "ss_test_collapse_step": (_i, [_vp, _i, _i, _vp, _i, _i, ctypes.c_double, _vp]),
+}
+
+_LIB = None
+
+
+def load():
+    """Load the shared library (once) and declare every prototype.  Raises NativeLibraryError."""
+    global _LIB  # pylint: disable=global-statement
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  shinestacker_b200 has no CPU fallback.")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:
+        raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def last_error():
+    return load().ss_last_error().decode("utf-8", "replace")

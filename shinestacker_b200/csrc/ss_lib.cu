@@ -1,0 +1,1075 @@
+// ss_lib.cu -- libshinestack_b200.so: C ABI (include/shinestack_b200.h) + kernel launches.
+// sm_100a only; no CPU fallback: every entry point that computes needs a compute-capability-10 GPU.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/shinestack_b200.h"
+#include "ss_kernels.cuh"
+
+#define SS_EXPORT extern "C" __attribute__((visibility("default")))
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int ss_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SS_CUDA(call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return ss_fail(SS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                           __FILE__, __LINE__);                                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void __launch_bounds__(SS_NT) ss_level_kernel(const __grid_constant__ SsLevelParams p)
+{
+    extern __shared__ float ss_smem[];
+    ss_level_tile<InT>(p, blockIdx.x, blockIdx.y, ss_smem);
+}
+
+// img.astype(float32) (reference pyramid.py:126) into planes; only needed when the pyramid has no
+// Laplacian level at all (image smaller than 2*min_size) and the input itself is the base level.
+template <typename InT>
+__global__ void ss_convert_kernel(const InT *in, int pitch_bytes, int h, int w, float *out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const InT *s = (const InT *)((const char *)in + (size_t)y * pitch_bytes) + 3 * x;
+    const size_t plane = (size_t)h * w, o = (size_t)y * w + x;
+    out[o] = (float)s[0];
+    out[plane + o] = (float)s[1];
+    out[2 * plane + o] = (float)s[2];
+}
+
+// Base level, step 1 (reference pyramid.py:99-101 and :67): gray = cvtColor(base).astype(dtype) by
+// truncation, plus the per-frame histogram that PyramidBase.entropy obtains from np.unique.
+__global__ void ss_base_gray_hist_kernel(const float *base, int n_px, int32_t *gray,
+                                         unsigned int *counts, int num_values)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    const float *b = base + (size_t)f * 3 * n_px;
+    const float v = __fmaf_rn(b[2 * (size_t)n_px + i], 0.299f,
+                              __fmaf_rn(b[i], 0.114f, __fmul_rn(b[(size_t)n_px + i], 0.587f)));
+    int gv = (int)v;  // C truncation, as ndarray.astype
+    gv = gv < 0 ? 0 : (gv >= num_values ? num_values - 1 : gv);
+    gray[(size_t)f * n_px + i] = gv;
+    atomicAdd(&counts[(size_t)f * num_values + gv], 1u);
+}
+
+// numpy's float32 pairwise add.reduce for n <= 128 contiguous values (reference: ndarray.sum() at
+// pyramid.py:77 and :85).
+__device__ float ss_np_pairwise_sum(const float *a, int n)
+{
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    float r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+}
+
+#define SS_MAX_WINDOW 11
+
+// Base level, step 2 (reference pyramid.py:66-93,102-105): per pixel and frame the window entropy
+// -sum(v*log p[v]) and variance, running strict-'>' arg-max of each over the frames, and the base
+// pixels of the two winners.
+__global__ void ss_base_select_kernel(const int32_t *gray, const float *log_p, const float *base,
+                                      int h, int w, int n_frames, int num_values, int side,
+                                      int frame_index0, float *best_ve, int32_t *best_ie,
+                                      float *best_vd, int32_t *best_id, float *pix_e, float *pix_d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_px = h * w;
+    if (i >= n_px) return;
+    const int y = i / w, x = i - y * w;
+    const int pad = (side - 1) / 2, n = side * side;
+    float buf[SS_MAX_WINDOW * SS_MAX_WINDOW];
+    int vals[SS_MAX_WINDOW * SS_MAX_WINDOW];
+    float ve = 0.f, vd = 0.f;
+    int ie = 0, id = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        const int32_t *g = gray + (size_t)f * n_px;
+        const float *lp = log_p + (size_t)f * num_values;
+        int c = 0;
+        long long s = 0;
+        for (int dy = -pad; dy <= pad; ++dy) {
+            int yy = y + dy;
+            while (yy < 0 || yy >= h) yy = yy < 0 ? -yy : 2 * h - 2 - yy;
+            for (int dx = -pad; dx <= pad; ++dx) {
+                int xx = x + dx;
+                while (xx < 0 || xx >= w) xx = xx < 0 ? -xx : 2 * w - 2 - xx;
+                const int v = g[yy * w + xx];
+                vals[c] = v;
+                buf[c] = __fmul_rn((float)v, lp[v]);
+                s += v;
+                ++c;
+            }
+        }
+        const float ent = __fmul_rn(-1.f, ss_np_pairwise_sum(buf, n));
+        const float mean = (float)((double)s / (double)n);
+        for (int k = 0; k < n; ++k) {
+            const float d = __fsub_rn((float)vals[k], mean);
+            buf[k] = __fmul_rn(d, d);
+        }
+        const float dev = __fdiv_rn(ss_np_pairwise_sum(buf, n), (float)n);
+        if (f == 0 || ent > ve) { ve = ent; ie = f; }
+        if (f == 0 || dev > vd) { vd = dev; id = f; }
+    }
+    best_ve[i] = ve; best_ie[i] = frame_index0 + ie;
+    best_vd[i] = vd; best_id[i] = frame_index0 + id;
+    for (int ch = 0; ch < 3; ++ch) {
+        pix_e[(size_t)ch * n_px + i] = base[((size_t)ie * 3 + ch) * n_px + i];
+        pix_d[(size_t)ch * n_px + i] = base[((size_t)id * 3 + ch) * n_px + i];
+    }
+}
+
+// get_fused_base's blend (reference pyramid.py:106-111): ((0 + base[best_e]) + base[best_d]) / 2.
+__global__ void ss_base_fuse_kernel(const float *pix_e, const float *pix_d, size_t n, float *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = __fdiv_rn(__fadd_rn(__fadd_rn(0.f, pix_e[i]), pix_d[i]), 2.f);
+}
+
+struct SsCollapseParams {
+    const float *img;    // level l+1 image, 3 planes h2 x w2
+    const float *layer;  // fused Laplacian of level l, 3 planes h x w (may be null: expand only)
+    float *out;          // 3 planes h x w (when !final)
+    void *out_px;        // final: interleaved uint8/uint16 H x W x 3
+    int out_pitch;       // bytes
+    int h, w, h2, w2;
+    int final_bytes;     // 0: not final; 1 / 2: clip(abs()) and truncate to uint8 / uint16
+    float k25[25];
+};
+
+// One collapse step (reference pyramid.py:59-64): img = expand(img)[:h,:w] + layer, the expand being
+// the zero-skipping form of expand_layer (pyramid.py:34-41); the last step also applies
+// clip(abs(img), 0, max) and the truncating cast of pyramid.py:179.
+__global__ void __launch_bounds__(256) ss_collapse_kernel(const __grid_constant__ SsCollapseParams p)
+{
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= p.w || y >= p.h) return;
+    const int wz = 2 * p.w2, hz = 2 * p.h2, wz_vec = wz - (wz % 8);
+    const bool tail = x >= wz_vec;
+    float v[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float *g = p.img + (size_t)ch * p.h2 * p.w2;
+        float acc = 0.f;
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy) {
+            int zy = y + dy;
+            if (zy < 0) zy = -zy;
+            if (zy >= hz) zy = 2 * hz - 2 - zy;
+            if (zy & 1) continue;
+            const float *row = g + (size_t)(zy >> 1) * p.w2;
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                int zx = x + dx;
+                if (zx < 0) zx = -zx;
+                if (zx >= wz) zx = 2 * wz - 2 - zx;
+                if (zx & 1) continue;
+                const float t = row[zx >> 1], k = p.k25[(dy + 2) * 5 + dx + 2];
+                acc = tail ? __fadd_rn(acc, __fmul_rn(t, k)) : __fmaf_rn(t, k, acc);
+            }
+        }
+        float e = __fmul_rn(4.f, acc);
+        if (p.layer) e = __fadd_rn(e, p.layer[((size_t)ch * p.h + y) * p.w + x]);
+        v[ch] = e;
+    }
+    if (!p.final_bytes) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) p.out[((size_t)ch * p.h + y) * p.w + x] = v[ch];
+    } else {
+        const float maxv = p.final_bytes == 1 ? 255.f : 65535.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float a = fabsf(v[ch]);
+            a = a > maxv ? maxv : a;   // abs() is never negative; NaN cannot occur
+            const unsigned int u = __float2uint_rz(a);
+            if (p.final_bytes == 1) ((uint8_t *)((char *)p.out_px + (size_t)y * p.out_pitch))[3 * x + ch] = (uint8_t)u;
+            else ((uint16_t *)((char *)p.out_px + (size_t)y * p.out_pitch))[3 * x + ch] = (uint16_t)u;
+        }
+    }
+}
+
+// clip(abs()) + cast of a planar image without any expand (pyramid with no Laplacian level).
+__global__ void ss_finalize_kernel(const float *img, int h, int w, int bytes, void *out, int pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const float maxv = bytes == 1 ? 255.f : 65535.f;
+    for (int ch = 0; ch < 3; ++ch) {
+        float a = fabsf(img[((size_t)ch * h + y) * w + x]);
+        a = a > maxv ? maxv : a;
+        const unsigned int u = __float2uint_rz(a);
+        if (bytes == 1) ((uint8_t *)((char *)out + (size_t)y * pitch))[3 * x + ch] = (uint8_t)u;
+        else ((uint16_t *)((char *)out + (size_t)y * pitch))[3 * x + ch] = (uint16_t)u;
+    }
+}
+
+// ---- multi-GPU exchange helpers ---------------------------------------------
+// key = (float bits of the non-negative value, canonical +0) << 32 | (0xFFFFFFFF - global frame index):
+// unsigned max over ranks == "largest value, ties to the lowest global frame index" == np.argmax.
+__global__ void ss_pack_keys_kernel(const float *val, const int32_t *idx, size_t n,
+                                    unsigned long long *keys)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = val[i];
+    if (v == 0.f) v = 0.f;  // -0 -> +0
+    keys[i] = ((unsigned long long)__float_as_uint(v) << 32) |
+              (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx[i]);
+}
+
+// After the max-reduction: adopt the winning (value, index); zero this rank's coefficients where it
+// lost, so that a float32 sum over ranks reproduces the winner exactly (x + 0 + ... + 0).
+__global__ void ss_adopt_keys_kernel(const unsigned long long *keys, size_t n, int planes,
+                                     float *val, int32_t *idx, float *coeff)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    const int win = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull));
+    const bool mine = (win == idx[i]);
+    val[i] = __uint_as_float((unsigned int)(k >> 32));
+    idx[i] = win;
+    if (!mine)
+        for (int c = 0; c < planes; ++c) coeff[(size_t)c * n + i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------
+struct SsLevel {
+    int h, w;
+    float *best_e = nullptr;
+    int32_t *best_idx = nullptr;
+    float *fused = nullptr;  // 3 planes
+    float *gnext = nullptr;  // scratch: g_{l+1} of the frames of one batch (unused for the last level)
+};
+
+struct ss_handle {
+    ss_config cfg;
+    int L = 0;                       // number of Laplacian levels
+    std::vector<int> lh, lw;         // sizes of levels 0..L
+    std::vector<SsLevel> lv;         // 0..L-1
+    float k25[25];
+    int side = 5;                    // base window side
+    int num_values = 256;
+    // frame store (ring of n_slots device frames)
+    char *frames = nullptr;
+    size_t frame_pitch = 0, frame_bytes = 0;
+    int n_slots = 0, batch = 0;
+    // base level
+    float *base = nullptr;           // max_frames x 3 x hL x wL
+    int32_t *gray = nullptr;         // max_frames x hL x wL
+    unsigned int *counts = nullptr;  // max_frames x num_values
+    float *log_p = nullptr;          // max_frames x num_values
+    float *best_ve = nullptr, *best_vd = nullptr, *pix_e = nullptr, *pix_d = nullptr;
+    int32_t *best_ie = nullptr, *best_id = nullptr;
+    float *fused_base = nullptr;     // 3 x hL x wL
+    float *tmp_a = nullptr, *tmp_b = nullptr;  // collapse ping-pong, 3 x H x W / 4 each... see alloc
+    void *out_dev = nullptr;         // interleaved output image
+    size_t out_pitch = 0;
+    unsigned long long *keys = nullptr;  // exchange buffer
+    float *coeffs = nullptr;             // exchange buffer (packed coefficients)
+    size_t n_keys = 0, n_coeffs = 0;
+    // streams / events
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    std::vector<cudaEvent_t> ev_copied, ev_done;  // per batch slot
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;
+    size_t timers_used = 0;
+    bool profile = false;            // per-launch events around every level kernel
+    struct LevelTimer { int level; cudaEvent_t a, b; };
+    std::vector<LevelTimer> ltimers;
+    size_t ltimers_used = 0;
+    // progress
+    int n_pushed = 0;      // frames handed over
+    int n_launched = 0;    // frames whose level chain has been launched
+    bool finished_begin = false;
+    bool have_state = false;
+    long long launches = 0;
+};
+
+static int ss_levels_for(int h, int w, int min_size, std::vector<int> &lh, std::vector<int> &lw)
+{
+    // reference pyramid.py:165 and :127-131
+    lh.assign(1, h);
+    lw.assign(1, w);
+    const double ratio = (double)(h < w ? h : w) / (double)min_size;
+    int levels = ratio > 0 ? (int)log2(ratio) : 0;  // int() truncates toward zero
+    if (levels < 0) levels = 0;
+    for (int i = 0; i < levels; ++i) {
+        const int nh = (lh.back() + 1) / 2, nw = (lw.back() + 1) / 2;
+        if ((nh < nw ? nh : nw) < 4) break;
+        lh.push_back(nh);
+        lw.push_back(nw);
+    }
+    return (int)lh.size() - 1;
+}
+
+static void ss_make_kernel(double a, float *k25)
+{
+    // reference pyramid.py:19-22 (float64 outer product, converted to float32 by cv2.filter2D)
+    const double k[5] = {0.25 - a / 2.0, 0.25, a, 0.25, 0.25 - a / 2.0};
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 5; ++j) k25[i * 5 + j] = (float)(k[i] * k[j]);
+}
+
+static int ss_timer_begin(ss_handle *h)
+{
+    if (h->timers_used == h->timers.size()) {
+        cudaEvent_t a, b;
+        SS_CUDA(cudaEventCreate(&a));
+        SS_CUDA(cudaEventCreate(&b));
+        h->timers.push_back({a, b});
+    }
+    SS_CUDA(cudaEventRecord(h->timers[h->timers_used].first, h->s_comp));
+    return 0;
+}
+static int ss_timer_end(ss_handle *h)
+{
+    SS_CUDA(cudaEventRecord(h->timers[h->timers_used].second, h->s_comp));
+    h->timers_used++;
+    return 0;
+}
+
+SS_EXPORT const char *ss_version(void) { return "shinestack_b200 0.1 (sm_100a)"; }
+SS_EXPORT const char *ss_last_error(void) { return g_err; }
+
+SS_EXPORT int ss_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess &&
+            major == 10)
+            ++ok;
+    }
+    return ok;
+}
+
+template <typename T>
+static int ss_dalloc(T **p, size_t count)
+{
+    SS_CUDA(cudaMalloc((void **)p, count * sizeof(T) + 16));
+    return 0;
+}
+
+SS_EXPORT void ss_destroy(ss_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->s_comp) cudaStreamSynchronize(h->s_comp);
+    if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+    for (auto &l : h->lv) {
+        cudaFree(l.best_e); cudaFree(l.best_idx); cudaFree(l.fused); cudaFree(l.gnext);
+    }
+    cudaFree(h->frames); cudaFree(h->base); cudaFree(h->gray); cudaFree(h->counts);
+    cudaFree(h->log_p); cudaFree(h->best_ve); cudaFree(h->best_vd); cudaFree(h->pix_e);
+    cudaFree(h->pix_d); cudaFree(h->best_ie); cudaFree(h->best_id); cudaFree(h->fused_base);
+    cudaFree(h->tmp_a); cudaFree(h->tmp_b); cudaFree(h->out_dev); cudaFree(h->keys);
+    cudaFree(h->coeffs);
+    for (auto e : h->ev_copied) cudaEventDestroy(e);
+    for (auto e : h->ev_done) cudaEventDestroy(e);
+    for (auto &t : h->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
+    for (auto &t : h->ltimers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    delete h;
+}
+
+static int ss_create_impl(const ss_config *cfg, ss_handle *h)
+{
+    h->cfg = *cfg;
+    SS_CUDA(cudaSetDevice(cfg->device));
+    int major = 0;
+    SS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+    if (major != 10)
+        return ss_fail(SS_ERR_NO_DEVICE, "device %d has compute capability %d.x; this library is "
+                       "built for sm_100a only and has no fallback path", cfg->device, major);
+    h->L = ss_levels_for(cfg->height, cfg->width, cfg->min_size, h->lh, h->lw);
+    ss_make_kernel(cfg->gen_kernel, h->k25);
+    h->side = 2 * ((cfg->kernel_size - 1) / 2) + 1;  // len(arange(-pad, pad+1)), pyramid.py:18,120
+    h->num_values = cfg->bytes_per_sample == 1 ? 256 : 65536;
+    h->batch = cfg->batch_frames > 0 ? cfg->batch_frames : 8;
+    if (h->batch > cfg->max_frames) h->batch = cfg->max_frames;
+    // frame ring: all frames resident when they fit the request, else two batches
+    h->n_slots = cfg->resident_frames > 0 ? cfg->resident_frames : 2 * h->batch;
+    if (h->n_slots < h->batch) h->n_slots = h->batch;
+    h->n_slots = (h->n_slots + h->batch - 1) / h->batch * h->batch;
+    h->frame_pitch = ((size_t)cfg->width * 3 * cfg->bytes_per_sample + 15) / 16 * 16;
+    h->frame_bytes = h->frame_pitch * cfg->height;
+    SS_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    SS_CUDA(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    const int n_bslots = h->n_slots / h->batch;
+    h->ev_copied.resize(n_bslots);
+    h->ev_done.resize(n_bslots);
+    for (int i = 0; i < n_bslots; ++i) {
+        SS_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+        SS_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    int rc;
+    if ((rc = ss_dalloc(&h->frames, h->frame_bytes * h->n_slots))) return rc;
+    h->lv.resize(h->L);
+    h->n_keys = 0;
+    for (int l = 0; l < h->L; ++l) {
+        SsLevel &v = h->lv[l];
+        v.h = h->lh[l]; v.w = h->lw[l];
+        const size_t n = (size_t)v.h * v.w;
+        if ((rc = ss_dalloc(&v.best_e, n))) return rc;
+        if ((rc = ss_dalloc(&v.best_idx, n))) return rc;
+        if ((rc = ss_dalloc(&v.fused, 3 * n))) return rc;
+        if (l + 1 < h->L)
+            if ((rc = ss_dalloc(&v.gnext, (size_t)h->batch * 3 * h->lh[l + 1] * h->lw[l + 1]))) return rc;
+        h->n_keys += n;
+    }
+    const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
+    h->n_coeffs = 3 * h->n_keys + 6 * nb;
+    h->n_keys += 2 * nb;
+    if ((rc = ss_dalloc(&h->base, (size_t)cfg->max_frames * 3 * nb))) return rc;
+    if ((rc = ss_dalloc(&h->gray, (size_t)cfg->max_frames * nb))) return rc;
+    if ((rc = ss_dalloc(&h->counts, (size_t)cfg->max_frames * h->num_values))) return rc;
+    if ((rc = ss_dalloc(&h->log_p, (size_t)cfg->max_frames * h->num_values))) return rc;
+    if ((rc = ss_dalloc(&h->best_ve, nb))) return rc;
+    if ((rc = ss_dalloc(&h->best_vd, nb))) return rc;
+    if ((rc = ss_dalloc(&h->best_ie, nb))) return rc;
+    if ((rc = ss_dalloc(&h->best_id, nb))) return rc;
+    if ((rc = ss_dalloc(&h->pix_e, 3 * nb))) return rc;
+    if ((rc = ss_dalloc(&h->pix_d, 3 * nb))) return rc;
+    if ((rc = ss_dalloc(&h->fused_base, 3 * nb))) return rc;
+    if (h->L >= 2) {
+        // collapse intermediates: the largest one is level 1
+        const size_t n1 = 3 * (size_t)h->lh[1] * h->lw[1];
+        if ((rc = ss_dalloc(&h->tmp_a, n1))) return rc;
+        if ((rc = ss_dalloc(&h->tmp_b, n1))) return rc;
+    }
+    h->out_pitch = (size_t)cfg->width * 3 * cfg->bytes_per_sample;
+    if ((rc = ss_dalloc((char **)&h->out_dev, h->out_pitch * cfg->height))) return rc;
+    SS_CUDA(cudaFuncSetAttribute(ss_level_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(SS_SMEM_FLOATS * sizeof(float))));
+    SS_CUDA(cudaFuncSetAttribute(ss_level_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(SS_SMEM_FLOATS * sizeof(float))));
+    SS_CUDA(cudaFuncSetAttribute(ss_level_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(SS_SMEM_FLOATS * sizeof(float))));
+    return 0;
+}
+
+SS_EXPORT int ss_create(const ss_config *cfg, ss_handle **out)
+{
+    if (!cfg || !out) return ss_fail(SS_ERR_INVALID_OPTION, "null argument");
+    *out = nullptr;
+    if (cfg->float_bits != 32)
+        return ss_fail(SS_ERR_INVALID_OPTION, "float_type: only float-32 is implemented on the GPU "
+                       "path (got %d bits)", cfg->float_bits);
+    if (cfg->bytes_per_sample != 1 && cfg->bytes_per_sample != 2)
+        return ss_fail(SS_ERR_BIT_DEPTH, "bytes_per_sample must be 1 or 2 (got %d)", cfg->bytes_per_sample);
+    if (cfg->width < 4 || cfg->height < 4)
+        return ss_fail(SS_ERR_SHAPE, "image %dx%d too small", cfg->width, cfg->height);
+    if (cfg->min_size < 1) return ss_fail(SS_ERR_INVALID_OPTION, "min_size must be >= 1");
+    if (cfg->kernel_size < 1 || 2 * ((cfg->kernel_size - 1) / 2) + 1 > SS_MAX_WINDOW)
+        return ss_fail(SS_ERR_INVALID_OPTION, "kernel_size must be in 1..%d", SS_MAX_WINDOW + 1);
+    if (cfg->max_frames < 1) return ss_fail(SS_ERR_INVALID_OPTION, "max_frames must be >= 1");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return ss_fail(SS_ERR_NO_DEVICE, "no CUDA device visible; libshinestack_b200 has no CPU "
+                       "fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= n)
+        return ss_fail(SS_ERR_NO_DEVICE, "device %d out of range (%d visible)", cfg->device, n);
+    ss_handle *h = new (std::nothrow) ss_handle();
+    if (!h) return ss_fail(SS_ERR_NOMEM, "out of host memory");
+    const int rc = ss_create_impl(cfg, h);
+    if (rc) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        ss_destroy(h);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+SS_EXPORT int ss_reset(ss_handle *h)
+{
+    if (!h) return ss_fail(SS_ERR_STATE, "null handle");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaStreamSynchronize(h->s_copy));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    h->n_pushed = h->n_launched = 0;
+    h->finished_begin = false;
+    h->have_state = false;
+    h->timers_used = 0;
+    h->ltimers_used = 0;
+    h->launches = 0;
+    return 0;
+}
+
+SS_EXPORT int ss_num_levels(const ss_handle *h) { return h ? h->L : SS_ERR_STATE; }
+
+SS_EXPORT int ss_level_size(const ss_handle *h, int level, int32_t *height, int32_t *width)
+{
+    if (!h || level < 0 || level > h->L) return ss_fail(SS_ERR_STATE, "bad level %d", level);
+    if (height) *height = h->lh[level];
+    if (width) *width = h->lw[level];
+    return 0;
+}
+
+SS_EXPORT int ss_host_alloc(void **ptr, size_t bytes)
+{
+    SS_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return 0;
+}
+SS_EXPORT int ss_host_free(void *ptr)
+{
+    SS_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
+// Launch the per-level kernel chain for frames [f0, f1) (all inside one batch slot).
+static int ss_launch_batch(ss_handle *h, int f0, int f1)
+{
+    const int nf = f1 - f0;
+    const int slot0 = f0 % h->n_slots;
+    const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
+    int rc;
+    if ((rc = ss_timer_begin(h))) return rc;
+    if (h->L == 0) {
+        for (int f = f0; f < f1; ++f) {
+            const char *src = h->frames + (size_t)(f % h->n_slots) * h->frame_bytes;
+            dim3 g((h->cfg.width + 255) / 256, h->cfg.height);
+            if (h->cfg.bytes_per_sample == 1)
+                ss_convert_kernel<uint8_t><<<g, 256, 0, h->s_comp>>>((const uint8_t *)src, (int)h->frame_pitch,
+                    h->cfg.height, h->cfg.width, h->base + (size_t)f * 3 * nb);
+            else
+                ss_convert_kernel<uint16_t><<<g, 256, 0, h->s_comp>>>((const uint16_t *)src, (int)h->frame_pitch,
+                    h->cfg.height, h->cfg.width, h->base + (size_t)f * 3 * nb);
+            h->launches++;
+        }
+    }
+    for (int l = 0; l < h->L; ++l) {
+        SsLevel &v = h->lv[l];
+        SsLevelParams p;
+        memset(&p, 0, sizeof(p));
+        p.h = v.h; p.w = v.w; p.h2 = h->lh[l + 1]; p.w2 = h->lw[l + 1];
+        if (l == 0) {
+            p.in = h->frames + (size_t)slot0 * h->frame_bytes;
+            p.in_frame_stride = (long long)h->frame_bytes;
+            p.in_pitch = (int)h->frame_pitch;
+        } else {
+            p.in = h->lv[l - 1].gnext;
+            p.in_pitch = v.w * 4;
+            p.in_plane_stride = (long long)v.h * v.w * 4;
+            p.in_frame_stride = 3 * p.in_plane_stride;
+        }
+        if (l + 1 < h->L) p.gnext = v.gnext;
+        else p.gnext = h->base + (size_t)f0 * 3 * nb;
+        p.gnext_pitch = p.w2;
+        p.gnext_plane_stride = (long long)p.h2 * p.w2;
+        p.gnext_frame_stride = 3 * p.gnext_plane_stride;
+        p.best_e = v.best_e; p.best_idx = v.best_idx; p.fused = v.fused;
+        p.n_frames = nf;
+        p.frame_index0 = h->cfg.frame_index_base + f0;
+        p.init = h->have_state ? 0 : 1;
+        memcpy(p.k25, h->k25, sizeof(p.k25));
+        dim3 grid((v.w + SS_TX - 1) / SS_TX, (v.h + SS_TY - 1) / SS_TY);
+        const size_t smem = SS_SMEM_FLOATS * sizeof(float);
+        if (h->profile) {
+            if (h->ltimers_used == h->ltimers.size()) {
+                ss_handle::LevelTimer t;
+                SS_CUDA(cudaEventCreate(&t.a));
+                SS_CUDA(cudaEventCreate(&t.b));
+                h->ltimers.push_back(t);
+            }
+            h->ltimers[h->ltimers_used].level = l;
+            SS_CUDA(cudaEventRecord(h->ltimers[h->ltimers_used].a, h->s_comp));
+        }
+        if (l == 0 && h->cfg.bytes_per_sample == 1)
+            ss_level_kernel<uint8_t><<<grid, SS_NT, smem, h->s_comp>>>(p);
+        else if (l == 0)
+            ss_level_kernel<uint16_t><<<grid, SS_NT, smem, h->s_comp>>>(p);
+        else
+            ss_level_kernel<float><<<grid, SS_NT, smem, h->s_comp>>>(p);
+        h->launches++;
+        if (h->profile) {
+            SS_CUDA(cudaEventRecord(h->ltimers[h->ltimers_used].b, h->s_comp));
+            h->ltimers_used++;
+        }
+    }
+    SS_CUDA(cudaGetLastError());
+    if ((rc = ss_timer_end(h))) return rc;
+    h->have_state = true;
+    return 0;
+}
+
+// Launch every complete batch (or, with flush, also the trailing partial one).
+static int ss_launch_pending(ss_handle *h, bool flush)
+{
+    while (h->n_launched < h->n_pushed) {
+        const int f0 = h->n_launched;
+        int f1 = f0 + h->batch - (f0 % h->batch);
+        if (f1 > h->n_pushed) {
+            if (!flush) break;
+            f1 = h->n_pushed;
+        }
+        const int bslot = (f0 % h->n_slots) / h->batch;
+        SS_CUDA(cudaEventRecord(h->ev_copied[bslot], h->s_copy));
+        SS_CUDA(cudaStreamWaitEvent(h->s_comp, h->ev_copied[bslot], 0));
+        const int rc = ss_launch_batch(h, f0, f1);
+        if (rc) return rc;
+        SS_CUDA(cudaEventRecord(h->ev_done[bslot], h->s_comp));
+        h->n_launched = f1;
+    }
+    return 0;
+}
+
+static int ss_push_impl(ss_handle *h, const void *src, size_t pitch, cudaMemcpyKind kind)
+{
+    if (!h || !src) return ss_fail(SS_ERR_STATE, "null argument");
+    if (h->finished_begin) return ss_fail(SS_ERR_STATE, "push after finish_begin; call ss_reset first");
+    if (h->n_pushed >= h->cfg.max_frames)
+        return ss_fail(SS_ERR_STATE, "more than max_frames=%d frames pushed", h->cfg.max_frames);
+    const size_t row = (size_t)h->cfg.width * 3 * h->cfg.bytes_per_sample;
+    if (pitch < row) return ss_fail(SS_ERR_SHAPE, "row pitch %zu smaller than a row (%zu bytes)", pitch, row);
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const int slot = h->n_pushed % h->n_slots;
+    if (h->n_pushed >= h->n_slots && slot % h->batch == 0) {
+        // the ring wraps: the batch that used these slots must have been consumed
+        SS_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_done[slot / h->batch], 0));
+    }
+    SS_CUDA(cudaMemcpy2DAsync(h->frames + (size_t)slot * h->frame_bytes, h->frame_pitch, src, pitch, row,
+                              h->cfg.height, kind, h->s_copy));
+    h->n_pushed++;
+    if (h->n_pushed % h->batch == 0) return ss_launch_pending(h, false);
+    return 0;
+}
+
+SS_EXPORT int ss_push_frame(ss_handle *h, const void *bgr, size_t row_pitch_bytes)
+{
+    return ss_push_impl(h, bgr, row_pitch_bytes, cudaMemcpyHostToDevice);
+}
+SS_EXPORT int ss_push_frame_device(ss_handle *h, const void *d_bgr, size_t row_pitch_bytes)
+{
+    return ss_push_impl(h, d_bgr, row_pitch_bytes, cudaMemcpyDeviceToDevice);
+}
+
+// Block until every pushed frame has reached the device (host staging buffers may be reused).
+SS_EXPORT int ss_sync_copies(ss_handle *h)
+{
+    if (!h) return ss_fail(SS_ERR_STATE, "null handle");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaStreamSynchronize(h->s_copy));
+    return 0;
+}
+
+SS_EXPORT int ss_sync(ss_handle *h)
+{
+    if (!h) return ss_fail(SS_ERR_STATE, "null handle");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaStreamSynchronize(h->s_copy));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    return 0;
+}
+
+// Re-run the kernel chain over the frames that are still resident in the ring (benchmarks: inputs
+// already in HBM).  Requires that no slot has been overwritten.
+SS_EXPORT int ss_rerun_resident(ss_handle *h)
+{
+    if (!h) return ss_fail(SS_ERR_STATE, "null handle");
+    if (h->n_pushed > h->n_slots)
+        return ss_fail(SS_ERR_STATE, "%d frames pushed but only %d resident slots", h->n_pushed, h->n_slots);
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaStreamSynchronize(h->s_copy));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    h->n_launched = 0;
+    h->finished_begin = false;
+    h->have_state = false;
+    h->timers_used = 0;
+    h->ltimers_used = 0;
+    h->launches = 0;
+    return ss_launch_pending(h, true);
+}
+
+SS_EXPORT int ss_finish_begin(ss_handle *h, int64_t *counts)
+{
+    if (!h) return ss_fail(SS_ERR_STATE, "null handle");
+    if (h->n_pushed == 0) return ss_fail(SS_ERR_STATE, "no frame pushed");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc;
+    if (!h->finished_begin) {
+        if ((rc = ss_launch_pending(h, true))) return rc;
+        const int nb = h->lh[h->L] * h->lw[h->L];
+        if ((rc = ss_timer_begin(h))) return rc;
+        SS_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(unsigned int) * h->num_values * h->n_pushed, h->s_comp));
+        dim3 g((nb + 255) / 256, h->n_pushed);
+        ss_base_gray_hist_kernel<<<g, 256, 0, h->s_comp>>>(h->base, nb, h->gray, h->counts, h->num_values);
+        h->launches++;
+        SS_CUDA(cudaGetLastError());
+        if ((rc = ss_timer_end(h))) return rc;
+        h->finished_begin = true;
+    }
+    if (counts) {
+        const size_t n = (size_t)h->n_pushed * h->num_values;
+        std::vector<unsigned int> tmp(n);
+        SS_CUDA(cudaMemcpyAsync(tmp.data(), h->counts, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_comp));
+        SS_CUDA(cudaStreamSynchronize(h->s_comp));
+        for (size_t i = 0; i < n; ++i) counts[i] = (int64_t)tmp[i];
+    }
+    return 0;
+}
+
+// Base-level selection on this rank's frames (entropy / deviation arg-max + winners' pixels).
+SS_EXPORT int ss_finish_select_base(ss_handle *h, const float *log_prob)
+{
+    if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin must be called first");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const int nb = h->lh[h->L] * h->lw[h->L];
+    const size_t n = (size_t)h->n_pushed * h->num_values;
+    std::vector<float> tab;
+    if (!log_prob) {
+        // C-only callers: logf from libm; numpy's SIMD log can differ from it in the last ulp, which
+        // matters only for exact ties-by-rounding of the base-level entropy arg-max.
+        std::vector<unsigned int> cnt(n);
+        SS_CUDA(cudaMemcpyAsync(cnt.data(), h->counts, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_comp));
+        SS_CUDA(cudaStreamSynchronize(h->s_comp));
+        tab.resize(n);
+        for (int f = 0; f < h->n_pushed; ++f)
+            for (int v = 0; v < h->num_values; ++v) {
+                const unsigned int c = cnt[(size_t)f * h->num_values + v];
+                const float pr = (float)((double)(float)c / (double)nb);
+                tab[(size_t)f * h->num_values + v] = c ? logf(pr) : -INFINITY;
+            }
+        log_prob = tab.data();
+    }
+    SS_CUDA(cudaMemcpyAsync(h->log_p, log_prob, n * sizeof(float), cudaMemcpyHostToDevice, h->s_comp));
+    if (!tab.empty()) SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    int rc;
+    if ((rc = ss_timer_begin(h))) return rc;
+    ss_base_select_kernel<<<(nb + 63) / 64, 64, 0, h->s_comp>>>(h->gray, h->log_p, h->base, h->lh[h->L],
+        h->lw[h->L], h->n_pushed, h->num_values, h->side, h->cfg.frame_index_base, h->best_ve, h->best_ie,
+        h->best_vd, h->best_id, h->pix_e, h->pix_d);
+    h->launches++;
+    SS_CUDA(cudaGetLastError());
+    if ((rc = ss_timer_end(h))) return rc;
+    return 0;
+}
+
+// Blend the base, collapse the fused pyramid, convert and download (reference pyramid.py:106-111,
+// 57-64, 179).
+SS_EXPORT int ss_finish_collapse(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes)
+{
+    if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin must be called first");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const int L = h->L;
+    const size_t nb = (size_t)h->lh[L] * h->lw[L];
+    int rc;
+    if ((rc = ss_timer_begin(h))) return rc;
+    ss_base_fuse_kernel<<<(unsigned)((3 * nb + 255) / 256), 256, 0, h->s_comp>>>(h->pix_e, h->pix_d, 3 * nb, h->fused_base);
+    h->launches++;
+    const float *img = h->fused_base;
+    if (L == 0) {
+        dim3 g((h->cfg.width + 255) / 256, h->cfg.height);
+        ss_finalize_kernel<<<g, 256, 0, h->s_comp>>>(img, h->cfg.height, h->cfg.width, h->cfg.bytes_per_sample,
+                                                      h->out_dev, (int)h->out_pitch);
+        h->launches++;
+    }
+    for (int l = L - 1; l >= 0; --l) {
+        SsCollapseParams p;
+        memset(&p, 0, sizeof(p));
+        p.img = img;
+        p.layer = h->lv[l].fused;
+        p.h = h->lh[l]; p.w = h->lw[l]; p.h2 = h->lh[l + 1]; p.w2 = h->lw[l + 1];
+        memcpy(p.k25, h->k25, sizeof(p.k25));
+        if (l == 0) {
+            p.final_bytes = h->cfg.bytes_per_sample;
+            p.out_px = h->out_dev;
+            p.out_pitch = (int)h->out_pitch;
+        } else {
+            p.out = (img == h->tmp_a) ? h->tmp_b : h->tmp_a;
+        }
+        dim3 g((p.w + 63) / 64, (p.h + 3) / 4);
+        ss_collapse_kernel<<<g, 256, 0, h->s_comp>>>(p);
+        h->launches++;
+        img = p.out;
+    }
+    SS_CUDA(cudaGetLastError());
+    if ((rc = ss_timer_end(h))) return rc;
+    if (out_bgr) {
+        const size_t row = (size_t)h->cfg.width * 3 * h->cfg.bytes_per_sample;
+        if (out_row_pitch_bytes < row) return ss_fail(SS_ERR_SHAPE, "output pitch too small");
+        SS_CUDA(cudaMemcpy2DAsync(out_bgr, out_row_pitch_bytes, h->out_dev, h->out_pitch, row, h->cfg.height,
+                                  cudaMemcpyDeviceToHost, h->s_comp));
+    }
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    return 0;
+}
+
+SS_EXPORT int ss_finish_end(ss_handle *h, const float *log_prob, void *out_bgr, size_t out_row_pitch_bytes)
+{
+    int rc = ss_finish_select_base(h, log_prob);
+    if (rc) return rc;
+    return ss_finish_collapse(h, out_bgr, out_row_pitch_bytes);
+}
+
+SS_EXPORT int ss_finish(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes)
+{
+    int rc = ss_finish_begin(h, nullptr);
+    if (rc) return rc;
+    return ss_finish_end(h, nullptr, out_bgr, out_row_pitch_bytes);
+}
+
+SS_EXPORT int ss_get_argmax(ss_handle *h, int level, int32_t *out)
+{
+    if (!h || !out || level < 0 || level > h->L + 1) return ss_fail(SS_ERR_STATE, "bad argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const int32_t *src;
+    size_t n;
+    if (level < h->L) { src = h->lv[level].best_idx; n = (size_t)h->lh[level] * h->lw[level]; }
+    else { src = level == h->L ? h->best_ie : h->best_id; n = (size_t)h->lh[h->L] * h->lw[h->L]; }
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    SS_CUDA(cudaMemcpy(out, src, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+SS_EXPORT int ss_get_best_energy(ss_handle *h, int level, float *out)
+{
+    if (!h || !out || level < 0 || level >= h->L) return ss_fail(SS_ERR_STATE, "bad argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    SS_CUDA(cudaMemcpy(out, h->lv[level].best_e, (size_t)h->lh[level] * h->lw[level] * sizeof(float),
+                       cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+SS_EXPORT int ss_get_fused_level(ss_handle *h, int level, float *out)
+{
+    if (!h || !out || level < 0 || level > h->L) return ss_fail(SS_ERR_STATE, "bad argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->lh[level] * h->lw[level];
+    const float *src = level < h->L ? h->lv[level].fused : h->fused_base;
+    std::vector<float> tmp(3 * n);
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    SS_CUDA(cudaMemcpy(tmp.data(), src, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) out[3 * i + c] = tmp[c * n + i];
+    return 0;
+}
+
+// g_{l+1} of frame `frame` (index within the most recent batch for l+1 < L; absolute for the base
+// level l+1 == L) as 3 float32 planes -- test hook for reduce_layer (reference pyramid.py:27-32).
+SS_EXPORT int ss_get_gauss_level(ss_handle *h, int level, int frame, float *out_planes)
+{
+    if (!h || !out_planes || level < 1 || level > h->L) return ss_fail(SS_ERR_STATE, "bad argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t n = 3 * (size_t)h->lh[level] * h->lw[level];
+    const float *src = level < h->L ? h->lv[level - 1].gnext + (size_t)frame * n : h->base + (size_t)frame * n;
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    SS_CUDA(cudaMemcpy(out_planes, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+SS_EXPORT int ss_kernel_time_ms(ss_handle *h, float *ms)
+{
+    if (!h || !ms) return ss_fail(SS_ERR_STATE, "null argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    float total = 0.f;
+    for (size_t i = 0; i < h->timers_used; ++i) {
+        float t = 0.f;
+        SS_CUDA(cudaEventElapsedTime(&t, h->timers[i].first, h->timers[i].second));
+        total += t;
+    }
+    *ms = total;
+    return 0;
+}
+
+// Time of timed segment i (batches first, then base histogram, base select, collapse).
+SS_EXPORT int ss_segment_time_ms(ss_handle *h, int i, float *ms)
+{
+    if (!h || !ms || i < 0 || (size_t)i >= h->timers_used) return ss_fail(SS_ERR_STATE, "bad segment");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    SS_CUDA(cudaEventElapsedTime(ms, h->timers[i].first, h->timers[i].second));
+    return 0;
+}
+
+// Per-launch CUDA-event timing of the fused level kernels (bench.py's roofline figure).
+SS_EXPORT int ss_set_profiling(ss_handle *h, int on)
+{
+    if (!h) return ss_fail(SS_ERR_STATE, "null handle");
+    h->profile = on != 0;
+    return 0;
+}
+
+SS_EXPORT int ss_level_kernel_time_ms(ss_handle *h, int level, float *total_ms, int32_t *launches)
+{
+    if (!h || !total_ms || !launches) return ss_fail(SS_ERR_STATE, "null argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    float tot = 0.f;
+    int n = 0;
+    for (size_t i = 0; i < h->ltimers_used; ++i) {
+        if (h->ltimers[i].level != level) continue;
+        float t = 0.f;
+        SS_CUDA(cudaEventElapsedTime(&t, h->ltimers[i].a, h->ltimers[i].b));
+        tot += t;
+        ++n;
+    }
+    *total_ms = tot;
+    *launches = n;
+    return 0;
+}
+
+SS_EXPORT int ss_launch_count(ss_handle *h, int64_t *launches)
+{
+    if (!h || !launches) return ss_fail(SS_ERR_STATE, "null argument");
+    *launches = h->launches;
+    return 0;
+}
+
+// ---- multi-GPU exchange ---------------------------------------------------------------------------
+// Packed layout: keys = [level 0 .. L-1 energies | base entropy | base deviation];
+// coeffs = [level 0 .. L-1 fused (3 planes each) | pix_e (3 planes) | pix_d (3 planes)].
+static int ss_ensure_exchange(ss_handle *h)
+{
+    int rc;
+    if (!h->keys && (rc = ss_dalloc(&h->keys, h->n_keys))) return rc;
+    if (!h->coeffs && (rc = ss_dalloc(&h->coeffs, h->n_coeffs))) return rc;
+    return 0;
+}
+
+SS_EXPORT int ss_exchange_keys(ss_handle *h, uint64_t **d_keys, size_t *count)
+{
+    if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin/select_base first");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = ss_ensure_exchange(h);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int l = 0; l < h->L; ++l) {
+        const size_t n = (size_t)h->lh[l] * h->lw[l];
+        ss_pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->s_comp>>>(h->lv[l].best_e, h->lv[l].best_idx, n, h->keys + off);
+        off += n;
+    }
+    const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
+    ss_pack_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->s_comp>>>(h->best_ve, h->best_ie, nb, h->keys + off);
+    off += nb;
+    ss_pack_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->s_comp>>>(h->best_vd, h->best_id, nb, h->keys + off);
+    h->launches += h->L + 2;
+    SS_CUDA(cudaGetLastError());
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    if (d_keys) *d_keys = (uint64_t *)h->keys;
+    if (count) *count = h->n_keys;
+    return 0;
+}
+
+SS_EXPORT int ss_exchange_mask_losers(ss_handle *h, float **d_coeffs, size_t *count)
+{
+    if (!h || !h->keys) return ss_fail(SS_ERR_STATE, "ss_exchange_keys first");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    size_t off = 0, coff = 0;
+    for (int l = 0; l < h->L; ++l) {
+        const size_t n = (size_t)h->lh[l] * h->lw[l];
+        ss_adopt_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->s_comp>>>(h->keys + off, n, 3, h->lv[l].best_e,
+                                                                               h->lv[l].best_idx, h->lv[l].fused);
+        SS_CUDA(cudaMemcpyAsync(h->coeffs + coff, h->lv[l].fused, 3 * n * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
+        off += n;
+        coff += 3 * n;
+    }
+    const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
+    ss_adopt_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->s_comp>>>(h->keys + off, nb, 3, h->best_ve, h->best_ie, h->pix_e);
+    SS_CUDA(cudaMemcpyAsync(h->coeffs + coff, h->pix_e, 3 * nb * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
+    off += nb; coff += 3 * nb;
+    ss_adopt_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->s_comp>>>(h->keys + off, nb, 3, h->best_vd, h->best_id, h->pix_d);
+    SS_CUDA(cudaMemcpyAsync(h->coeffs + coff, h->pix_d, 3 * nb * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
+    h->launches += h->L + 2;
+    SS_CUDA(cudaGetLastError());
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    if (d_coeffs) *d_coeffs = h->coeffs;
+    if (count) *count = h->n_coeffs;
+    return 0;
+}
+
+SS_EXPORT int ss_exchange_adopt(ss_handle *h)
+{
+    if (!h || !h->coeffs) return ss_fail(SS_ERR_STATE, "ss_exchange_mask_losers first");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    size_t coff = 0;
+    for (int l = 0; l < h->L; ++l) {
+        const size_t n = (size_t)h->lh[l] * h->lw[l];
+        SS_CUDA(cudaMemcpyAsync(h->lv[l].fused, h->coeffs + coff, 3 * n * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
+        coff += 3 * n;
+    }
+    const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
+    SS_CUDA(cudaMemcpyAsync(h->pix_e, h->coeffs + coff, 3 * nb * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
+    coff += 3 * nb;
+    SS_CUDA(cudaMemcpyAsync(h->pix_d, h->coeffs + coff, 3 * nb * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    return 0;
+}
+
+// ---- test hooks -----------------------------------------------------------------------------------
+// One collapse step on host arrays (3 float32 planes each) through the product's collapse kernel.
+SS_EXPORT int ss_test_collapse_step(const float *img_planes, int h2, int w2, const float *layer_planes,
+                                    int h, int w, double gen_kernel, float *out_planes)
+{
+    if (ss_device_count() == 0) return ss_fail(SS_ERR_NO_DEVICE, "no sm_100 device");
+    float *d_img = nullptr, *d_lay = nullptr, *d_out = nullptr;
+    const size_t n2 = 3 * (size_t)h2 * w2, n = 3 * (size_t)h * w;
+    SS_CUDA(cudaMalloc(&d_img, n2 * 4));
+    SS_CUDA(cudaMalloc(&d_out, n * 4));
+    SS_CUDA(cudaMemcpy(d_img, img_planes, n2 * 4, cudaMemcpyHostToDevice));
+    if (layer_planes) {
+        SS_CUDA(cudaMalloc(&d_lay, n * 4));
+        SS_CUDA(cudaMemcpy(d_lay, layer_planes, n * 4, cudaMemcpyHostToDevice));
+    }
+    SsCollapseParams p;
+    memset(&p, 0, sizeof(p));
+    p.img = d_img; p.layer = d_lay; p.out = d_out;
+    p.h = h; p.w = w; p.h2 = h2; p.w2 = w2;
+    ss_make_kernel(gen_kernel, p.k25);
+    dim3 g((w + 63) / 64, (h + 3) / 4);
+    ss_collapse_kernel<<<g, 256>>>(p);
+    SS_CUDA(cudaGetLastError());
+    SS_CUDA(cudaMemcpy(out_planes, d_out, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_img); cudaFree(d_lay); cudaFree(d_out);
+    return 0;
+}

@@ -1,0 +1,333 @@
+"""Host-side mirror of the reference stack-algo interface for the pyramid path.
+
+``PyramidStack`` here has the constructor, attributes and methods that
+``FocusStack`` / ``FocusStackBunch`` (reference src/shinestacker/algorithms/stack.py:23,29,47,76,108)
+use on a ``stack_algo`` object -- ``process``, ``do_step_callback``, ``name()``, ``steps_per_frame()``,
+``focus_stack(filenames)`` -- and the same constructor keywords, progress callbacks and exception
+types as the reference class (reference src/shinestacker/algorithms/pyramid.py:10-22,114-179 and
+base_stack_algo.py:9-42).  All pixel arithmetic runs in libshinestack_b200.so (hand-written sm_100a
+CUDA kernels) through the C ABI declared in include/shinestack_b200.h; this module only decodes
+files (cv2.imread, as the reference does), moves bytes and computes the base-level log-probability
+table with numpy (so that it is bit-identical to the reference's ``np.log``).
+
+There is deliberately no CPU implementation here: without the shared library or without an sm_100
+GPU every call raises ``NativeLibraryError``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _native
+from .exceptions import (InvalidOptionError, ImageLoadError, BitDepthError, ShapeError,
+                         RunStopException, NativeLibraryError)
+
+# reference src/shinestacker/config/constants.py:159-162, :8-11
+DEFAULT_PY_MIN_SIZE = 32
+DEFAULT_PY_KERNEL_SIZE = 5
+DEFAULT_PY_GEN_KERNEL = 0.4
+FLOAT_32 = 'float-32'
+FLOAT_64 = 'float-64'
+DEFAULT_PY_FLOAT = FLOAT_32
+
+
+def read_img(file_path):
+    """reference src/shinestacker/algorithms/utils.py:11-20."""
+    import cv2  # pylint: disable=import-outside-toplevel
+    if not os.path.isfile(file_path):
+        raise RuntimeError("File does not exist: " + file_path)
+    ext = file_path.split(".")[-1]
+    img = None
+    if ext in ['jpeg', 'jpg']:
+        img = cv2.imread(file_path)
+    elif ext in ['tiff', 'tif', 'png']:
+        img = cv2.imread(file_path, cv2.IMREAD_UNCHANGED)
+    return img
+
+
+def log_prob_table(counts):
+    """np.log(probabilities) of PyramidBase.entropy (reference pyramid.py:67-69,77) for every frame.
+
+    ``counts``: (n_frames, num_values) int64 histogram of each frame's truncated gray base level.
+    The reference evaluates ``counts.astype(float32) / counts.sum()`` in float64 (float32 array /
+    int64 scalar) and rounds to float32 when storing into ``probabilities``; values that do not
+    occur keep probability 0 (-inf after the log, never indexed).
+    """
+    counts = np.asarray(counts, dtype=np.int64)
+    total = counts.sum(axis=1, keepdims=True)
+    prob = (counts.astype(np.float32) / total).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        return np.ascontiguousarray(np.log(prob))
+
+
+def _check(rc):
+    if rc == _native.SS_OK:
+        return
+    msg = _native.last_error()
+    if rc == _native.SS_ERR_INVALID_OPTION:
+        raise InvalidOptionError("native", rc, details=msg)
+    raise NativeLibraryError(f"libshinestack_b200 error {rc}: {msg}")
+
+
+class PyramidBase:
+    """Constructor contract of the reference PyramidBase/BaseStackAlgo (pyramid.py:10-22,
+    base_stack_algo.py:9-31)."""
+
+    def __init__(self, min_size=DEFAULT_PY_MIN_SIZE, kernel_size=DEFAULT_PY_KERNEL_SIZE,
+                 gen_kernel=DEFAULT_PY_GEN_KERNEL, float_type=DEFAULT_PY_FLOAT):
+        self._name = "pyramid"
+        self._steps_per_frame = 2
+        self.process = None
+        if float_type == FLOAT_32:
+            self.float_type = np.float32
+        elif float_type == FLOAT_64:
+            raise InvalidOptionError(
+                "float_type", float_type,
+                details=" the B200 path implements FLOAT_32 only")
+        else:
+            raise InvalidOptionError(
+                "float_type", float_type,
+                details=" valid values are FLOAT_32 and FLOAT_64")
+        self.min_size = min_size
+        self.kernel_size = kernel_size
+        self.pad_amount = (kernel_size - 1) // 2
+        self.do_step_callback = False
+        self.gen_kernel_param = float(gen_kernel)
+        kernel = np.array([0.25 - gen_kernel / 2.0, 0.25,
+                           gen_kernel, 0.25, 0.25 - gen_kernel / 2.0])
+        self.gen_kernel = np.outer(kernel, kernel)
+
+    def name(self):
+        return self._name
+
+    def steps_per_frame(self):
+        return self._steps_per_frame
+
+    def print_message(self, msg):
+        if self.process is None:
+            return
+        try:
+            from shinestacker.core.colors import color_str  # type: ignore
+            from shinestacker.config.constants import constants  # type: ignore
+            msg = color_str(msg, constants.LOG_COLOR_LEVEL_3)
+        except Exception:  # pylint: disable=broad-except
+            pass
+        self.process.sub_message_r(msg)
+
+
+class PyramidStack(PyramidBase):
+    """Drop-in replacement of the reference ``PyramidStack`` (pyramid.py:114-179) running on a B200.
+
+    Extra keywords (all optional): ``device`` CUDA ordinal, ``batch_frames`` frames fused per kernel
+    chain launch, ``keep_depth_maps`` download the integer arg-max maps after each stack.
+    """
+
+    def __init__(self, min_size=DEFAULT_PY_MIN_SIZE, kernel_size=DEFAULT_PY_KERNEL_SIZE,
+                 gen_kernel=DEFAULT_PY_GEN_KERNEL, float_type=DEFAULT_PY_FLOAT,
+                 device=0, batch_frames=8, keep_depth_maps=True, frame_index_base=0):
+        super().__init__(min_size, kernel_size, gen_kernel, float_type)
+        self.offset = np.arange(-self.pad_amount, self.pad_amount + 1)
+        self.dtype = None
+        self.num_pixel_values = None
+        self.max_pixel_value = None
+        self.device = int(device)
+        self.batch_frames = int(batch_frames)
+        self.keep_depth_maps = keep_depth_maps
+        self.frame_index_base = int(frame_index_base)
+        self.depth_maps = None     # dict(best=[level 0..L-1], best_e, best_d) after focus_stack
+        self.last_kernel_ms = None
+        self.last_launches = None
+        self._lib = _native.load()
+        self._h = None
+        self._geom = None
+        self._stage = []
+        self._stage_bytes = 0
+
+    # ---- native handle management ---------------------------------------------------------------
+    def _ensure_handle(self, shape, dtype, n_frames, resident=False):
+        h, w = int(shape[0]), int(shape[1])
+        bps = np.dtype(dtype).itemsize
+        geom = (h, w, bps)
+        if self._h is not None and self._geom == geom and n_frames <= self._max_frames and \
+                (not resident or self._resident >= n_frames):
+            _check(self._lib.ss_reset(self._h))
+            return
+        self.close()
+        cfg = _native.SsConfig()
+        cfg.width, cfg.height, cfg.bytes_per_sample = w, h, bps
+        cfg.min_size, cfg.kernel_size = int(self.min_size), int(self.kernel_size)
+        cfg.gen_kernel = self.gen_kernel_param
+        cfg.float_bits = 32
+        cfg.device = self.device
+        cfg.max_frames = max(int(n_frames), 1)
+        cfg.batch_frames = self.batch_frames
+        cfg.frame_index_base = self.frame_index_base
+        cfg.resident_frames = int(n_frames) if resident else 0
+        hp = ctypes.c_void_p()
+        _check(self._lib.ss_create(ctypes.byref(cfg), ctypes.byref(hp)))
+        self._h = hp
+        self._geom = geom
+        self._max_frames = cfg.max_frames
+        self._resident = cfg.resident_frames
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.ss_destroy(self._h)
+            self._h = None
+        for ptr, _ in getattr(self, "_stage", []):
+            self._lib.ss_host_free(ptr)
+        self._stage = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    def _staging(self, nbytes, count):
+        """Ring of pinned host buffers the decoded frames are copied into before the async upload."""
+        if self._stage_bytes != nbytes or len(self._stage) < count:
+            for ptr, _ in self._stage:
+                self._lib.ss_host_free(ptr)
+            self._stage = []
+            for _ in range(count):
+                p = ctypes.c_void_p()
+                _check(self._lib.ss_host_alloc(ctypes.byref(p), nbytes))
+                buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+                self._stage.append((p, np.frombuffer(buf, dtype=np.uint8)))
+            self._stage_bytes = nbytes
+        return self._stage
+
+    # ---- reference protocol ---------------------------------------------------------------------
+    def _set_metadata(self, img):
+        self.dtype = img.dtype
+        self.num_pixel_values = 256 if self.dtype == np.uint8 else 65536
+        self.max_pixel_value = 255 if self.dtype == np.uint8 else 65535
+
+    @staticmethod
+    def _validate(img, shape, dtype):
+        # reference utils.py:56-63
+        if img is None:
+            raise RuntimeError("Image is None")
+        if img.shape[:2] != shape[:2]:
+            raise ShapeError(shape, img.shape[:2])
+        if img.dtype != dtype:
+            raise BitDepthError(dtype, img.dtype)
+
+    def _callbacks(self, step):
+        if self.process is None:
+            return
+        if self.do_step_callback:
+            self.process.callback('after_step', self.process.id, self.process.name, step)
+        if self.process.callback('check_running', self.process.id, self.process.name) is False:
+            raise RunStopException(self.name())
+
+    def _push(self, i, img, ring):
+        img = np.ascontiguousarray(img)
+        slot = i % len(ring)
+        if i >= len(ring) and slot == 0:
+            _check(self._lib.ss_sync_copies(self._h))
+        ptr, view = ring[slot]
+        view[:img.nbytes] = img.reshape(-1).view(np.uint8)
+        _check(self._lib.ss_push_frame(self._h, ptr, img.shape[1] * 3 * img.dtype.itemsize))
+
+    def _finish(self, n, shape):
+        lib, h = self._lib, self._h
+        counts = np.empty((n, self.num_pixel_values), dtype=np.int64)
+        _check(lib.ss_finish_begin(h, counts.ctypes.data_as(ctypes.c_void_p)))
+        table = log_prob_table(counts)
+        out = np.empty((shape[0], shape[1], 3), dtype=self.dtype)
+        _check(lib.ss_finish_end(h, table.ctypes.data_as(ctypes.c_void_p),
+                                 out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+        ms = ctypes.c_float()
+        _check(lib.ss_kernel_time_ms(h, ctypes.byref(ms)))
+        self.last_kernel_ms = ms.value
+        nl = ctypes.c_int64()
+        _check(lib.ss_launch_count(h, ctypes.byref(nl)))
+        self.last_launches = nl.value
+        if self.keep_depth_maps:
+            self.depth_maps = self.get_depth_maps()
+        return out
+
+    def get_depth_maps(self):
+        """Integer arg-max maps of the last stack (np.argmax results of reference pyramid.py:51 and
+        :104-105): dict(best=[level 0 .. L-1], best_e, best_d)."""
+        lib, h = self._lib, self._h
+        L = lib.ss_num_levels(h)
+        maps = []
+        for level in range(L + 2):
+            hh, ww = ctypes.c_int32(), ctypes.c_int32()
+            _check(lib.ss_level_size(h, min(level, L), ctypes.byref(hh), ctypes.byref(ww)))
+            m = np.empty((hh.value, ww.value), dtype=np.int32)
+            _check(lib.ss_get_argmax(h, level, m.ctypes.data_as(ctypes.c_void_p)))
+            maps.append(m)
+        return dict(best=maps[:L], best_e=maps[L], best_d=maps[L + 1], levels=L)
+
+    def get_fused_pyramid(self):
+        """Fused Laplacian levels + fused base of the last stack, H_l x W_l x 3 float32 (tests)."""
+        lib, h = self._lib, self._h
+        L = lib.ss_num_levels(h)
+        out = []
+        for level in range(L + 1):
+            hh, ww = ctypes.c_int32(), ctypes.c_int32()
+            _check(lib.ss_level_size(h, level, ctypes.byref(hh), ctypes.byref(ww)))
+            a = np.empty((hh.value, ww.value, 3), dtype=np.float32)
+            _check(lib.ss_get_fused_level(h, level, a.ctypes.data_as(ctypes.c_void_p)))
+            out.append(a)
+        return out
+
+    def focus_stack(self, filenames):
+        """reference pyramid.py:150-179: list of image paths -> fused H x W x 3 BGR array of the
+        input dtype.  Each file is decoded once (the reference decodes it twice); progress steps
+        ``i`` (validated) and ``i + n`` (processed) are reported for every frame like the reference."""
+        n = len(filenames)
+        metadata = None
+        ring = None
+        try:
+            for i, img_path in enumerate(filenames):
+                self.print_message(f": validating file {img_path.split('/')[-1]}")
+                img = read_img(img_path)
+                if img is None:
+                    raise ImageLoadError(img_path)
+                if metadata is None:
+                    metadata = (img.shape[:2], img.dtype)
+                    if img.ndim != 3 or img.shape[2] != 3 or img.dtype not in (np.uint8, np.uint16):
+                        raise ImageLoadError(img_path, "expected a 3-channel 8 or 16 bit image")
+                    self._set_metadata(img)
+                    self._ensure_handle(img.shape, img.dtype, n)
+                    ring = self._staging(img.nbytes, 2 * max(self.batch_frames, 1))
+                else:
+                    self._validate(img, *metadata)
+                self._callbacks(i)
+                self.print_message(f": processing file {img_path.split('/')[-1]}")
+                self._push(i, img, ring)
+                self._callbacks(i + n)
+            if metadata is None:
+                raise ImageLoadError("", "empty file list")
+            self.print_message(': pyramids fusion completed')
+            return self._finish(n, metadata[0])
+        except BaseException:
+            if self._h is not None:
+                self._lib.ss_reset(self._h)
+            raise
+
+    def focus_stack_arrays(self, frames):
+        """In-memory entry point: iterable of H x W x 3 BGR uint8/uint16 arrays -> fused image."""
+        frames = list(frames)
+        if not frames:
+            raise ImageLoadError("", "empty frame list")
+        img0 = frames[0]
+        if img0.ndim != 3 or img0.shape[2] != 3 or img0.dtype not in (np.uint8, np.uint16):
+            raise ImageLoadError("<array>", "expected a 3-channel 8 or 16 bit image")
+        self._set_metadata(img0)
+        self._ensure_handle(img0.shape, img0.dtype, len(frames))
+        ring = self._staging(img0.nbytes, 2 * max(self.batch_frames, 1))
+        try:
+            for i, img in enumerate(frames):
+                self._validate(img, img0.shape[:2], img0.dtype)
+                self._push(i, img, ring)
+            return self._finish(len(frames), img0.shape[:2])
+        except BaseException:
+            if self._h is not None:
+                self._lib.ss_reset(self._h)
+            raise

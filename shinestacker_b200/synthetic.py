@@ -49,6 +49,11 @@ def frame_from_scene(sharp, blurred, i, n, dtype=np.uint8):
 def make_stack(n, h, w, dtype=np.uint8, seed=0):
     """List of ``n`` HxWx3 BGR frames of the given dtype."""
     sharp, blurred = make_scene(h, w, dtype, seed)
+    # quantise the two scenes once; every frame is then a byte-level composition of them (identical
+    # to frame_from_scene on the float scenes, clip/astype being elementwise)
+    maxv = 255 if np.dtype(dtype) == np.uint8 else 65535
+    sharp = np.clip(sharp, 0, maxv).astype(dtype)
+    blurred = np.clip(blurred, 0, maxv).astype(dtype)
     return [frame_from_scene(sharp, blurred, i, n, dtype) for i in range(n)]
 
 

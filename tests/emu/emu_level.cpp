@@ -1,0 +1,39 @@
+// CPU emulation of the fused level kernel's tile code (TEST INFRASTRUCTURE ONLY): compiles
+// shinestacker_b200/csrc/ss_kernels.cuh with g++ and runs the tiles sequentially, so the halo /
+// border / tail-column index arithmetic can be checked against the oracle without a GPU.
+// Build: g++ -O1 -mfma -ffp-contract=off -DSS_HOST_EMU -shared -fPIC
+#define SS_HOST_EMU 1
+#include "../../shinestacker_b200/csrc/ss_kernels.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+extern "C" int emu_level(const void *in, int bytes_per_sample /*1,2: interleaved; 4: planar f32*/,
+                         int n_frames, int h, int w, const float *k25, float *gnext, float *best_e,
+                         int32_t *best_idx, float *fused, int frame_index0, int init)
+{
+    SsLevelParams p;
+    memset(&p, 0, sizeof(p));
+    p.h = h; p.w = w; p.h2 = (h + 1) / 2; p.w2 = (w + 1) / 2;
+    p.in = in;
+    if (bytes_per_sample == 4) {
+        p.in_pitch = w * 4; p.in_plane_stride = (long long)h * w * 4; p.in_frame_stride = 3 * p.in_plane_stride;
+    } else {
+        p.in_pitch = w * 3 * bytes_per_sample; p.in_frame_stride = (long long)h * p.in_pitch;
+    }
+    p.gnext = gnext; p.gnext_pitch = p.w2; p.gnext_plane_stride = (long long)p.h2 * p.w2;
+    p.gnext_frame_stride = 3 * p.gnext_plane_stride;
+    p.best_e = best_e; p.best_idx = best_idx; p.fused = fused;
+    p.n_frames = n_frames; p.frame_index0 = frame_index0; p.init = init;
+    memcpy(p.k25, k25, sizeof(p.k25));
+    float *smem = (float *)malloc(sizeof(float) * SS_SMEM_FLOATS);
+    // poison shared memory so that any read of a never-written slot shows up as NaN
+    for (int ty = 0; ty < (h + SS_TY - 1) / SS_TY; ++ty)
+        for (int tx = 0; tx < (w + SS_TX - 1) / SS_TX; ++tx) {
+            memset(smem, 0xff, sizeof(float) * SS_SMEM_FLOATS);
+            if (bytes_per_sample == 1) ss_level_tile<uint8_t>(p, tx, ty, smem);
+            else if (bytes_per_sample == 2) ss_level_tile<uint16_t>(p, tx, ty, smem);
+            else ss_level_tile<float>(p, tx, ty, smem);
+        }
+    free(smem);
+    return 0;
+}

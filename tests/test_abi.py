@@ -1,0 +1,96 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/shinestack_b200.h declares, the host mirror keeps the reference's constructor / error
+contract, and the product path fails loudly (never falls back) without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from shinestacker_b200 import _native, pyramid
+from shinestacker_b200 import PyramidStack, InvalidOptionError, NativeLibraryError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "shinestack_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    # and the ctypes prototypes cover the header
+    assert set(names) == set(_native.SIGNATURES), set(names) ^ set(_native.SIGNATURES)
+
+
+def test_version_and_config_layout():
+    lib = _native.load()
+    assert b"sm_100a" in lib.ss_version()
+    assert ctypes.sizeof(_native.SsConfig) == 72
+
+
+def test_float_type_contract():
+    # reference base_stack_algo.py:13-22
+    with pytest.raises(InvalidOptionError):
+        PyramidStack(float_type="float-16")
+    with pytest.raises(InvalidOptionError):
+        PyramidStack(float_type="float-64")   # documented gap: FLOAT_32 only on the B200 path
+    a = PyramidStack()
+    assert a.name() == "pyramid" and a.steps_per_frame() == 2
+    assert a.float_type is np.float32 and a.do_step_callback is False
+    assert a.gen_kernel.shape == (5, 5) and a.gen_kernel.dtype == np.float64
+    assert a.pad_amount == 2 and list(a.offset) == [-2, -1, 0, 1, 2]
+
+
+def test_invalid_options_reported_by_native_layer():
+    lib = _native.load()
+    cfg = _native.SsConfig(width=64, height=64, bytes_per_sample=1, min_size=32, kernel_size=5,
+                           gen_kernel=0.4, float_bits=64, device=0, max_frames=2)
+    h = ctypes.c_void_p()
+    assert lib.ss_create(ctypes.byref(cfg), ctypes.byref(h)) == _native.SS_ERR_INVALID_OPTION
+    assert b"float" in lib.ss_last_error()
+    cfg.float_bits, cfg.bytes_per_sample = 32, 3
+    assert lib.ss_create(ctypes.byref(cfg), ctypes.byref(h)) == _native.SS_ERR_BIT_DEPTH
+
+
+def test_no_silent_cpu_fallback():
+    lib = _native.load()
+    if lib.ss_device_count() > 0:
+        pytest.skip("a B200 is present")
+    with pytest.raises(NativeLibraryError):
+        PyramidStack().focus_stack_arrays([np.zeros((64, 64, 3), np.uint8)])
+
+
+def test_log_prob_table_matches_reference_expression(oracle):
+    rng = np.random.default_rng(3)
+    gray = rng.integers(0, 256, size=(3, 48, 64)).astype(np.int32)
+    counts = np.stack([np.bincount(g.ravel(), minlength=256) for g in gray])
+    tab = pyramid.log_prob_table(counts)
+    for i in range(3):
+        assert np.array_equal(tab[i], oracle.log_prob_table(gray[i], 256), equal_nan=True)
+        # literal reference expression (pyramid.py:67-69)
+        levels, cnt = np.unique(gray[i].astype(np.uint8), return_counts=True)
+        prob = np.zeros(256, dtype=np.float32)
+        prob[levels] = cnt.astype(np.float32) / cnt.sum()
+        with np.errstate(divide="ignore"):
+            assert np.array_equal(tab[i], np.log(prob))
+
+
+def test_read_img_contract(tmp_path):
+    import cv2
+    with pytest.raises(RuntimeError):
+        pyramid.read_img(str(tmp_path / "missing.tif"))
+    img = (np.arange(40 * 50 * 3) % 65536).astype(np.uint16).reshape(40, 50, 3)
+    p = str(tmp_path / "a.tif")
+    cv2.imwrite(p, img)
+    assert np.array_equal(pyramid.read_img(p), img)
+    q = str(tmp_path / "a.bmp")
+    cv2.imwrite(q, (img >> 8).astype(np.uint8))
+    assert pyramid.read_img(q) is None      # unsupported extension -> None, like the reference

@@ -2,22 +2,32 @@
 //
 // One body, two builds: nvcc compiles it as CUDA kernels (the product); tests/emu/ compiles the very
 // same tile code with g++ (-DSS_HOST_EMU) so the index arithmetic (halos, REFLECT101 fix-ups, tail
-// columns) can be checked on a CPU-only box.  The emulation is test infrastructure; the product never
-// uses it.
+// columns, register blocking) can be checked on a CPU-only box.  The emulation is test
+// infrastructure; the product never uses it.
 //
 // Arithmetic contract (what makes the result bit-identical to the reference CPU path):
 //   * every 5x5 filter output is ONE sequential chain over the 25 taps in row-major order starting
 //     from +0: fused multiply-add for output columns x < w - w%8, separate multiply and add for the
 //     last w%8 columns (w = width of the array the reference hands to cv2.filter2D);
-//   * expand skips the taps that fall on stuffed zeros (exact), keeps row-major order, then *4;
+//   * expand skips the taps that fall on stuffed zeros (exact), keeps row-major order; the "*4" and the
+//     following subtraction / addition are folded into one fma(+-4, acc, x): 4*acc is exact, so the
+//     single rounding of the fma equals the reference's two-step result;
 //   * gray = fma(R,.299f, fma(B,.114f, G*.587f));  energy = filter(gray*gray);
 //   * arg-max over frames = strict '>' in frame order; winner coefficients are stored as 0 + lap.
 // Build with -fmad=false: every FMA below is explicit and none may be created by the compiler.
+//
+// Performance model (B200, measured with tools/microbench.cu): scalar FFMA issues at ~125 of 128
+// lanes/clk/SM and the packed FFMA2 form is not faster, so the kernel is bound by FP32 issue slots
+// (~75 chain steps per input pixel) and by shared-memory bandwidth (128 B/clk/SM, i.e. one float per
+// 4 FMAs).  The fast path therefore register-blocks every stage (>= 3-6 FMAs per float loaded from
+// shared memory, 64/128-bit shared loads, fully unrolled tap loops with coefficients in the constant
+// bank); tiles that touch an image border or a tail column take the generic path.
 #pragma once
 #include <stdint.h>
 
 #ifdef SS_HOST_EMU
 #include <math.h>
+#include <string.h>
 #define SS_DEV static inline
 #define SS_THREADS(tid) for (int tid = 0; tid < SS_NT; ++tid)
 #define SS_SYNC()
@@ -26,7 +36,10 @@
 SS_DEV float ss_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
 SS_DEV float ss_mul(float a, float b) { return a * b; }
 SS_DEV float ss_add(float a, float b) { return a + b; }
-SS_DEV float ss_sub(float a, float b) { return a - b; }
+struct ss_f2 { float x, y; };
+struct ss_f4 { float x, y, z, w; };
+struct ss_u2 { uint32_t x, y; };
+struct ss_u4 { uint32_t x, y, z, w; };
 #else
 #define SS_DEV __device__ __forceinline__
 #define SS_THREADS(tid) for (int tid = threadIdx.x, ss_once_ = 1; ss_once_; ss_once_ = 0)
@@ -36,34 +49,48 @@ SS_DEV float ss_sub(float a, float b) { return a - b; }
 SS_DEV float ss_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 SS_DEV float ss_mul(float a, float b) { return __fmul_rn(a, b); }
 SS_DEV float ss_add(float a, float b) { return __fadd_rn(a, b); }
-SS_DEV float ss_sub(float a, float b) { return __fsub_rn(a, b); }
+typedef float2 ss_f2;
+typedef float4 ss_f4;
+typedef uint2 ss_u2;
+typedef uint4 ss_u4;
 #endif
 
+SS_DEV ss_f2 ss_mk2(float a, float b) { ss_f2 r; r.x = a; r.y = b; return r; }
+SS_DEV ss_f4 ss_mk4(float a, float b, float c, float d) { ss_f4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
+
 // ---- tile geometry of the fused level kernel --------------------------------------------------------
-#define SS_NT 256            // threads per CTA
-#define SS_TX 64             // output tile width  (pixels of level l)
-#define SS_TY 32             // output tile height
-#define SS_P0W (SS_TX + 12)  // g_l patch: halo 6  (energy 2 + expand 2 (in g_{l+1} units 1) + reduce 2)
-#define SS_P0H (SS_TY + 12)
-#define SS_P0S 77            // row stride of the g_l patch in floats (odd: fewer bank conflicts)
-#define SS_P1W (SS_TX / 2 + 4)  // g_{l+1} patch
-#define SS_P1H (SS_TY / 2 + 4)
-#define SS_P1S 37
-#define SS_SQW (SS_TX + 4)   // gray^2 patch: halo 2
-#define SS_SQH (SS_TY + 4)
-#define SS_SQS 69
-#define SS_LPS 65            // winner-candidate Laplacian tile row stride
-#define SS_SMEM_FLOATS (3 * SS_P0H * SS_P0S + 3 * SS_P1H * SS_P1S + SS_SQH * SS_SQS + 3 * SS_TY * SS_LPS)
+#define SS_NT 256            // threads per CTA; thread (tx,ty) = (tid&15, tid>>4) owns a 4x4 pixel block
+#define SS_TX 64             // output tile (pixels of level l)
+#define SS_TY 64
+// g_l patch P0: rows Y in [y0-6, y0+70), columns X in [x0-8, x0+72) (the reduce needs x0-6..x0+68; the two
+// extra columns on the left make every global row segment 8/16-byte aligned)
+#define SS_P0W 80
+#define SS_P0H 76
+#define SS_P0S 84            // row stride (floats): 84 mod 32 = 20 -> 8 consecutive rows hit 8 distinct 16-byte bank groups
+#define SS_P0P (SS_P0H * SS_P0S + 8)   // plane stride (floats)
+#define SS_P0X 8             // column of X = x0 in the patch
+#define SS_P0Y 6             // row of Y = y0
+// g_{l+1} patch P1: I in [y0/2-2, y0/2+34), J in [x0/2-2, x0/2+34); column jj is stored at jj + 1 so that the
+// expand stage's 4-column windows (jj = 2tx+1..2tx+4) are 8-byte aligned
+#define SS_P1W 36
+#define SS_P1H 36
+#define SS_P1S 40
+#define SS_P1P (SS_P1H * SS_P1S + 4)
+#define SS_P1O 1
+// gray^2 patch SQ: rows y in [y0-2, y0+66), columns x in [x0-2, x0+66)
+#define SS_SQW 68
+#define SS_SQH 68
+#define SS_SQS 72
+#define SS_SMEM_FLOATS (3 * SS_P0P + 3 * SS_P1P + SS_SQH * SS_SQS)
 
 struct SsLevelParams {
-    // level l geometry
     int h, w;            // size of g_l
     int h2, w2;          // size of g_{l+1} = ceil(h/2), ceil(w/2)
     // input g_l: level 0 -> interleaved BGR samples (uint8/uint16), else planar float32
-    const void *in;      // first frame of the batch
-    long long in_frame_stride;   // bytes between frames
-    long long in_plane_stride;   // planar only: bytes between channel planes
-    int in_pitch;                // bytes per row
+    const void *in;      // first frame of the batch (16-byte aligned)
+    long long in_frame_stride;   // bytes between frames (multiple of 16)
+    long long in_plane_stride;   // planar only: bytes between channel planes (multiple of 16)
+    int in_pitch;                // bytes per row (multiple of 16)
     // output g_{l+1}: planar float32, one slot per frame of the batch
     float *gnext;
     long long gnext_frame_stride;  // floats
@@ -88,12 +115,6 @@ SS_DEV int ss_reflect_clamp(int i, int n)
     return i;
 }
 
-template <bool TAIL>
-SS_DEV float ss_mac(float v, float k, float acc)
-{
-    return TAIL ? ss_add(acc, ss_mul(v, k)) : ss_fma(v, k, acc);
-}
-
 template <typename InT>
 SS_DEV void ss_load_px(const SsLevelParams &p, const char *frame, int y, int x, float &b, float &g,
                        float &r)
@@ -109,25 +130,120 @@ SS_DEV void ss_load_px(const SsLevelParams &p, const char *frame, int y, int x, 
     }
 }
 
-// 25-tap chain on a patch with row stride S, taps at rows r0..r0+4, columns c0..c0+4.
-template <bool TAIL, int S>
-SS_DEV float ss_conv25(const float *patch, int r0, int c0, const float *k25)
+// ---- generic (any border / tail column) per-output helpers ------------------------------------------
+SS_DEV float ss_conv25_generic(const float *patch, int stride, const float *k25, bool tail)
 {
     float acc = 0.f;
+    if (tail) {
 #pragma unroll
-    for (int dy = 0; dy < 5; ++dy)
+        for (int dy = 0; dy < 5; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 5; ++dx)
-            acc = ss_mac<TAIL>(patch[(r0 + dy) * S + c0 + dx], k25[dy * 5 + dx], acc);
+            for (int dx = 0; dx < 5; ++dx)
+                acc = ss_add(acc, ss_mul(patch[dy * stride + dx], k25[dy * 5 + dx]));
+    } else {
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) acc = ss_fma(patch[dy * stride + dx], k25[dy * 5 + dx], acc);
+    }
     return acc;
 }
 
+// Laplacian of one pixel (qq,pp in SQ coordinates, image coordinates y,x), all three channels; returns
+// gray^2.
+SS_DEV float ss_lap_px_generic(const float *P0, const float *P1, const float *k25, int qq, int pp, int y,
+                               int x, int i0, int j0, bool tail, float lap[3])
+{
+    for (int ch = 0; ch < 3; ++ch) {
+        const float *g1 = P1 + ch * SS_P1P;
+        float acc = 0.f;
+        for (int dy = -2; dy <= 2; ++dy) {
+            const int zy = y + dy;
+            if (zy & 1) continue;
+            const int ii = (zy >> 1) - i0;
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int zx = x + dx;
+                if (zx & 1) continue;
+                const int jj = (zx >> 1) - j0;
+                const float v = g1[ii * SS_P1S + jj + SS_P1O], k = k25[(dy + 2) * 5 + dx + 2];
+                acc = tail ? ss_add(acc, ss_mul(v, k)) : ss_fma(v, k, acc);
+            }
+        }
+        // g - 4*acc with one rounding == the reference's (4*acc, exact) followed by the subtraction
+        lap[ch] = ss_fma(-4.f, acc, P0[ch * SS_P0P + (qq + SS_P0Y - 2) * SS_P0S + pp + SS_P0X - 2]);
+    }
+    const float gray = ss_fma(lap[2], 0.299f, ss_fma(lap[0], 0.114f, ss_mul(lap[1], 0.587f)));
+    return ss_mul(gray, gray);
+}
+
+// ---- fast-path register-blocked stages ---------------------------------------------------------------
+// S1 item: one channel, 3 output rows x 6 output columns of g_{l+1}.  Input rows 2*ii0 .. 2*ii0+8 of the
+// P0 patch stream through registers; each row feeds the (up to three) output rows whose 5-row window
+// contains it, so every chain still sees its taps in row-major order.
+SS_DEV void ss_reduce_block(const float *p0c, int ii0, int jj0, const float *k25, float acc[18])
+{
+#pragma unroll
+    for (int i = 0; i < 18; ++i) acc[i] = 0.f;
+    // taps of output jj are patch columns 2*jj + 2 .. 2*jj + 6 (SS_P0X = 8 and j0 = x0/2 - 2)
+    const float *base = p0c + (2 * ii0) * SS_P0S + 2 * jj0 + 2;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const ss_f2 t = *(const ss_f2 *)(base + r * SS_P0S + 2 * q);
+            v[2 * q] = t.x; v[2 * q + 1] = t.y;
+        }
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const int dy = r - 2 * o;
+            if (dy < 0 || dy > 4) continue;
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx)
+                    acc[o * 6 + c] = ss_fma(v[2 * c + dx], k25[dy * 5 + dx], acc[o * 6 + c]);
+        }
+    }
+}
+
+// Expand taps for an N x N pixel block whose top-left pixel has even image coordinates (N = 2 or 4), one
+// channel.  win[a][b] holds g_{l+1} rows (q0-2)/2 + a and columns (p0-2)/2 + b, a,b < N/2 + 2; output (r,c)
+// uses window rows r/2+{0,1,2} with kernel rows {0,2,4} when r is even and rows (r+1)/2+{0,1} with kernel
+// rows {1,3} when r is odd (same for the columns): exactly the taps of the zero-stuffed 5x5 filter that do
+// not hit a stuffed zero, in row-major order.
+template <int N>
+SS_DEV void ss_expand_block(const float (*win)[N / 2 + 2], const float *k25, float *acc)
+{
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int ty = 0; ty < 3; ++ty) {
+                if ((r & 1) && ty == 2) continue;
+                const int wr = (r & 1) ? (r + 1) / 2 + ty : r / 2 + ty;
+                const int ky = (r & 1) ? 1 + 2 * ty : 2 * ty;
+#pragma unroll
+                for (int tx = 0; tx < 3; ++tx) {
+                    if ((c & 1) && tx == 2) continue;
+                    const int wc = (c & 1) ? (c + 1) / 2 + tx : c / 2 + tx;
+                    const int kx = (c & 1) ? 1 + 2 * tx : 2 * tx;
+                    a = ss_fma(win[wr][wc], k25[ky * 5 + kx], a);
+                }
+            }
+            acc[r * N + c] = a;
+        }
+}
+
 // The fused level step for one tile: for every frame of the batch
-//   S0  g_l patch (halo 6, REFLECT101 at the image border)              -> smem P0
-//   S1  g_{l+1} = reduce(g_l) on the patch (reference pyramid.py:27-32) -> smem P1 + global (interior)
-//   S2  lap = g_l - 4*expand(g_{l+1}) (pyramid.py:34-46,133-138), gray^2 (pyramid.py:49-50) -> smem SQ, LAP
-//   S3  energy = filter(gray^2); running strict-'>' arg-max (pyramid.py:50-54) in registers
-// and finally the running state goes back to global memory.
+//   S0  g_l patch (REFLECT101 at the image border)                        -> smem P0
+//   S1  g_{l+1} = reduce(g_l) on the patch (reference pyramid.py:27-32)   -> smem P1 (interior -> global)
+//   S2  lap = g_l - 4*expand(g_{l+1}) (pyramid.py:34-46,133-138) parked in place of g_l in P0,
+//       gray^2 (pyramid.py:49-50)                                         -> smem SQ
+//   S3  energy = filter(gray^2); running strict-'>' arg-max (pyramid.py:50-54): best energy in registers,
+//       winner index / coefficients (0 + lap) written to global memory when a pixel's best changes
 template <typename InT>
 #ifndef SS_HOST_EMU
 __device__ __forceinline__
@@ -137,35 +253,35 @@ static inline
 void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
 {
     float *P0 = smem;
-    float *P1 = P0 + 3 * SS_P0H * SS_P0S;
-    float *SQ = P1 + 3 * SS_P1H * SS_P1S;
-    float *LAP = SQ + SS_SQH * SS_SQS;
+    float *P1 = P0 + 3 * SS_P0P;
+    float *SQ = P1 + 3 * SS_P1P;
     const int x0 = tile_x * SS_TX, y0 = tile_y * SS_TY;
-    const int w_vec = p.w - (p.w % 8);              // FMA columns of the reduce / energy filters
+    const int w_vec = p.w - (p.w % 8);                // FMA columns of the reduce / energy filters
     const int wz = 2 * p.w2, wz_vec = wz - (wz % 8);  // ... of the expand filter (width 2*w2)
     const int j0 = x0 / 2 - 2, i0 = y0 / 2 - 2;       // g_{l+1} coordinates of P1[0][0]
-    // does any patch position of this tile fall outside the images?
-    const bool border = (x0 < 6) || (y0 < 6) || (x0 + SS_TX + 6 > p.w) || (y0 + SS_TY + 6 > p.h);
+    // every patch position inside the images?  (else REFLECT101 loads + fix-up passes)
+    const bool interior = (x0 >= SS_P0X) && (y0 >= SS_P0Y) && (x0 + SS_TX + 8 <= p.w) &&
+                          (y0 + SS_TY + 6 <= p.h) && (x0 / 2 + SS_TX / 2 + 2 <= p.w2) &&
+                          (y0 / 2 + SS_TY / 2 + 2 <= p.h2);
+    // no output of this tile in any stage falls on a tail (mul+add) column?  Then the register-blocked
+    // stages are used; at image borders they also evaluate out-of-image positions (finite junk computed
+    // from clamped data) which the fix-up passes overwrite or which are never stored.
+    const bool fast = (x0 + SS_TX + 4 <= w_vec) && (x0 + SS_TX + 4 <= wz_vec);
+    const bool full = (x0 + SS_TX <= p.w) && (y0 + SS_TY <= p.h);
+    const long long plane_px = (long long)p.h * p.w;
 
-    SS_PT_DECL(float, be, 8);
-    SS_PT_DECL(int, bi, 8);
-    SS_PT_DECL(float, bl, 24);
+    SS_PT_DECL(float, be, 16);
 
-    // thread -> owned 4x2 pixel block
     if (!p.init) {
         SS_THREADS(tid)
         {
             const int tx = tid & 15, ty = tid >> 4;
-            for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int x = x0 + 4 * tx + c, y = y0 + 2 * ty + r, q = r * 4 + c;
-                    if (x < p.w && y < p.h) {
-                        const long long o = (long long)y * p.w + x;
-                        SS_PT(be)[q] = p.best_e[o];
-                        SS_PT(bi)[q] = p.best_idx[o];
-                        for (int ch = 0; ch < 3; ++ch)
-                            SS_PT(bl)[ch * 8 + q] = p.fused[(long long)ch * p.h * p.w + o];
-                    }
+                    const int x = x0 + 4 * tx + c, y = y0 + 4 * ty + r;
+                    if (x < p.w && y < p.h) SS_PT(be)[r * 4 + c] = p.best_e[(long long)y * p.w + x];
                 }
         }
     }
@@ -173,39 +289,109 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
     for (int f = 0; f < p.n_frames; ++f) {
         const char *frame = (const char *)p.in + (long long)f * p.in_frame_stride;
         // ---- S0: g_l patch -------------------------------------------------------------------------
-        SS_THREADS(tid)
-        {
-            for (int i = tid; i < SS_P0H * SS_P0W; i += SS_NT) {
-                const int r = i / SS_P0W, c = i - r * SS_P0W;
-                const int y = ss_reflect_clamp(y0 - 6 + r, p.h), x = ss_reflect_clamp(x0 - 6 + c, p.w);
-                float b, g, rr;
-                ss_load_px<InT>(p, frame, y, x, b, g, rr);
-                P0[(0 * SS_P0H + r) * SS_P0S + c] = b;
-                P0[(1 * SS_P0H + r) * SS_P0S + c] = g;
-                P0[(2 * SS_P0H + r) * SS_P0S + c] = rr;
+        // item -> (row r = i % 76, unit u = i / 76): consecutive threads write consecutive patch rows, which
+        // the row stride of 84 floats spreads over distinct bank groups (conflict-free 16-byte stores)
+        if (interior) {
+            SS_THREADS(tid)
+            {
+                if constexpr (sizeof(InT) == 1) {
+                    // unit = 8 pixels = 24 bytes = 3 x 8-byte loads (8-byte aligned: (x0-8)*3 = 8*k)
+                    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
+                        const int u = i / SS_P0H, r = i - u * SS_P0H;
+                        const char *src = frame + (long long)(y0 - SS_P0Y + r) * p.in_pitch +
+                                          (x0 - SS_P0X) * 3 + u * 24;
+                        const ss_u2 a = *(const ss_u2 *)src, b = *(const ss_u2 *)(src + 8),
+                                    c = *(const ss_u2 *)(src + 16);
+                        const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                        float v[3][8];
+#pragma unroll
+                        for (int k = 0; k < 24; ++k)
+                            v[k % 3][k / 3] = (float)((wd[k >> 2] >> (8 * (k & 3))) & 0xffu);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float *dst = P0 + ch * SS_P0P + r * SS_P0S + u * 8;
+                            *(ss_f4 *)dst = ss_mk4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+                            *(ss_f4 *)(dst + 4) = ss_mk4(v[ch][4], v[ch][5], v[ch][6], v[ch][7]);
+                        }
+                    }
+                } else if constexpr (sizeof(InT) == 2) {
+                    // unit = 8 pixels = 48 bytes = 3 x 16-byte loads
+                    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
+                        const int u = i / SS_P0H, r = i - u * SS_P0H;
+                        const char *src = frame + (long long)(y0 - SS_P0Y + r) * p.in_pitch +
+                                          (x0 - SS_P0X) * 6 + u * 48;
+                        const ss_u4 a = *(const ss_u4 *)src, b = *(const ss_u4 *)(src + 16),
+                                    c = *(const ss_u4 *)(src + 32);
+                        const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                        float v[3][8];
+#pragma unroll
+                        for (int k = 0; k < 24; ++k)
+                            v[k % 3][k / 3] = (float)((wd[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float *dst = P0 + ch * SS_P0P + r * SS_P0S + u * 8;
+                            *(ss_f4 *)dst = ss_mk4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+                            *(ss_f4 *)(dst + 4) = ss_mk4(v[ch][4], v[ch][5], v[ch][6], v[ch][7]);
+                        }
+                    }
+                } else {
+                    // planar float32: unit = 4 floats of one channel row (16-byte aligned)
+                    for (int i = tid; i < 3 * SS_P0H * 20; i += SS_NT) {
+                        const int cu = i / SS_P0H, r = i - cu * SS_P0H;
+                        const int ch = cu / 20, u = cu - ch * 20;
+                        const char *src = frame + ch * p.in_plane_stride +
+                                          (long long)(y0 - SS_P0Y + r) * p.in_pitch + (x0 - SS_P0X) * 4 + u * 16;
+                        *(ss_f4 *)(P0 + ch * SS_P0P + r * SS_P0S + u * 4) = *(const ss_f4 *)src;
+                    }
+                }
+            }
+        } else {
+            SS_THREADS(tid)
+            {
+                for (int i = tid; i < SS_P0H * SS_P0W; i += SS_NT) {
+                    const int r = i / SS_P0W, c = i - r * SS_P0W;
+                    const int y = ss_reflect_clamp(y0 - SS_P0Y + r, p.h);
+                    const int x = ss_reflect_clamp(x0 - SS_P0X + c, p.w);
+                    float b, g, rr;
+                    ss_load_px<InT>(p, frame, y, x, b, g, rr);
+                    P0[0 * SS_P0P + r * SS_P0S + c] = b;
+                    P0[1 * SS_P0P + r * SS_P0S + c] = g;
+                    P0[2 * SS_P0P + r * SS_P0S + c] = rr;
+                }
             }
         }
         SS_SYNC();
-        // ---- S1: reduce -> P1 (in-image positions), interior -> global -----------------------------
-        SS_THREADS(tid)
-        {
-            for (int i = tid; i < 3 * SS_P1H * SS_P1W; i += SS_NT) {
-                const int ch = i / (SS_P1H * SS_P1W), rem = i - ch * (SS_P1H * SS_P1W);
-                const int ii = rem / SS_P1W, jj = rem - ii * SS_P1W;
-                const int I = i0 + ii, J = j0 + jj;
-                if (I < 0 || I >= p.h2 || J < 0 || J >= p.w2) continue;
-                const float *patch = P0 + ch * SS_P0H * SS_P0S;
-                float v;
-                if (2 * J >= w_vec) v = ss_conv25<true, SS_P0S>(patch, 2 * ii, 2 * jj, p.k25);
-                else v = ss_conv25<false, SS_P0S>(patch, 2 * ii, 2 * jj, p.k25);
-                P1[(ch * SS_P1H + ii) * SS_P1S + jj] = v;
-                if (ii >= 2 && ii < SS_P1H - 2 && jj >= 2 && jj < SS_P1W - 2)
-                    p.gnext[f * p.gnext_frame_stride + ch * p.gnext_plane_stride +
-                            (long long)I * p.gnext_pitch + J] = v;
+        // ---- S1: reduce -> P1 ------------------------------------------------------------------------
+        if (fast) {
+            SS_THREADS(tid)
+            {
+                if (tid < 216) {
+                    const int cb = tid % 6, t2 = tid / 6, ch = t2 % 3, rb = t2 / 3;
+                    const int ii0 = 3 * rb, jj0 = 6 * cb;
+                    float acc[18];
+                    ss_reduce_block(P0 + ch * SS_P0P, ii0, jj0, p.k25, acc);
+                    float *dst = P1 + ch * SS_P1P + ii0 * SS_P1S + jj0 + SS_P1O;
+#pragma unroll
+                    for (int o = 0; o < 3; ++o)
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) dst[o * SS_P1S + c] = acc[o * 6 + c];
+                }
+            }
+        } else {
+            SS_THREADS(tid)
+            {
+                for (int i = tid; i < 3 * SS_P1H * SS_P1W; i += SS_NT) {
+                    const int ch = i / (SS_P1H * SS_P1W), rem = i - ch * (SS_P1H * SS_P1W);
+                    const int ii = rem / SS_P1W, jj = rem - ii * SS_P1W;
+                    const int I = i0 + ii, J = j0 + jj;
+                    if (I < 0 || I >= p.h2 || J < 0 || J >= p.w2) continue;
+                    P1[ch * SS_P1P + ii * SS_P1S + jj + SS_P1O] =
+                        ss_conv25_generic(P0 + ch * SS_P0P + 2 * ii * SS_P0S + 2 * jj + 2, SS_P0S, p.k25, 2 * J >= w_vec);
+                }
             }
         }
         SS_SYNC();
-        if (border) {
+        if (!interior) {
             // out-of-image g_{l+1} positions as the expand filter sees them: the stuffed image has size
             // 2*h2 x 2*w2 and REFLECT101 on it maps even index -2 -> 2 (J=-1 -> 1) and 2*w2 -> 2*w2-2
             // (J=w2 -> w2-1).
@@ -221,53 +407,124 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
                     if (Is < 0 || Is >= p.h2 || Js < 0 || Js >= p.w2) continue;  // only junk needs it
                     const int is = Is - i0, js = Js - j0;
                     if (is < 0 || is >= SS_P1H || js < 0 || js >= SS_P1W) continue;
-                    P1[(ch * SS_P1H + ii) * SS_P1S + jj] = P1[(ch * SS_P1H + is) * SS_P1S + js];
+                    P1[ch * SS_P1P + ii * SS_P1S + jj + SS_P1O] = P1[ch * SS_P1P + is * SS_P1S + js + SS_P1O];
                 }
             }
             SS_SYNC();
         }
-        // ---- S2: Laplacian, gray, square -----------------------------------------------------------
+        // ---- S2: g_{l+1} interior -> global; Laplacian (parked in P0), gray^2 -> SQ ----------------------
         SS_THREADS(tid)
         {
-            for (int i = tid; i < SS_SQH * SS_SQW; i += SS_NT) {
-                const int qq = i / SS_SQW, pp = i - qq * SS_SQW;
-                const int y = y0 - 2 + qq, x = x0 - 2 + pp;
-                if (y < 0 || y >= p.h || x < 0 || x >= p.w) continue;
-                const bool tail = x >= wz_vec;
-                float lap[3];
+            // the 32 x 32 interior of P1 is this tile's share of g_{l+1}: coalesced row segments
+            float *gdst = p.gnext + f * p.gnext_frame_stride;
+            for (int i = tid; i < 3 * 32 * 32; i += SS_NT) {
+                const int ch = i >> 10, ii = 2 + ((i >> 5) & 31), jj = 2 + (i & 31);
+                const int I = i0 + ii, J = j0 + jj;
+                if (interior || (I < p.h2 && J < p.w2))
+                    gdst[ch * p.gnext_plane_stride + (long long)I * p.gnext_pitch + J] =
+                        P1[ch * SS_P1P + ii * SS_P1S + jj + SS_P1O];
+            }
+        }
+        if (fast) {
+            SS_THREADS(tid)
+            {
+                const int tx = tid & 15, ty = tid >> 4;
+                // own 4x4 block
+                float gsq[16];
+                {
+                    float l3[3][16];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float *g1 = P1 + ch * SS_P1H * SS_P1S;
-                    float acc = 0.f;
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float win[4][4], acc[16];
 #pragma unroll
-                    for (int dy = -2; dy <= 2; ++dy) {
-                        const int zy = y + dy;
-                        if (zy & 1) continue;
-                        const int ii = (zy >> 1) - i0;
+                        for (int a = 0; a < 4; ++a) {
+                            const float *src = P1 + ch * SS_P1P + (2 * ty + 1 + a) * SS_P1S + 2 * tx + 1 + SS_P1O;
+                            const ss_f2 u = *(const ss_f2 *)src, v = *(const ss_f2 *)(src + 2);
+                            win[a][0] = u.x; win[a][1] = u.y; win[a][2] = v.x; win[a][3] = v.y;
+                        }
+                        ss_expand_block<4>(win, p.k25, acc);
 #pragma unroll
-                        for (int dx = -2; dx <= 2; ++dx) {
-                            const int zx = x + dx;
-                            if (zx & 1) continue;
-                            const int jj = (zx >> 1) - j0;
-                            const float v = g1[ii * SS_P1S + jj], k = p.k25[(dy + 2) * 5 + dx + 2];
-                            acc = tail ? ss_mac<true>(v, k, acc) : ss_mac<false>(v, k, acc);
+                        for (int r = 0; r < 4; ++r) {
+                            float *gp = P0 + ch * SS_P0P + (4 * ty + r + SS_P0Y) * SS_P0S + 4 * tx + SS_P0X;
+                            const ss_f4 g = *(const ss_f4 *)gp;
+                            l3[ch][r * 4 + 0] = ss_fma(-4.f, acc[r * 4 + 0], g.x);
+                            l3[ch][r * 4 + 1] = ss_fma(-4.f, acc[r * 4 + 1], g.y);
+                            l3[ch][r * 4 + 2] = ss_fma(-4.f, acc[r * 4 + 2], g.z);
+                            l3[ch][r * 4 + 3] = ss_fma(-4.f, acc[r * 4 + 3], g.w);
+                            // park the Laplacian in place of g_l: this position is read by no other thread
+                            *(ss_f4 *)gp = ss_mk4(l3[ch][r * 4], l3[ch][r * 4 + 1], l3[ch][r * 4 + 2], l3[ch][r * 4 + 3]);
                         }
                     }
-                    const float e = ss_mul(4.f, acc);
-                    lap[ch] = ss_sub(P0[(ch * SS_P0H + qq + 4) * SS_P0S + pp + 4], e);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float gray = ss_fma(l3[2][q], 0.299f, ss_fma(l3[0][q], 0.114f, ss_mul(l3[1][q], 0.587f)));
+                        gsq[q] = ss_mul(gray, gray);
+                    }
                 }
-                const float gray = ss_fma(lap[2], 0.299f, ss_fma(lap[0], 0.114f, ss_mul(lap[1], 0.587f)));
-                SQ[qq * SS_SQS + pp] = ss_mul(gray, gray);
-                if (qq >= 2 && qq < SS_SQH - 2 && pp >= 2 && pp < SS_SQW - 2) {
-                    const int o = (qq - 2) * SS_LPS + pp - 2;
-                    LAP[o] = lap[0];
-                    LAP[SS_TY * SS_LPS + o] = lap[1];
-                    LAP[2 * SS_TY * SS_LPS + o] = lap[2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float *dst = SQ + (4 * ty + r + 2) * SS_SQS + 4 * tx + 2;
+                    *(ss_f2 *)dst = ss_mk2(gsq[r * 4], gsq[r * 4 + 1]);
+                    *(ss_f2 *)(dst + 2) = ss_mk2(gsq[r * 4 + 2], gsq[r * 4 + 3]);
+                }
+                // halo ring of SQ (2 pixels wide): 132 aligned 2x2 quads
+                if (tid < 132) {
+                    int qq, pp;
+                    if (tid < 34) { qq = 0; pp = 2 * tid; }                         // top strip
+                    else if (tid < 68) { qq = SS_SQH - 2; pp = 2 * (tid - 34); }     // bottom strip
+                    else if (tid < 100) { qq = 2 + 2 * (tid - 68); pp = 0; }         // left strip
+                    else { qq = 2 + 2 * (tid - 100); pp = SS_SQW - 2; }              // right strip
+                    float l3[3][4];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float win[3][3], acc[4];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+#pragma unroll
+                            for (int b = 0; b < 3; ++b)
+                                win[a][b] = P1[ch * SS_P1P + (qq / 2 + a) * SS_P1S + pp / 2 + b + SS_P1O];
+                        ss_expand_block<2>(win, p.k25, acc);
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                                l3[ch][r * 2 + c] = ss_fma(-4.f, acc[r * 2 + c],
+                                    P0[ch * SS_P0P + (qq + r + SS_P0Y - 2) * SS_P0S + pp + c + SS_P0X - 2]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float gray = ss_fma(l3[2][q], 0.299f, ss_fma(l3[0][q], 0.114f, ss_mul(l3[1][q], 0.587f)));
+                        SQ[(qq + (q >> 1)) * SS_SQS + pp + (q & 1)] = ss_mul(gray, gray);
+                    }
+                }
+            }
+        } else {
+            SS_THREADS(tid)
+            {
+                const int tx = tid & 15, ty = tid >> 4;
+                for (int q = 0; q < 16; ++q) {
+                    const int qq = 4 * ty + (q >> 2) + 2, pp = 4 * tx + (q & 3) + 2;
+                    const int y = y0 - 2 + qq, x = x0 - 2 + pp;
+                    if (y >= p.h || x >= p.w) continue;
+                    float lap[3];
+                    SQ[qq * SS_SQS + pp] = ss_lap_px_generic(P0, P1, p.k25, qq, pp, y, x, i0, j0, x >= wz_vec, lap);
+                    for (int ch = 0; ch < 3; ++ch)
+                        P0[ch * SS_P0P + (qq + SS_P0Y - 2) * SS_P0S + pp + SS_P0X - 2] = lap[ch];
+                }
+                for (int i = tid; i < 4 * (SS_SQW + SS_SQH - 4); i += SS_NT) {
+                    int qq, pp;
+                    if (i < 2 * SS_SQW) { qq = i / SS_SQW; pp = i - qq * SS_SQW; }
+                    else if (i < 4 * SS_SQW) { const int k = i - 2 * SS_SQW; qq = SS_SQH - 2 + k / SS_SQW; pp = k % SS_SQW; }
+                    else { const int k = i - 4 * SS_SQW; qq = 2 + (k >> 2); pp = (k & 3) < 2 ? (k & 3) : SS_SQW - 4 + (k & 3); }
+                    const int y = y0 - 2 + qq, x = x0 - 2 + pp;
+                    if (y < 0 || y >= p.h || x < 0 || x >= p.w) continue;
+                    float lap[3];
+                    SQ[qq * SS_SQS + pp] = ss_lap_px_generic(P0, P1, p.k25, qq, pp, y, x, i0, j0, x >= wz_vec, lap);
                 }
             }
         }
         SS_SYNC();
-        if (border) {
+        if (!interior) {
             // out-of-image gray^2 positions: REFLECT101 of the energy filter at the size of g_l
             SS_THREADS(tid)
             {
@@ -291,43 +548,71 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
             const int tx = tid & 15, ty = tid >> 4;
             const int gidx = p.frame_index0 + f;
             const bool take_all = p.init && f == 0;
+            float e[16];
+            if (fast) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+                for (int q = 0; q < 16; ++q) e[q] = 0.f;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int xx = 4 * tx + c, yy = 2 * ty + r, q = r * 4 + c;
-                    const int x = x0 + xx, y = y0 + yy;
-                    if (x >= p.w || y >= p.h) continue;
-                    float e;
-                    if (x >= w_vec) e = ss_conv25<true, SS_SQS>(SQ, yy, xx, p.k25);
-                    else e = ss_conv25<false, SS_SQS>(SQ, yy, xx, p.k25);
-                    if (take_all || e > SS_PT(be)[q]) {
-                        SS_PT(be)[q] = e;
-                        SS_PT(bi)[q] = gidx;
-                        const int o = yy * SS_LPS + xx;
-                        SS_PT(bl)[q] = ss_add(0.f, LAP[o]);
-                        SS_PT(bl)[8 + q] = ss_add(0.f, LAP[SS_TY * SS_LPS + o]);
-                        SS_PT(bl)[16 + q] = ss_add(0.f, LAP[2 * SS_TY * SS_LPS + o]);
+                for (int r = 0; r < 8; ++r) {
+                    const float *src = SQ + (4 * ty + r) * SS_SQS + 4 * tx;
+                    const ss_f4 a = *(const ss_f4 *)src, b = *(const ss_f4 *)(src + 4);
+                    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        const int dy = r - o;
+                        if (dy < 0 || dy > 4) continue;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+#pragma unroll
+                            for (int dx = 0; dx < 5; ++dx)
+                                e[o * 4 + c] = ss_fma(v[c + dx], p.k25[dy * 5 + dx], e[o * 4 + c]);
                     }
                 }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int yy = 4 * ty + (q >> 2), xx = 4 * tx + (q & 3);
+                    e[q] = ss_conv25_generic(SQ + yy * SS_SQS + xx, SS_SQS, p.k25, x0 + xx >= w_vec);
+                }
+            }
+            unsigned won = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const bool inb = full || ((x0 + 4 * tx + (q & 3) < p.w) && (y0 + 4 * ty + (q >> 2) < p.h));
+                if (inb && (take_all || e[q] > SS_PT(be)[q])) {
+                    SS_PT(be)[q] = e[q];
+                    won |= 1u << q;
+                }
+            }
+            if (won) {
+                const long long o0 = (long long)(y0 + 4 * ty) * p.w + x0 + 4 * tx;
+                const float *lsrc = P0 + (4 * ty + SS_P0Y) * SS_P0S + 4 * tx + SS_P0X;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    if (won & (1u << q)) {
+                        const long long o = o0 + (long long)(q >> 2) * p.w + (q & 3);
+                        const float *ls = lsrc + (q >> 2) * SS_P0S + (q & 3);
+                        p.best_idx[o] = gidx;
+                        p.fused[o] = ss_add(0.f, ls[0]);
+                        p.fused[plane_px + o] = ss_add(0.f, ls[SS_P0P]);
+                        p.fused[2 * plane_px + o] = ss_add(0.f, ls[2 * SS_P0P]);
+                    }
+                }
+            }
         }
-        // no barrier needed here: the next frame's S0/S1 only overwrite P0/P1 (last read in S2, two
-        // barriers ago); SQ/LAP are rewritten in S2, two barriers after this S3.
+        // S3 reads the parked Laplacians from P0, so it must finish before the next frame's S0
+        SS_SYNC();
     }
 
     SS_THREADS(tid)
     {
         const int tx = tid & 15, ty = tid >> 4;
-        for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int x = x0 + 4 * tx + c, y = y0 + 2 * ty + r, q = r * 4 + c;
-                if (x < p.w && y < p.h) {
-                    const long long o = (long long)y * p.w + x;
-                    p.best_e[o] = SS_PT(be)[q];
-                    p.best_idx[o] = SS_PT(bi)[q];
-                    for (int ch = 0; ch < 3; ++ch)
-                        p.fused[(long long)ch * p.h * p.w + o] = SS_PT(bl)[ch * 8 + q];
-                }
+                const int x = x0 + 4 * tx + c, y = y0 + 4 * ty + r;
+                if (x < p.w && y < p.h) p.best_e[(long long)y * p.w + x] = SS_PT(be)[r * 4 + c];
             }
     }
 }

@@ -41,7 +41,7 @@ static int ss_fail(int code, const char *fmt, ...)
 // kernels
 // ---------------------------------------------------------------------------------------------------
 template <typename InT>
-__global__ void __launch_bounds__(SS_NT) ss_level_kernel(const __grid_constant__ SsLevelParams p)
+__global__ void __launch_bounds__(SS_NT, 2) ss_level_kernel(const __grid_constant__ SsLevelParams p)
 {
     extern __shared__ float ss_smem[];
     ss_level_tile<InT>(p, blockIdx.x, blockIdx.y, ss_smem);
@@ -278,6 +278,7 @@ struct SsLevel {
     int32_t *best_idx = nullptr;
     float *fused = nullptr;  // 3 planes
     float *gnext = nullptr;  // scratch: g_{l+1} of the frames of one batch (unused for the last level)
+    int gpitch = 0;          // row pitch of gnext in floats (multiple of 4: 16-byte aligned rows)
 };
 
 struct ss_handle {
@@ -457,8 +458,9 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
         if ((rc = ss_dalloc(&v.best_e, n))) return rc;
         if ((rc = ss_dalloc(&v.best_idx, n))) return rc;
         if ((rc = ss_dalloc(&v.fused, 3 * n))) return rc;
+        v.gpitch = (h->lw[l + 1] + 3) / 4 * 4;
         if (l + 1 < h->L)
-            if ((rc = ss_dalloc(&v.gnext, (size_t)h->batch * 3 * h->lh[l + 1] * h->lw[l + 1]))) return rc;
+            if ((rc = ss_dalloc(&v.gnext, (size_t)h->batch * 3 * h->lh[l + 1] * v.gpitch))) return rc;
         h->n_keys += n;
     }
     const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
@@ -597,14 +599,13 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
             p.in_pitch = (int)h->frame_pitch;
         } else {
             p.in = h->lv[l - 1].gnext;
-            p.in_pitch = v.w * 4;
-            p.in_plane_stride = (long long)v.h * v.w * 4;
+            p.in_pitch = h->lv[l - 1].gpitch * 4;
+            p.in_plane_stride = (long long)v.h * p.in_pitch;
             p.in_frame_stride = 3 * p.in_plane_stride;
         }
-        if (l + 1 < h->L) p.gnext = v.gnext;
-        else p.gnext = h->base + (size_t)f0 * 3 * nb;
-        p.gnext_pitch = p.w2;
-        p.gnext_plane_stride = (long long)p.h2 * p.w2;
+        if (l + 1 < h->L) { p.gnext = v.gnext; p.gnext_pitch = v.gpitch; }
+        else { p.gnext = h->base + (size_t)f0 * 3 * nb; p.gnext_pitch = p.w2; }  // base level: tightly packed
+        p.gnext_plane_stride = (long long)p.h2 * p.gnext_pitch;
         p.gnext_frame_stride = 3 * p.gnext_plane_stride;
         p.best_e = v.best_e; p.best_idx = v.best_idx; p.fused = v.fused;
         p.n_frames = nf;
@@ -900,10 +901,11 @@ SS_EXPORT int ss_get_gauss_level(ss_handle *h, int level, int frame, float *out_
 {
     if (!h || !out_planes || level < 1 || level > h->L) return ss_fail(SS_ERR_STATE, "bad argument");
     SS_CUDA(cudaSetDevice(h->cfg.device));
-    const size_t n = 3 * (size_t)h->lh[level] * h->lw[level];
-    const float *src = level < h->L ? h->lv[level - 1].gnext + (size_t)frame * n : h->base + (size_t)frame * n;
+    const size_t rows = 3 * (size_t)h->lh[level], wbytes = (size_t)h->lw[level] * sizeof(float);
+    const size_t pitch = level < h->L ? (size_t)h->lv[level - 1].gpitch : (size_t)h->lw[level];
+    const float *src = (level < h->L ? h->lv[level - 1].gnext : h->base) + (size_t)frame * rows * pitch;
     SS_CUDA(cudaStreamSynchronize(h->s_comp));
-    SS_CUDA(cudaMemcpy(out_planes, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+    SS_CUDA(cudaMemcpy2D(out_planes, wbytes, src, pitch * sizeof(float), wbytes, rows, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -8,19 +8,21 @@
 #include <string.h>
 
 extern "C" int emu_level(const void *in, int bytes_per_sample /*1,2: interleaved; 4: planar f32*/,
-                         int n_frames, int h, int w, const float *k25, float *gnext, float *best_e,
-                         int32_t *best_idx, float *fused, int frame_index0, int init)
+                         int in_pitch_bytes, int n_frames, int h, int w, const float *k25, float *gnext,
+                         int gnext_pitch, float *best_e, int32_t *best_idx, float *fused, int frame_index0,
+                         int init)
 {
     SsLevelParams p;
     memset(&p, 0, sizeof(p));
     p.h = h; p.w = w; p.h2 = (h + 1) / 2; p.w2 = (w + 1) / 2;
     p.in = in;
+    p.in_pitch = in_pitch_bytes;
     if (bytes_per_sample == 4) {
-        p.in_pitch = w * 4; p.in_plane_stride = (long long)h * w * 4; p.in_frame_stride = 3 * p.in_plane_stride;
+        p.in_plane_stride = (long long)h * in_pitch_bytes; p.in_frame_stride = 3 * p.in_plane_stride;
     } else {
-        p.in_pitch = w * 3 * bytes_per_sample; p.in_frame_stride = (long long)h * p.in_pitch;
+        p.in_frame_stride = (long long)h * p.in_pitch;
     }
-    p.gnext = gnext; p.gnext_pitch = p.w2; p.gnext_plane_stride = (long long)p.h2 * p.w2;
+    p.gnext = gnext; p.gnext_pitch = gnext_pitch; p.gnext_plane_stride = (long long)p.h2 * gnext_pitch;
     p.gnext_frame_stride = 3 * p.gnext_plane_stride;
     p.best_e = best_e; p.best_idx = best_idx; p.fused = fused;
     p.n_frames = n_frames; p.frame_index0 = frame_index0; p.init = init;

@@ -33,22 +33,28 @@ def run_levels(emu, oracle, frames, split=None):
     h, w = frames[0].shape[:2]
     k = oracle.make_kernel(0.4)
     levels = oracle.num_levels(h, w)
-    cur = np.ascontiguousarray(np.stack(frames))
     bps = frames[0].dtype.itemsize
+    # level-0 frames with a 16-byte aligned row pitch, like the library's frame store
+    pitch = (w * 3 * bps + 15) // 16 * 16
+    cur = np.zeros((n, h, pitch), np.uint8)
+    for i, f in enumerate(frames):
+        cur[i, :, :w * 3 * bps] = f.reshape(h, -1).view(np.uint8)
+    in_pitch = pitch
     res = []
     for l in range(levels):
         h2, w2 = (h + 1) // 2, (w + 1) // 2
-        gnext = np.full((n, 3, h2, w2), np.nan, np.float32)
+        gp = (w2 + 3) // 4 * 4
+        gnext = np.full((n, 3, h2, gp), np.nan, np.float32)
         be = np.full((h, w), np.nan, np.float32)
         bi = np.full((h, w), -1, np.int32)
         fu = np.full((3, h, w), np.nan, np.float32)
         batches = [(0, n)] if not split else [(a, min(a + split, n)) for a in range(0, n, split)]
         for a, b in batches:
-            emu.emu_level(_p(cur[a:b]), bps if l == 0 else 4, b - a, h, w, _p(k), _p(gnext[a:b]), _p(be),
-                          _p(bi), _p(fu), a, int(a == 0))
+            emu.emu_level(_p(cur[a:b]), bps if l == 0 else 4, in_pitch, b - a, h, w, _p(k), _p(gnext[a:b]), gp,
+                          _p(be), _p(bi), _p(fu), a, int(a == 0))
         res.append((bi, fu))
-        cur, h, w = gnext, h2, w2
-    return res, cur
+        cur, h, w, in_pitch = gnext, h2, w2, gp * 4
+    return res, cur[:, :, :, :w]
 
 
 @pytest.mark.parametrize("gen,n,h,w,dtype,seed,split", [
@@ -58,6 +64,9 @@ def run_levels(emu, oracle, frames, split=None):
     ("noise", 5, 300, 407, np.uint8, 4, 3),
     ("noise", 2, 70, 66, np.uint8, 6, None),
     ("noise", 3, 64, 375, np.uint8, 7, 1),
+    ("noise", 2, 288, 512, np.uint8, 8, None),      # interior (fast-path) tiles at levels 0 and 1
+    ("stack", 3, 300, 448, np.uint16, 9, 2),
+    ("noise", 2, 384, 700, np.uint8, 10, None),     # interior tile + tail columns (700 % 8 == 4)
 ])
 def test_emulated_level_kernel_matches_oracle(emu, oracle, gen, n, h, w, dtype, seed, split):
     f = synthetic.make_stack if gen == "stack" else synthetic.make_noise_stack

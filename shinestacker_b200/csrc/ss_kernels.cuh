@@ -55,6 +55,25 @@ typedef uint2 ss_u2;
 typedef uint4 ss_u4;
 #endif
 
+// 8-byte asynchronous global -> shared copy (LDGSTS) and its completion wait
+#ifdef SS_HOST_EMU
+SS_DEV void ss_cp_async8(void *dst, const void *src) { memcpy(dst, src, 8); }
+SS_DEV void ss_cp_async16(void *dst, const void *src) { memcpy(dst, src, 16); }
+SS_DEV void ss_cp_async_wait() {}
+#else
+SS_DEV void ss_cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+SS_DEV void ss_cp_async8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+SS_DEV void ss_cp_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+#endif
+
 SS_DEV ss_f2 ss_mk2(float a, float b) { ss_f2 r; r.x = a; r.y = b; return r; }
 SS_DEV ss_f4 ss_mk4(float a, float b, float c, float d) { ss_f4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 
@@ -67,7 +86,9 @@ SS_DEV ss_f4 ss_mk4(float a, float b, float c, float d) { ss_f4 r; r.x = a; r.y 
 #define SS_P0W 80
 #define SS_P0H 76
 #define SS_P0S 84            // row stride (floats): 84 mod 32 = 20 -> 8 consecutive rows hit 8 distinct 16-byte bank groups
-#define SS_P0P (SS_P0H * SS_P0S + 8)   // plane stride (floats)
+#define SS_P0P (SS_P0H * SS_P0S + 24)  // plane stride (floats), = 8 mod 32: with the reduce stage's lane order
+                                       // (6 column blocks x 3 channels x row blocks) the 16-byte shared loads of
+                                       // consecutive lanes advance by 48 bytes mod 128 -> conflict-free
 #define SS_P0X 8             // column of X = x0 in the patch
 #define SS_P0Y 6             // row of Y = y0
 // g_{l+1} patch P1: I in [y0/2-2, y0/2+34), J in [x0/2-2, x0/2+34); column jj is stored at jj + 1 so that the
@@ -81,7 +102,12 @@ SS_DEV ss_f4 ss_mk4(float a, float b, float c, float d) { ss_f4 r; r.x = a; r.y 
 #define SS_SQW 68
 #define SS_SQH 68
 #define SS_SQS 72
-#define SS_SMEM_FLOATS (3 * SS_P0P + 3 * SS_P1P + SS_SQH * SS_SQS)
+// uint8 frames: the raw bytes of the NEXT frame's patch (76 rows x 240 bytes, row stride 248 bytes so that
+// 8-byte shared loads of consecutive rows are conflict-free) are copied asynchronously into the P1 region
+// while the energy stage of the current frame runs (P1 is dead by then)
+#define SS_RAWS 248
+#define SS_P1REGION ((SS_P0H * SS_RAWS + 3) / 4 > 3 * SS_P1P ? (SS_P0H * SS_RAWS + 3) / 4 : 3 * SS_P1P)
+#define SS_SMEM_FLOATS (3 * SS_P0P + SS_P1REGION + SS_SQH * SS_SQS)
 
 struct SsLevelParams {
     int h, w;            // size of g_l
@@ -103,6 +129,11 @@ struct SsLevelParams {
     int n_frames;        // frames in this batch
     int frame_index0;    // global index of the first frame of the batch
     int init;            // 1: the batch starts the stack (no prior state)
+    // frame-split for small levels: blockIdx.z = g handles frames [g*n/G, (g+1)*n/G) with a private state
+    // slice (offset g*group_stride elements; planes of `fused` stay h*w apart) that always starts fresh;
+    // ss_merge_groups_kernel folds the slices into the running state in frame order.
+    int groups;
+    long long group_stride;
     float k25[25];
 };
 
@@ -186,14 +217,23 @@ SS_DEV void ss_reduce_block(const float *p0c, int ii0, int jj0, const float *k25
     for (int i = 0; i < 18; ++i) acc[i] = 0.f;
     // taps of output jj are patch columns 2*jj + 2 .. 2*jj + 6 (SS_P0X = 8 and j0 = x0/2 - 2)
     const float *base = p0c + (2 * ii0) * SS_P0S + 2 * jj0 + 2;
+    float vv[2][16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const ss_f2 t = *(const ss_f2 *)(base + 2 * q);
+        vv[0][2 * q] = t.x; vv[0][2 * q + 1] = t.y;
+    }
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
-        float v[16];
+        // next row's shared loads are issued before this row's FMAs (latency hidden by ~90 FMAs)
+        if (r + 1 < 9) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const ss_f2 t = *(const ss_f2 *)(base + r * SS_P0S + 2 * q);
-            v[2 * q] = t.x; v[2 * q + 1] = t.y;
+            for (int q = 0; q < 8; ++q) {
+                const ss_f2 t = *(const ss_f2 *)(base + (r + 1) * SS_P0S + 2 * q);
+                vv[(r + 1) & 1][2 * q] = t.x; vv[(r + 1) & 1][2 * q + 1] = t.y;
+            }
         }
+        const float *v = vv[r & 1];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
             const int dy = r - 2 * o;
@@ -237,6 +277,123 @@ SS_DEV void ss_expand_block(const float (*win)[N / 2 + 2], const float *k25, flo
         }
 }
 
+// Conversion of 8-pixel units (24 / 48 bytes) into the planar float patch.  item i -> (unit u = i / 76, row
+// r = i % 76): consecutive threads handle consecutive patch rows, which the row stride of 84 floats spreads
+// over distinct bank groups (conflict-free 16-byte shared stores).
+SS_DEV void ss_s0_store_unit(float *P0, int r, int u, const float v[3][8])
+{
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float *dst = P0 + ch * SS_P0P + r * SS_P0S + u * 8;
+        *(ss_f4 *)dst = ss_mk4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+        *(ss_f4 *)(dst + 4) = ss_mk4(v[ch][4], v[ch][5], v[ch][6], v[ch][7]);
+    }
+}
+
+// ---- S0 helpers (interior tiles) --------------------------------------------------------------------------
+// uint8: asynchronous copy of the raw patch bytes (rows y0-6.., byte columns (x0-8)*3 .. +240; 8-byte aligned
+// because (x0-8)*3 = 8*k) into the staging area.
+SS_DEV void ss_s0_async_u8(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, char *raw)
+{
+    const int c = tid & 31, r0 = tid >> 5;   // chunk column (30 used), first row; rows advance by 8
+    if (c >= 30) return;
+    const char *src = frame + (long long)(y0 - SS_P0Y + r0) * p.in_pitch + (x0 - SS_P0X) * 3 + 8 * c;
+    char *dst = raw + r0 * SS_RAWS + 8 * c;
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+        if (r0 + 8 * k < SS_P0H)
+            ss_cp_async8(dst + 8 * k * SS_RAWS, src + (long long)(8 * k) * p.in_pitch);
+}
+
+// uint16: the raw patch (76 rows x 480 bytes, row stride 496) is staged in the P1 + SQ regions, which are
+// both dead between the energy stage of one frame and the reduce stage of the next.
+#define SS_RAWS16 496
+SS_DEV void ss_s0_async_u16(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, char *raw)
+{
+    const int c = tid & 31, r0 = tid >> 5;   // 16-byte chunk column (30 used), first row
+    if (c >= 30) return;
+    const char *src = frame + (long long)(y0 - SS_P0Y + r0) * p.in_pitch + (x0 - SS_P0X) * 6 + 16 * c;
+    char *dst = raw + r0 * SS_RAWS16 + 16 * c;
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+        if (r0 + 8 * k < SS_P0H)
+            ss_cp_async16(dst + 8 * k * SS_RAWS16, src + (long long)(8 * k) * p.in_pitch);
+}
+
+SS_DEV void ss_s0_convert_u16(float *P0, int tid, const char *raw)
+{
+    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
+        const int u = i / SS_P0H, r = i - u * SS_P0H;
+        const char *src = raw + r * SS_RAWS16 + u * 48;
+        const ss_u4 a = *(const ss_u4 *)src, b = *(const ss_u4 *)(src + 16), c = *(const ss_u4 *)(src + 32);
+        const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        float v[3][8];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+        ss_s0_store_unit(P0, r, u, v);
+    }
+}
+
+// float32 planes: the patch rows are copied straight into P0 (16-byte chunks, all in flight at once).
+SS_DEV void ss_s0_async_f32(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0)
+{
+    const int c = tid & 31, r0 = tid >> 5;   // 16-byte chunk column (20 used), first row
+    if (c >= 20) return;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const char *src = frame + ch * p.in_plane_stride + (long long)(y0 - SS_P0Y + r0) * p.in_pitch +
+                          (x0 - SS_P0X) * 4 + 16 * c;
+        float *dst = P0 + ch * SS_P0P + r0 * SS_P0S + 4 * c;
+#pragma unroll
+        for (int k = 0; k < 10; ++k)
+            if (r0 + 8 * k < SS_P0H)
+                ss_cp_async16(dst + 8 * k * SS_P0S, src + (long long)(8 * k) * p.in_pitch);
+    }
+}
+
+SS_DEV void ss_s0_convert_u8(float *P0, int tid, const char *raw)
+{
+    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
+        const int u = i / SS_P0H, r = i - u * SS_P0H;
+        const char *src = raw + r * SS_RAWS + u * 24;
+        const ss_u2 a = *(const ss_u2 *)src, b = *(const ss_u2 *)(src + 8), c = *(const ss_u2 *)(src + 16);
+        const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+        float v[3][8];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        ss_s0_store_unit(P0, r, u, v);
+    }
+}
+
+SS_DEV void ss_s0_direct_u8(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0)
+{
+    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
+        const int u = i / SS_P0H, r = i - u * SS_P0H;
+        const char *src = frame + (long long)(y0 - SS_P0Y + r) * p.in_pitch + (x0 - SS_P0X) * 3 + u * 24;
+        const ss_u2 a = *(const ss_u2 *)src, b = *(const ss_u2 *)(src + 8), c = *(const ss_u2 *)(src + 16);
+        const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+        float v[3][8];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        ss_s0_store_unit(P0, r, u, v);
+    }
+}
+
+SS_DEV void ss_s0_direct_u16(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0)
+{
+    // unit = 8 pixels = 48 bytes = 3 x 16-byte loads (16-byte aligned: (x0-8)*6 = 16*k)
+    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
+        const int u = i / SS_P0H, r = i - u * SS_P0H;
+        const char *src = frame + (long long)(y0 - SS_P0Y + r) * p.in_pitch + (x0 - SS_P0X) * 6 + u * 48;
+        const ss_u4 a = *(const ss_u4 *)src, b = *(const ss_u4 *)(src + 16), c = *(const ss_u4 *)(src + 32);
+        const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        float v[3][8];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+        ss_s0_store_unit(P0, r, u, v);
+    }
+}
+
 // The fused level step for one tile: for every frame of the batch
 //   S0  g_l patch (REFLECT101 at the image border)                        -> smem P0
 //   S1  g_{l+1} = reduce(g_l) on the patch (reference pyramid.py:27-32)   -> smem P1 (interior -> global)
@@ -250,11 +407,11 @@ __device__ __forceinline__
 #else
 static inline
 #endif
-void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
+void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, int group, float *smem)
 {
     float *P0 = smem;
     float *P1 = P0 + 3 * SS_P0P;
-    float *SQ = P1 + 3 * SS_P1P;
+    float *SQ = P1 + SS_P1REGION;
     const int x0 = tile_x * SS_TX, y0 = tile_y * SS_TY;
     const int w_vec = p.w - (p.w % 8);                // FMA columns of the reduce / energy filters
     const int wz = 2 * p.w2, wz_vec = wz - (wz % 8);  // ... of the expand filter (width 2*w2)
@@ -269,10 +426,24 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
     const bool fast = (x0 + SS_TX + 4 <= w_vec) && (x0 + SS_TX + 4 <= wz_vec);
     const bool full = (x0 + SS_TX <= p.w) && (y0 + SS_TY <= p.h);
     const long long plane_px = (long long)p.h * p.w;
+    const int f_begin = p.groups > 1 ? (int)((long long)group * p.n_frames / p.groups) : 0;
+    const int f_end = p.groups > 1 ? (int)((long long)(group + 1) * p.n_frames / p.groups) : p.n_frames;
+    const bool fresh = p.init || p.groups > 1;
+    float *const st_e = p.best_e + group * p.group_stride;
+    int32_t *const st_idx = p.best_idx + group * p.group_stride;
+    float *const st_fused = p.fused + 3 * group * p.group_stride;
 
     SS_PT_DECL(float, be, 16);
 
-    if (!p.init) {
+    if (interior && sizeof(InT) == 1) {
+        SS_THREADS(tid)
+        {
+            ss_s0_async_u8(p, (const char *)p.in + (long long)f_begin * p.in_frame_stride, x0, y0, tid, (char *)P1);
+            ss_cp_async_wait();
+        }
+        SS_SYNC();
+    }
+    if (!fresh) {
         SS_THREADS(tid)
         {
             const int tx = tid & 15, ty = tid >> 4;
@@ -281,69 +452,32 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int x = x0 + 4 * tx + c, y = y0 + 4 * ty + r;
-                    if (x < p.w && y < p.h) SS_PT(be)[r * 4 + c] = p.best_e[(long long)y * p.w + x];
+                    if (x < p.w && y < p.h) SS_PT(be)[r * 4 + c] = st_e[(long long)y * p.w + x];
                 }
         }
     }
 
-    for (int f = 0; f < p.n_frames; ++f) {
+    for (int f = f_begin; f < f_end; ++f) {
         const char *frame = (const char *)p.in + (long long)f * p.in_frame_stride;
         // ---- S0: g_l patch -------------------------------------------------------------------------
-        // item -> (row r = i % 76, unit u = i / 76): consecutive threads write consecutive patch rows, which
-        // the row stride of 84 floats spreads over distinct bank groups (conflict-free 16-byte stores)
         if (interior) {
             SS_THREADS(tid)
             {
                 if constexpr (sizeof(InT) == 1) {
-                    // unit = 8 pixels = 24 bytes = 3 x 8-byte loads (8-byte aligned: (x0-8)*3 = 8*k)
-                    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
-                        const int u = i / SS_P0H, r = i - u * SS_P0H;
-                        const char *src = frame + (long long)(y0 - SS_P0Y + r) * p.in_pitch +
-                                          (x0 - SS_P0X) * 3 + u * 24;
-                        const ss_u2 a = *(const ss_u2 *)src, b = *(const ss_u2 *)(src + 8),
-                                    c = *(const ss_u2 *)(src + 16);
-                        const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                        float v[3][8];
-#pragma unroll
-                        for (int k = 0; k < 24; ++k)
-                            v[k % 3][k / 3] = (float)((wd[k >> 2] >> (8 * (k & 3))) & 0xffu);
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            float *dst = P0 + ch * SS_P0P + r * SS_P0S + u * 8;
-                            *(ss_f4 *)dst = ss_mk4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
-                            *(ss_f4 *)(dst + 4) = ss_mk4(v[ch][4], v[ch][5], v[ch][6], v[ch][7]);
-                        }
-                    }
+                    // the raw bytes were copied asynchronously during the previous energy stage (or, for
+                    // the first frame, just before the loop)
+                    ss_s0_convert_u8(P0, tid, (const char *)P1);
                 } else if constexpr (sizeof(InT) == 2) {
-                    // unit = 8 pixels = 48 bytes = 3 x 16-byte loads
-                    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
-                        const int u = i / SS_P0H, r = i - u * SS_P0H;
-                        const char *src = frame + (long long)(y0 - SS_P0Y + r) * p.in_pitch +
-                                          (x0 - SS_P0X) * 6 + u * 48;
-                        const ss_u4 a = *(const ss_u4 *)src, b = *(const ss_u4 *)(src + 16),
-                                    c = *(const ss_u4 *)(src + 32);
-                        const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-                        float v[3][8];
-#pragma unroll
-                        for (int k = 0; k < 24; ++k)
-                            v[k % 3][k / 3] = (float)((wd[k >> 1] >> (16 * (k & 1))) & 0xffffu);
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            float *dst = P0 + ch * SS_P0P + r * SS_P0S + u * 8;
-                            *(ss_f4 *)dst = ss_mk4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
-                            *(ss_f4 *)(dst + 4) = ss_mk4(v[ch][4], v[ch][5], v[ch][6], v[ch][7]);
-                        }
-                    }
+                    ss_s0_async_u16(p, frame, x0, y0, tid, (char *)P1);
+                    ss_cp_async_wait();
                 } else {
-                    // planar float32: unit = 4 floats of one channel row (16-byte aligned)
-                    for (int i = tid; i < 3 * SS_P0H * 20; i += SS_NT) {
-                        const int cu = i / SS_P0H, r = i - cu * SS_P0H;
-                        const int ch = cu / 20, u = cu - ch * 20;
-                        const char *src = frame + ch * p.in_plane_stride +
-                                          (long long)(y0 - SS_P0Y + r) * p.in_pitch + (x0 - SS_P0X) * 4 + u * 16;
-                        *(ss_f4 *)(P0 + ch * SS_P0P + r * SS_P0S + u * 4) = *(const ss_f4 *)src;
-                    }
+                    ss_s0_async_f32(p, frame, x0, y0, tid, P0);
+                    ss_cp_async_wait();
                 }
+            }
+            if constexpr (sizeof(InT) == 2) {
+                SS_SYNC();
+                SS_THREADS(tid) { ss_s0_convert_u16(P0, tid, (const char *)P1); }
             }
         } else {
             SS_THREADS(tid)
@@ -415,14 +549,20 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
         // ---- S2: g_{l+1} interior -> global; Laplacian (parked in P0), gray^2 -> SQ ----------------------
         SS_THREADS(tid)
         {
-            // the 32 x 32 interior of P1 is this tile's share of g_{l+1}: coalesced row segments
-            float *gdst = p.gnext + f * p.gnext_frame_stride;
-            for (int i = tid; i < 3 * 32 * 32; i += SS_NT) {
-                const int ch = i >> 10, ii = 2 + ((i >> 5) & 31), jj = 2 + (i & 31);
-                const int I = i0 + ii, J = j0 + jj;
-                if (interior || (I < p.h2 && J < p.w2))
-                    gdst[ch * p.gnext_plane_stride + (long long)I * p.gnext_pitch + J] =
-                        P1[ch * SS_P1P + ii * SS_P1S + jj + SS_P1O];
+            // the 32 x 32 interior of P1 is this tile's share of g_{l+1}: coalesced row segments; thread ->
+            // (row tid>>5 (+8m), column tid&31) of every channel, so all offsets below are compile-time
+            const int ii = 2 + (tid >> 5), jj = 2 + (tid & 31);
+            const int I = i0 + ii, J = j0 + jj;
+            float *gdst = p.gnext + f * p.gnext_frame_stride + (long long)I * p.gnext_pitch + J;
+            const float *gsrc = P1 + ii * SS_P1S + jj + SS_P1O;
+            if (J < p.w2) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        if (interior || I + 8 * m < p.h2)
+                            gdst[ch * p.gnext_plane_stride + (long long)(8 * m) * p.gnext_pitch] =
+                                gsrc[ch * SS_P1P + 8 * m * SS_P1S];
             }
         }
         if (fast) {
@@ -547,16 +687,28 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
         {
             const int tx = tid & 15, ty = tid >> 4;
             const int gidx = p.frame_index0 + f;
-            const bool take_all = p.init && f == 0;
+            const bool take_all = fresh && f == f_begin;
+            if (interior && sizeof(InT) == 1 && f + 1 < f_end)
+                ss_s0_async_u8(p, frame + p.in_frame_stride, x0, y0, tid, (char *)P1);   // P1 is dead until S1
             float e[16];
             if (fast) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) e[q] = 0.f;
+                const float *src = SQ + (4 * ty) * SS_SQS + 4 * tx;
+                float vv[2][8];
+                {
+                    const ss_f4 a = *(const ss_f4 *)src, b = *(const ss_f4 *)(src + 4);
+                    vv[0][0] = a.x; vv[0][1] = a.y; vv[0][2] = a.z; vv[0][3] = a.w;
+                    vv[0][4] = b.x; vv[0][5] = b.y; vv[0][6] = b.z; vv[0][7] = b.w;
+                }
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const float *src = SQ + (4 * ty + r) * SS_SQS + 4 * tx;
-                    const ss_f4 a = *(const ss_f4 *)src, b = *(const ss_f4 *)(src + 4);
-                    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    if (r + 1 < 8) {
+                        const ss_f4 a = *(const ss_f4 *)(src + (r + 1) * SS_SQS), b = *(const ss_f4 *)(src + (r + 1) * SS_SQS + 4);
+                        float *n = vv[(r + 1) & 1];
+                        n[0] = a.x; n[1] = a.y; n[2] = a.z; n[3] = a.w; n[4] = b.x; n[5] = b.y; n[6] = b.z; n[7] = b.w;
+                    }
+                    const float *v = vv[r & 1];
 #pragma unroll
                     for (int o = 0; o < 4; ++o) {
                         const int dy = r - o;
@@ -592,15 +744,19 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
                     if (won & (1u << q)) {
                         const long long o = o0 + (long long)(q >> 2) * p.w + (q & 3);
                         const float *ls = lsrc + (q >> 2) * SS_P0S + (q & 3);
-                        p.best_idx[o] = gidx;
-                        p.fused[o] = ss_add(0.f, ls[0]);
-                        p.fused[plane_px + o] = ss_add(0.f, ls[SS_P0P]);
-                        p.fused[2 * plane_px + o] = ss_add(0.f, ls[2 * SS_P0P]);
+                        st_idx[o] = gidx;
+                        st_fused[o] = ss_add(0.f, ls[0]);
+                        st_fused[plane_px + o] = ss_add(0.f, ls[SS_P0P]);
+                        st_fused[2 * plane_px + o] = ss_add(0.f, ls[2 * SS_P0P]);
                     }
                 }
             }
         }
-        // S3 reads the parked Laplacians from P0, so it must finish before the next frame's S0
+        // S3 reads the parked Laplacians from P0, so it must finish before the next frame's S0; the
+        // asynchronous copies of the next frame's raw patch must have landed as well
+        if (interior && sizeof(InT) == 1) {
+            SS_THREADS(tid) { ss_cp_async_wait(); }
+        }
         SS_SYNC();
     }
 
@@ -612,7 +768,7 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, float *smem)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int x = x0 + 4 * tx + c, y = y0 + 4 * ty + r;
-                if (x < p.w && y < p.h) p.best_e[(long long)y * p.w + x] = SS_PT(be)[r * 4 + c];
+                if (x < p.w && y < p.h) st_e[(long long)y * p.w + x] = SS_PT(be)[r * 4 + c];
             }
     }
 }

@@ -44,7 +44,33 @@ template <typename InT>
 __global__ void __launch_bounds__(SS_NT, 2) ss_level_kernel(const __grid_constant__ SsLevelParams p)
 {
     extern __shared__ float ss_smem[];
-    ss_level_tile<InT>(p, blockIdx.x, blockIdx.y, ss_smem);
+    ss_level_tile<InT>(p, blockIdx.x, blockIdx.y, blockIdx.z, ss_smem);
+}
+
+// Folds the per-group partial states of a frame-split level launch into the running state, groups in
+// frame order with strict '>' (== np.argmax's first-maximum rule over the whole stack).
+__global__ void ss_merge_groups_kernel(size_t n, int groups, const float *g_e, const int32_t *g_idx,
+                                       const float *g_fused, int have_state, float *best_e,
+                                       int32_t *best_idx, float *fused)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float e, c0, c1, c2;
+    int idx, g = 0;
+    if (have_state) {
+        e = best_e[i]; idx = best_idx[i]; c0 = fused[i]; c1 = fused[n + i]; c2 = fused[2 * n + i];
+    } else {
+        e = g_e[i]; idx = g_idx[i]; c0 = g_fused[i]; c1 = g_fused[n + i]; c2 = g_fused[2 * n + i];
+        g = 1;
+    }
+    for (; g < groups; ++g) {
+        const float eg = g_e[(size_t)g * n + i];
+        if (eg > e) {
+            const float *gf = g_fused + 3 * (size_t)g * n;
+            e = eg; idx = g_idx[(size_t)g * n + i]; c0 = gf[i]; c1 = gf[n + i]; c2 = gf[2 * n + i];
+        }
+    }
+    best_e[i] = e; best_idx[i] = idx; fused[i] = c0; fused[n + i] = c1; fused[2 * n + i] = c2;
 }
 
 // img.astype(float32) (reference pyramid.py:126) into planes; only needed when the pyramid has no
@@ -173,53 +199,92 @@ struct SsCollapseParams {
 };
 
 // One collapse step (reference pyramid.py:59-64): img = expand(img)[:h,:w] + layer, the expand being
-// the zero-skipping form of expand_layer (pyramid.py:34-41); the last step also applies
-// clip(abs(img), 0, max) and the truncating cast of pyramid.py:179.
+// the zero-skipping form of expand_layer (pyramid.py:34-41); 4*acc + layer is one fma (4*acc is exact);
+// the last step also applies clip(abs(img), 0, max) and the truncating cast of pyramid.py:179.
+// One thread per aligned 2x2 output quad: its taps are a 3x3 window of the coarser image.
+__device__ __forceinline__ float ss_collapse_px_generic(const float *g, int h2, int w2, int y, int x,
+                                                        const float *k25, bool tail)
+{
+    const int wz = 2 * w2, hz = 2 * h2;
+    float acc = 0.f;
+    for (int dy = -2; dy <= 2; ++dy) {
+        int zy = y + dy;
+        if (zy < 0) zy = -zy;
+        if (zy >= hz) zy = 2 * hz - 2 - zy;
+        if (zy & 1) continue;
+        const float *row = g + (size_t)(zy >> 1) * w2;
+        for (int dx = -2; dx <= 2; ++dx) {
+            int zx = x + dx;
+            if (zx < 0) zx = -zx;
+            if (zx >= wz) zx = 2 * wz - 2 - zx;
+            if (zx & 1) continue;
+            const float t = row[zx >> 1], k = k25[(dy + 2) * 5 + dx + 2];
+            acc = tail ? __fadd_rn(acc, __fmul_rn(t, k)) : __fmaf_rn(t, k, acc);
+        }
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(256) ss_collapse_kernel(const __grid_constant__ SsCollapseParams p)
 {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int qx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int x = 2 * qx, y = 2 * qy;
     if (x >= p.w || y >= p.h) return;
-    const int wz = 2 * p.w2, hz = 2 * p.h2, wz_vec = wz - (wz % 8);
-    const bool tail = x >= wz_vec;
-    float v[3];
+    const int wz = 2 * p.w2, wz_vec = wz - (wz % 8);
+    const bool tail = x + 1 >= wz_vec;
+    float v[3][4];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float *g = p.img + (size_t)ch * p.h2 * p.w2;
-        float acc = 0.f;
+        float acc[4];
+        if (!tail) {
+            // window rows (y-2)/2 + a, columns (x-2)/2 + b; out-of-image indices as REFLECT101 on the
+            // zero-stuffed image sees them: -1 -> 1, h2 -> h2-1
+            float win[3][3];
 #pragma unroll
-        for (int dy = -2; dy <= 2; ++dy) {
-            int zy = y + dy;
-            if (zy < 0) zy = -zy;
-            if (zy >= hz) zy = 2 * hz - 2 - zy;
-            if (zy & 1) continue;
-            const float *row = g + (size_t)(zy >> 1) * p.w2;
+            for (int a = 0; a < 3; ++a) {
+                int I = qy - 1 + a;
+                I = I < 0 ? -I : (I >= p.h2 ? 2 * p.h2 - 1 - I : I);
 #pragma unroll
-            for (int dx = -2; dx <= 2; ++dx) {
-                int zx = x + dx;
-                if (zx < 0) zx = -zx;
-                if (zx >= wz) zx = 2 * wz - 2 - zx;
-                if (zx & 1) continue;
-                const float t = row[zx >> 1], k = p.k25[(dy + 2) * 5 + dx + 2];
-                acc = tail ? __fadd_rn(acc, __fmul_rn(t, k)) : __fmaf_rn(t, k, acc);
+                for (int b = 0; b < 3; ++b) {
+                    int J = qx - 1 + b;
+                    J = J < 0 ? -J : (J >= p.w2 ? 2 * p.w2 - 1 - J : J);
+                    win[a][b] = g[(size_t)I * p.w2 + J];
+                }
             }
+            ss_expand_block<2>(win, p.k25, acc);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                acc[q] = ss_collapse_px_generic(g, p.h2, p.w2, y + (q >> 1), x + (q & 1), p.k25, x + (q & 1) >= wz_vec);
         }
-        float e = __fmul_rn(4.f, acc);
-        if (p.layer) e = __fadd_rn(e, p.layer[((size_t)ch * p.h + y) * p.w + x]);
-        v[ch] = e;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int yy = y + (q >> 1), xx = x + (q & 1);
+            float e;
+            if (p.layer && yy < p.h && xx < p.w) e = __fmaf_rn(4.f, acc[q], p.layer[((size_t)ch * p.h + yy) * p.w + xx]);
+            else e = __fmul_rn(4.f, acc[q]);
+            v[ch][q] = e;
+        }
     }
-    if (!p.final_bytes) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) p.out[((size_t)ch * p.h + y) * p.w + x] = v[ch];
-    } else {
-        const float maxv = p.final_bytes == 1 ? 255.f : 65535.f;
+    for (int q = 0; q < 4; ++q) {
+        const int yy = y + (q >> 1), xx = x + (q & 1);
+        if (yy >= p.h || xx >= p.w) continue;
+        if (!p.final_bytes) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float a = fabsf(v[ch]);
-            a = a > maxv ? maxv : a;   // abs() is never negative; NaN cannot occur
-            const unsigned int u = __float2uint_rz(a);
-            if (p.final_bytes == 1) ((uint8_t *)((char *)p.out_px + (size_t)y * p.out_pitch))[3 * x + ch] = (uint8_t)u;
-            else ((uint16_t *)((char *)p.out_px + (size_t)y * p.out_pitch))[3 * x + ch] = (uint16_t)u;
+            for (int ch = 0; ch < 3; ++ch) p.out[((size_t)ch * p.h + yy) * p.w + xx] = v[ch][q];
+        } else {
+            const float maxv = p.final_bytes == 1 ? 255.f : 65535.f;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float a = fabsf(v[ch][q]);
+                a = a > maxv ? maxv : a;   // abs() is never negative; NaN cannot occur
+                const unsigned int u = __float2uint_rz(a);
+                if (p.final_bytes == 1) ((uint8_t *)((char *)p.out_px + (size_t)yy * p.out_pitch))[3 * xx + ch] = (uint8_t)u;
+                else ((uint16_t *)((char *)p.out_px + (size_t)yy * p.out_pitch))[3 * xx + ch] = (uint16_t)u;
+            }
         }
     }
 }
@@ -279,6 +344,10 @@ struct SsLevel {
     float *fused = nullptr;  // 3 planes
     float *gnext = nullptr;  // scratch: g_{l+1} of the frames of one batch (unused for the last level)
     int gpitch = 0;          // row pitch of gnext in floats (multiple of 4: 16-byte aligned rows)
+    int max_groups = 1;      // frame-split factor for a full batch (levels with too few tiles to fill the GPU)
+    float *grp_e = nullptr;  // per-group partial states (max_groups slices) when max_groups > 1
+    int32_t *grp_idx = nullptr;
+    float *grp_fused = nullptr;
 };
 
 struct ss_handle {
@@ -402,6 +471,7 @@ SS_EXPORT void ss_destroy(ss_handle *h)
     if (h->s_copy) cudaStreamSynchronize(h->s_copy);
     for (auto &l : h->lv) {
         cudaFree(l.best_e); cudaFree(l.best_idx); cudaFree(l.fused); cudaFree(l.gnext);
+        cudaFree(l.grp_e); cudaFree(l.grp_idx); cudaFree(l.grp_fused);
     }
     cudaFree(h->frames); cudaFree(h->base); cudaFree(h->gray); cudaFree(h->counts);
     cudaFree(h->log_p); cudaFree(h->best_ve); cudaFree(h->best_vd); cudaFree(h->pix_e);
@@ -459,6 +529,19 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
         if ((rc = ss_dalloc(&v.best_idx, n))) return rc;
         if ((rc = ss_dalloc(&v.fused, 3 * n))) return rc;
         v.gpitch = (h->lw[l + 1] + 3) / 4 * 4;
+        {
+            // enough CTAs for ~2 waves of 2 CTAs/SM on 148 SMs
+            const int tiles = ((v.w + SS_TX - 1) / SS_TX) * ((v.h + SS_TY - 1) / SS_TY);
+            int g = (2 * 2 * 148) / tiles;
+            if (g < 1) g = 1;
+            if (g > h->batch) g = h->batch;
+            v.max_groups = g;
+            if (g > 1) {
+                if ((rc = ss_dalloc(&v.grp_e, (size_t)g * n))) return rc;
+                if ((rc = ss_dalloc(&v.grp_idx, (size_t)g * n))) return rc;
+                if ((rc = ss_dalloc(&v.grp_fused, (size_t)g * 3 * n))) return rc;
+            }
+        }
         if (l + 1 < h->L)
             if ((rc = ss_dalloc(&v.gnext, (size_t)h->batch * 3 * h->lh[l + 1] * v.gpitch))) return rc;
         h->n_keys += n;
@@ -607,12 +690,21 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
         else { p.gnext = h->base + (size_t)f0 * 3 * nb; p.gnext_pitch = p.w2; }  // base level: tightly packed
         p.gnext_plane_stride = (long long)p.h2 * p.gnext_pitch;
         p.gnext_frame_stride = 3 * p.gnext_plane_stride;
-        p.best_e = v.best_e; p.best_idx = v.best_idx; p.fused = v.fused;
+        int groups = v.max_groups < nf ? v.max_groups : nf;
+        if (groups < 1) groups = 1;
+        const size_t npx = (size_t)v.h * v.w;
+        if (groups > 1) {
+            p.best_e = v.grp_e; p.best_idx = v.grp_idx; p.fused = v.grp_fused;
+            p.group_stride = (long long)npx;
+        } else {
+            p.best_e = v.best_e; p.best_idx = v.best_idx; p.fused = v.fused;
+        }
+        p.groups = groups;
         p.n_frames = nf;
         p.frame_index0 = h->cfg.frame_index_base + f0;
         p.init = h->have_state ? 0 : 1;
         memcpy(p.k25, h->k25, sizeof(p.k25));
-        dim3 grid((v.w + SS_TX - 1) / SS_TX, (v.h + SS_TY - 1) / SS_TY);
+        dim3 grid((v.w + SS_TX - 1) / SS_TX, (v.h + SS_TY - 1) / SS_TY, groups);
         const size_t smem = SS_SMEM_FLOATS * sizeof(float);
         if (h->profile) {
             if (h->ltimers_used == h->ltimers.size()) {
@@ -631,6 +723,11 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
         else
             ss_level_kernel<float><<<grid, SS_NT, smem, h->s_comp>>>(p);
         h->launches++;
+        if (groups > 1) {
+            ss_merge_groups_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, h->s_comp>>>(
+                npx, groups, v.grp_e, v.grp_idx, v.grp_fused, h->have_state ? 1 : 0, v.best_e, v.best_idx, v.fused);
+            h->launches++;
+        }
         if (h->profile) {
             SS_CUDA(cudaEventRecord(h->ltimers[h->ltimers_used].b, h->s_comp));
             h->ltimers_used++;
@@ -827,7 +924,7 @@ SS_EXPORT int ss_finish_collapse(ss_handle *h, void *out_bgr, size_t out_row_pit
         } else {
             p.out = (img == h->tmp_a) ? h->tmp_b : h->tmp_a;
         }
-        dim3 g((p.w + 63) / 64, (p.h + 3) / 4);
+        dim3 g((p.w + 63) / 64, (p.h + 15) / 16);
         ss_collapse_kernel<<<g, 256, 0, h->s_comp>>>(p);
         h->launches++;
         img = p.out;
@@ -1068,7 +1165,7 @@ SS_EXPORT int ss_test_collapse_step(const float *img_planes, int h2, int w2, con
     p.img = d_img; p.layer = d_lay; p.out = d_out;
     p.h = h; p.w = w; p.h2 = h2; p.w2 = w2;
     ss_make_kernel(gen_kernel, p.k25);
-    dim3 g((w + 63) / 64, (h + 3) / 4);
+    dim3 g((w + 63) / 64, (h + 15) / 16);
     ss_collapse_kernel<<<g, 256>>>(p);
     SS_CUDA(cudaGetLastError());
     SS_CUDA(cudaMemcpy(out_planes, d_out, n * 4, cudaMemcpyDeviceToHost));

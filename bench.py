@@ -25,6 +25,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -302,6 +303,7 @@ def main():
                     "h2d_bytes_per_step": N * frame_bytes + N * 4 * (256 if b == 1 else 65536),
                     "d2h_bytes_per_step": frame_bytes + N * 4 * (256 if b == 1 else 65536),
                     "matches_resident_result": same},
+            "output_crc32": int(zlib.crc32(out.tobytes())),
             "gpu_launches": launches,
             "device_chain_ms_per_step": chain_ms / a.steps,
             "roofline": {"bound": "hbm", "kernel": "ss_level_kernel (level 0: reduce + expand/Laplacian + "

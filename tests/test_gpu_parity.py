@@ -167,3 +167,53 @@ def test_full_width_staircase_properties(dtype, n):
     x0, x1 = (3 * w) // n + 16, (4 * w) // n - 16
     err = np.abs(out[64:-64, x0:x1].astype(np.int64) - ref[64:-64, x0:x1].astype(np.int64))
     assert err.max() <= max(1, maxv // 128)   # coarse levels may come from another (blurred) frame
+
+
+def test_frame_sharding_merge_on_one_gpu(oracle):
+    """Two handles fuse the two halves of a stack (as two ranks would); the library's key packing /
+    loser masking kernels plus a max and a sum over the shards (done here with torch on the same device
+    instead of NCCL) must reproduce the single-handle result bit for bit."""
+    import torch
+    from shinestacker_b200.sharded import ShardedPyramidStack, shard_range, _DevArray
+    from shinestacker_b200.pyramid import log_prob_table, _check
+    n, h, w = 7, 300, 420
+    frames = synthetic.make_noise_stack(n, h, w, np.uint8, 95)
+    frames[4][:50, :60] = frames[2][:50, :60]          # exact ties across the shard boundary
+    ref, info = oracle.focus_stack(frames)
+    world = 2
+    shards, keys, lib = [], [], _native.load()
+    for r in range(world):
+        f0, f1 = shard_range(n, r, world)
+        s = ShardedPyramidStack(r, 1, device=0, batch_frames=2)     # world=1: no collective inside
+        s.world, s.rank = world, r
+        a = PyramidStack(device=0, frame_index_base=f0, keep_depth_maps=False, batch_frames=2)
+        a._set_metadata(frames[0])
+        a._ensure_handle(frames[0].shape, frames[0].dtype, f1 - f0)
+        ring = a._staging(frames[0].nbytes, 4)
+        for i, f in enumerate(frames[f0:f1]):
+            a._push(i, f, ring)
+        counts = np.empty((f1 - f0, 256), dtype=np.int64)
+        _check(lib.ss_finish_begin(a._h, counts.ctypes.data_as(ctypes.c_void_p)))
+        tab = log_prob_table(counts)
+        _check(lib.ss_finish_select_base(a._h, tab.ctypes.data_as(ctypes.c_void_p)))
+        ptr, cnt = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(lib.ss_exchange_keys(a._h, ctypes.byref(ptr), ctypes.byref(cnt)))
+        keys.append(torch.as_tensor(_DevArray(ptr.value, cnt.value, "<i8"), device="cuda:0"))
+        shards.append(a)
+    red = torch.maximum(keys[0], keys[1])
+    coeffs = []
+    for a, k in zip(shards, keys):
+        k.copy_(red)
+        torch.cuda.synchronize()
+        p2, c2 = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(lib.ss_exchange_mask_losers(a._h, ctypes.byref(p2), ctypes.byref(c2)))
+        coeffs.append(torch.as_tensor(_DevArray(p2.value, c2.value, "<f4"), device="cuda:0"))
+    coeffs[0].add_(coeffs[1])
+    torch.cuda.synchronize()
+    root = shards[0]
+    _check(lib.ss_exchange_adopt(root._h))
+    out = np.empty((h, w, 3), np.uint8)
+    _check(lib.ss_finish_collapse(root._h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+    maps = root.get_depth_maps()
+    golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
+                                               best_d=info["best_d"], levels=info["levels"]), "sharded")

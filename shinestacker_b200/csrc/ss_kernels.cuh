@@ -365,31 +365,46 @@ SS_DEV void ss_s0_convert_u8(float *P0, int tid, const char *raw)
     }
 }
 
-SS_DEV void ss_s0_direct_u8(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0)
-{
-    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
-        const int u = i / SS_P0H, r = i - u * SS_P0H;
-        const char *src = frame + (long long)(y0 - SS_P0Y + r) * p.in_pitch + (x0 - SS_P0X) * 3 + u * 24;
-        const ss_u2 a = *(const ss_u2 *)src, b = *(const ss_u2 *)(src + 8), c = *(const ss_u2 *)(src + 16);
-        const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-        float v[3][8];
-#pragma unroll
-        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 2] >> (8 * (k & 3))) & 0xffu);
-        ss_s0_store_unit(P0, r, u, v);
-    }
-}
 
-SS_DEV void ss_s0_direct_u16(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0)
+
+// S0 for tiles that touch an image border: same 8-pixel units as the interior path whenever a unit lies
+// inside the image (vector loads from the REFLECT101-mapped row), per-pixel reflected loads otherwise.
+template <typename InT>
+SS_DEV void ss_s0_border(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0)
 {
-    // unit = 8 pixels = 48 bytes = 3 x 16-byte loads (16-byte aligned: (x0-8)*6 = 16*k)
+#pragma unroll 1
     for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
         const int u = i / SS_P0H, r = i - u * SS_P0H;
-        const char *src = frame + (long long)(y0 - SS_P0Y + r) * p.in_pitch + (x0 - SS_P0X) * 6 + u * 48;
-        const ss_u4 a = *(const ss_u4 *)src, b = *(const ss_u4 *)(src + 16), c = *(const ss_u4 *)(src + 32);
-        const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        const int y = ss_reflect_clamp(y0 - SS_P0Y + r, p.h);
+        const int X = x0 - SS_P0X + 8 * u;
         float v[3][8];
+        if (X >= 0 && X + 8 <= p.w) {
+            if constexpr (sizeof(InT) == 1) {
+                const char *src = frame + (long long)y * p.in_pitch + X * 3;
+                const ss_u2 a = *(const ss_u2 *)src, b = *(const ss_u2 *)(src + 8), c = *(const ss_u2 *)(src + 16);
+                const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
 #pragma unroll
-        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+                for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 2] >> (8 * (k & 3))) & 0xffu);
+            } else if constexpr (sizeof(InT) == 2) {
+                const char *src = frame + (long long)y * p.in_pitch + X * 6;
+                const ss_u4 a = *(const ss_u4 *)src, b = *(const ss_u4 *)(src + 16), c = *(const ss_u4 *)(src + 32);
+                const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const char *src = frame + ch * p.in_plane_stride + (long long)y * p.in_pitch + X * 4;
+                    const ss_f4 a = *(const ss_f4 *)src, b = *(const ss_f4 *)(src + 16);
+                    v[ch][0] = a.x; v[ch][1] = a.y; v[ch][2] = a.z; v[ch][3] = a.w;
+                    v[ch][4] = b.x; v[ch][5] = b.y; v[ch][6] = b.z; v[ch][7] = b.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                ss_load_px<InT>(p, frame, y, ss_reflect_clamp(X + k, p.w), v[0][k], v[1][k], v[2][k]);
+        }
         ss_s0_store_unit(P0, r, u, v);
     }
 }
@@ -480,19 +495,7 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, int group, fl
                 SS_THREADS(tid) { ss_s0_convert_u16(P0, tid, (const char *)P1); }
             }
         } else {
-            SS_THREADS(tid)
-            {
-                for (int i = tid; i < SS_P0H * SS_P0W; i += SS_NT) {
-                    const int r = i / SS_P0W, c = i - r * SS_P0W;
-                    const int y = ss_reflect_clamp(y0 - SS_P0Y + r, p.h);
-                    const int x = ss_reflect_clamp(x0 - SS_P0X + c, p.w);
-                    float b, g, rr;
-                    ss_load_px<InT>(p, frame, y, x, b, g, rr);
-                    P0[0 * SS_P0P + r * SS_P0S + c] = b;
-                    P0[1 * SS_P0P + r * SS_P0S + c] = g;
-                    P0[2 * SS_P0P + r * SS_P0S + c] = rr;
-                }
-            }
+            SS_THREADS(tid) { ss_s0_border<InT>(p, frame, x0, y0, tid, P0); }
         }
         SS_SYNC();
         // ---- S1: reduce -> P1 ------------------------------------------------------------------------

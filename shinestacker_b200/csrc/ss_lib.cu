@@ -40,11 +40,25 @@ static int ss_fail(int code, const char *fmt, ...)
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
+// Tiles that touch an image border do extra work (reflected loads, fix-up passes); they are mapped to the
+// lowest block ids so that they start first and the tail of the launch consists of regular tiles.
+__device__ __forceinline__ void ss_tile_of_block(int b, int nbx, int nby, int &tx, int &ty)
+{
+    if (nbx <= 2 || nby <= 2) { tx = b % nbx; ty = b / nbx; return; }
+    const int nb = 2 * nbx + 2 * (nby - 2);
+    if (b < nbx) { tx = b; ty = 0; }
+    else if (b < 2 * nbx) { tx = b - nbx; ty = nby - 1; }
+    else if (b < nb) { const int k = b - 2 * nbx; tx = (k & 1) ? nbx - 1 : 0; ty = 1 + (k >> 1); }
+    else { const int k = b - nb; tx = 1 + k % (nbx - 2); ty = 1 + k / (nbx - 2); }
+}
+
 template <typename InT>
 __global__ void __launch_bounds__(SS_NT, 2) ss_level_kernel(const __grid_constant__ SsLevelParams p)
 {
     extern __shared__ float ss_smem[];
-    ss_level_tile<InT>(p, blockIdx.x, blockIdx.y, blockIdx.z, ss_smem);
+    int tx, ty;
+    ss_tile_of_block(blockIdx.y * gridDim.x + blockIdx.x, gridDim.x, gridDim.y, tx, ty);
+    ss_level_tile<InT>(p, tx, ty, blockIdx.z, ss_smem);
 }
 
 // Folds the per-group partial states of a frame-split level launch into the running state, groups in
@@ -530,9 +544,10 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
         if ((rc = ss_dalloc(&v.fused, 3 * n))) return rc;
         v.gpitch = (h->lw[l + 1] + 3) / 4 * 4;
         {
-            // enough CTAs for ~2 waves of 2 CTAs/SM on 148 SMs
+            // frame-split so that every level launch has >= ~6 waves of CTAs (2 CTAs/SM x 148 SMs per wave):
+            // border tiles run longer than interior ones and few waves leave the SMs idle at the tail
             const int tiles = ((v.w + SS_TX - 1) / SS_TX) * ((v.h + SS_TY - 1) / SS_TY);
-            int g = (2 * 2 * 148) / tiles;
+            int g = (6 * 2 * 148 + tiles - 1) / tiles;
             if (g < 1) g = 1;
             if (g > h->batch) g = h->batch;
             v.max_groups = g;

@@ -74,6 +74,32 @@ SS_DEV void ss_cp_async8(void *dst, const void *src)
 SS_DEV void ss_cp_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 #endif
 
+// TMA (cp.async.bulk.tensor) + mbarrier primitives: one elected thread brings the raw uint8 patch of the
+// next frame into shared memory with a single instruction; completion is signalled on an mbarrier.
+#ifndef SS_HOST_EMU
+SS_DEV unsigned ss_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+SS_DEV void ss_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ss_saddr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SS_DEV void ss_tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t *bar, unsigned bytes)
+{
+    // order this CTA's earlier generic-proxy accesses to the destination before the async-proxy writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ss_saddr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(ss_saddr(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(ss_saddr(bar))
+                 : "memory");
+}
+SS_DEV void ss_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tSS_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra SS_DONE;\n\tbra SS_WAIT;\n\tSS_DONE:\n\t}" ::"r"(ss_saddr(bar)), "r"(parity)
+                 : "memory");
+}
+#endif
+
 SS_DEV ss_f2 ss_mk2(float a, float b) { ss_f2 r; r.x = a; r.y = b; return r; }
 SS_DEV ss_f4 ss_mk4(float a, float b, float c, float d) { ss_f4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 
@@ -102,12 +128,15 @@ SS_DEV ss_f4 ss_mk4(float a, float b, float c, float d) { ss_f4 r; r.x = a; r.y 
 #define SS_SQW 68
 #define SS_SQH 68
 #define SS_SQS 72
-// uint8 frames: the raw bytes of the NEXT frame's patch (76 rows x 240 bytes, row stride 248 bytes so that
-// 8-byte shared loads of consecutive rows are conflict-free) are copied asynchronously into the P1 region
+// uint8 frames: the raw bytes of the NEXT frame's patch (76 rows x 240 bytes, dense: it is one TMA box) are
+// copied asynchronously into the P1 region
 // while the energy stage of the current frame runs (P1 is dead by then)
-#define SS_RAWS 248
-#define SS_P1REGION ((SS_P0H * SS_RAWS + 3) / 4 > 3 * SS_P1P ? (SS_P0H * SS_RAWS + 3) / 4 : 3 * SS_P1P)
-#define SS_SMEM_FLOATS (3 * SS_P0P + SS_P1REGION + SS_SQH * SS_SQS)
+#define SS_RAWS 240
+#define SS_P1REGION 4712   // floats: >= 3 * SS_P1P (4332) and >= 76 * 240 / 4 (4560); also the front part of the
+                           // 76 x 496-byte uint16 staging area that continues into SQ
+#define SS_P1OFF ((3 * SS_P0P + 31) / 32 * 32)   // P1 / raw staging starts 128-byte aligned (TMA destination)
+#define SS_SMEM_FLOATS (SS_P1OFF + SS_P1REGION + SS_SQH * SS_SQS)
+#define SS_SMEM_BYTES (SS_SMEM_FLOATS * 4 + 16)   // + the mbarrier
 
 struct SsLevelParams {
     int h, w;            // size of g_l
@@ -134,6 +163,8 @@ struct SsLevelParams {
     // ss_merge_groups_kernel folds the slices into the running state in frame order.
     int groups;
     long long group_stride;
+    int tma_row0;        // uint8 level 0: row of the batch's first frame in the frame-store tensor map (rows of
+                         // that store begin 8 bytes into their pitch, so byte column 8 + 3*(x0-8) is 16-byte aligned)
     float k25[25];
 };
 
@@ -422,10 +453,10 @@ __device__ __forceinline__
 #else
 static inline
 #endif
-void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, int group, float *smem)
+void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int tile_y, int group, float *smem)
 {
     float *P0 = smem;
-    float *P1 = P0 + 3 * SS_P0P;
+    float *P1 = P0 + SS_P1OFF;
     float *SQ = P1 + SS_P1REGION;
     const int x0 = tile_x * SS_TX, y0 = tile_y * SS_TY;
     const int w_vec = p.w - (p.w % 8);                // FMA columns of the reduce / energy filters
@@ -450,6 +481,22 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, int group, fl
 
     SS_PT_DECL(float, be, 16);
 
+    // uint8, interior tiles: raw patch of frame f arrives by TMA (device) / memcpy (host emulation)
+#ifndef SS_HOST_EMU
+    uint64_t *mbar = (uint64_t *)(smem + SS_SMEM_FLOATS);
+    unsigned mbar_phase = 0;
+    if (interior && sizeof(InT) == 1) {
+        if (threadIdx.x == 0) {
+            ss_mbar_init(mbar, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + f_begin * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
+        ss_mbar_wait(mbar, mbar_phase);
+        mbar_phase ^= 1;
+    }
+#else
+    (void)tmap;
     if (interior && sizeof(InT) == 1) {
         SS_THREADS(tid)
         {
@@ -458,6 +505,7 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, int group, fl
         }
         SS_SYNC();
     }
+#endif
     if (!fresh) {
         SS_THREADS(tid)
         {
@@ -552,20 +600,25 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, int group, fl
         // ---- S2: g_{l+1} interior -> global; Laplacian (parked in P0), gray^2 -> SQ ----------------------
         SS_THREADS(tid)
         {
-            // the 32 x 32 interior of P1 is this tile's share of g_{l+1}: coalesced row segments; thread ->
-            // (row tid>>5 (+8m), column tid&31) of every channel, so all offsets below are compile-time
-            const int ii = 2 + (tid >> 5), jj = 2 + (tid & 31);
+            // the 32 x 32 interior of P1 is this tile's share of g_{l+1}: thread -> (row tid>>3, 4 columns
+            // 4*(tid&7)..) of every channel, written as one 16-byte store when the row pitch allows it
+            const int ii = 2 + (tid >> 3), jj = 2 + 4 * (tid & 7);
             const int I = i0 + ii, J = j0 + jj;
             float *gdst = p.gnext + f * p.gnext_frame_stride + (long long)I * p.gnext_pitch + J;
             const float *gsrc = P1 + ii * SS_P1S + jj + SS_P1O;
-            if (J < p.w2) {
+            if (I < p.h2) {
+                if ((p.gnext_pitch & 3) == 0 && J + 4 <= p.w2) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
+                    for (int ch = 0; ch < 3; ++ch)
+                        *(ss_f4 *)(gdst + ch * p.gnext_plane_stride) =
+                            ss_mk4(gsrc[ch * SS_P1P], gsrc[ch * SS_P1P + 1], gsrc[ch * SS_P1P + 2], gsrc[ch * SS_P1P + 3]);
+                } else {
 #pragma unroll
-                    for (int m = 0; m < 4; ++m)
-                        if (interior || I + 8 * m < p.h2)
-                            gdst[ch * p.gnext_plane_stride + (long long)(8 * m) * p.gnext_pitch] =
-                                gsrc[ch * SS_P1P + 8 * m * SS_P1S];
+                    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (J + c < p.w2) gdst[ch * p.gnext_plane_stride + c] = gsrc[ch * SS_P1P + c];
+                }
             }
         }
         if (fast) {
@@ -691,8 +744,14 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, int group, fl
             const int tx = tid & 15, ty = tid >> 4;
             const int gidx = p.frame_index0 + f;
             const bool take_all = fresh && f == f_begin;
-            if (interior && sizeof(InT) == 1 && f + 1 < f_end)
-                ss_s0_async_u8(p, frame + p.in_frame_stride, x0, y0, tid, (char *)P1);   // P1 is dead until S1
+            if (interior && sizeof(InT) == 1 && f + 1 < f_end) {   // P1 is dead until the next S1
+#ifndef SS_HOST_EMU
+                if (tid == 0)
+                    ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + (f + 1) * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
+#else
+                ss_s0_async_u8(p, frame + p.in_frame_stride, x0, y0, tid, (char *)P1);
+#endif
+            }
             float e[16];
             if (fast) {
 #pragma unroll
@@ -757,9 +816,16 @@ void ss_level_tile(const SsLevelParams &p, int tile_x, int tile_y, int group, fl
         }
         // S3 reads the parked Laplacians from P0, so it must finish before the next frame's S0; the
         // asynchronous copies of the next frame's raw patch must have landed as well
+#ifndef SS_HOST_EMU
+        if (interior && sizeof(InT) == 1 && f + 1 < f_end) {
+            ss_mbar_wait(mbar, mbar_phase);
+            mbar_phase ^= 1;
+        }
+#else
         if (interior && sizeof(InT) == 1) {
             SS_THREADS(tid) { ss_cp_async_wait(); }
         }
+#endif
         SS_SYNC();
     }
 

@@ -1,5 +1,6 @@
 // ss_lib.cu -- libshinestack_b200.so: C ABI (include/shinestack_b200.h) + kernel launches.
 // sm_100a only; no CPU fallback: every entry point that computes needs a compute-capability-10 GPU.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -53,12 +54,13 @@ __device__ __forceinline__ void ss_tile_of_block(int b, int nbx, int nby, int &t
 }
 
 template <typename InT>
-__global__ void __launch_bounds__(SS_NT, 2) ss_level_kernel(const __grid_constant__ SsLevelParams p)
+__global__ void __launch_bounds__(SS_NT, 2) ss_level_kernel(const __grid_constant__ SsLevelParams p,
+                                                            const __grid_constant__ CUtensorMap tmap)
 {
-    extern __shared__ float ss_smem[];
+    extern __shared__ __align__(128) float ss_smem[];
     int tx, ty;
     ss_tile_of_block(blockIdx.y * gridDim.x + blockIdx.x, gridDim.x, gridDim.y, tx, ty);
-    ss_level_tile<InT>(p, tx, ty, blockIdx.z, ss_smem);
+    ss_level_tile<InT>(p, &tmap, tx, ty, blockIdx.z, ss_smem);
 }
 
 // Folds the per-group partial states of a frame-split level launch into the running state, groups in
@@ -374,7 +376,8 @@ struct ss_handle {
     int num_values = 256;
     // frame store (ring of n_slots device frames)
     char *frames = nullptr;
-    size_t frame_pitch = 0, frame_bytes = 0;
+    size_t frame_pitch = 0, frame_bytes = 0, frame_shift = 0;
+    CUtensorMap tmap_frames;         // uint8 frame store as a 2-D byte tensor [n_slots * H rows][pitch]: TMA boxes
     int n_slots = 0, batch = 0;
     // base level
     float *base = nullptr;           // max_frames x 3 x hL x wL
@@ -520,7 +523,10 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     h->n_slots = cfg->resident_frames > 0 ? cfg->resident_frames : 2 * h->batch;
     if (h->n_slots < h->batch) h->n_slots = h->batch;
     h->n_slots = (h->n_slots + h->batch - 1) / h->batch * h->batch;
-    h->frame_pitch = ((size_t)cfg->width * 3 * cfg->bytes_per_sample + 15) / 16 * 16;
+    // uint8 rows start 8 bytes into their pitch: the byte column of pixel x0-8 (x0 a multiple of 64) is then
+    // a multiple of 16, which TMA requires of a box origin
+    h->frame_shift = cfg->bytes_per_sample == 1 ? 8 : 0;
+    h->frame_pitch = ((size_t)cfg->width * 3 * cfg->bytes_per_sample + h->frame_shift + 15) / 16 * 16;
     h->frame_bytes = h->frame_pitch * cfg->height;
     SS_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     SS_CUDA(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
@@ -533,6 +539,26 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     }
     int rc;
     if ((rc = ss_dalloc(&h->frames, h->frame_bytes * h->n_slots))) return rc;
+    memset(&h->tmap_frames, 0, sizeof(h->tmap_frames));
+    if (cfg->bytes_per_sample == 1) {
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return ss_fail(SS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        const cuuint64_t gdim[2] = {(cuuint64_t)h->frame_pitch, (cuuint64_t)cfg->height * h->n_slots};
+        const cuuint64_t gstride[1] = {(cuuint64_t)h->frame_pitch};
+        const cuuint32_t box[2] = {SS_RAWS, SS_P0H};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = ((encode_fn)fn)(&h->tmap_frames, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->frames, gdim, gstride,
+                                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return ss_fail(SS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    }
     h->lv.resize(h->L);
     h->n_keys = 0;
     for (int l = 0; l < h->L; ++l) {
@@ -584,11 +610,11 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     h->out_pitch = (size_t)cfg->width * 3 * cfg->bytes_per_sample;
     if ((rc = ss_dalloc((char **)&h->out_dev, h->out_pitch * cfg->height))) return rc;
     SS_CUDA(cudaFuncSetAttribute(ss_level_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(SS_SMEM_FLOATS * sizeof(float))));
+                                 (int)SS_SMEM_BYTES));
     SS_CUDA(cudaFuncSetAttribute(ss_level_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(SS_SMEM_FLOATS * sizeof(float))));
+                                 (int)SS_SMEM_BYTES));
     SS_CUDA(cudaFuncSetAttribute(ss_level_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(SS_SMEM_FLOATS * sizeof(float))));
+                                 (int)SS_SMEM_BYTES));
     return 0;
 }
 
@@ -675,7 +701,7 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
     if ((rc = ss_timer_begin(h))) return rc;
     if (h->L == 0) {
         for (int f = f0; f < f1; ++f) {
-            const char *src = h->frames + (size_t)(f % h->n_slots) * h->frame_bytes;
+            const char *src = h->frames + (size_t)(f % h->n_slots) * h->frame_bytes + h->frame_shift;
             dim3 g((h->cfg.width + 255) / 256, h->cfg.height);
             if (h->cfg.bytes_per_sample == 1)
                 ss_convert_kernel<uint8_t><<<g, 256, 0, h->s_comp>>>((const uint8_t *)src, (int)h->frame_pitch,
@@ -692,7 +718,8 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
         memset(&p, 0, sizeof(p));
         p.h = v.h; p.w = v.w; p.h2 = h->lh[l + 1]; p.w2 = h->lw[l + 1];
         if (l == 0) {
-            p.in = h->frames + (size_t)slot0 * h->frame_bytes;
+            p.in = h->frames + (size_t)slot0 * h->frame_bytes + h->frame_shift;
+            p.tma_row0 = slot0 * h->cfg.height;
             p.in_frame_stride = (long long)h->frame_bytes;
             p.in_pitch = (int)h->frame_pitch;
         } else {
@@ -720,7 +747,7 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
         p.init = h->have_state ? 0 : 1;
         memcpy(p.k25, h->k25, sizeof(p.k25));
         dim3 grid((v.w + SS_TX - 1) / SS_TX, (v.h + SS_TY - 1) / SS_TY, groups);
-        const size_t smem = SS_SMEM_FLOATS * sizeof(float);
+        const size_t smem = SS_SMEM_BYTES;
         if (h->profile) {
             if (h->ltimers_used == h->ltimers.size()) {
                 ss_handle::LevelTimer t;
@@ -732,11 +759,11 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
             SS_CUDA(cudaEventRecord(h->ltimers[h->ltimers_used].a, h->s_comp));
         }
         if (l == 0 && h->cfg.bytes_per_sample == 1)
-            ss_level_kernel<uint8_t><<<grid, SS_NT, smem, h->s_comp>>>(p);
+            ss_level_kernel<uint8_t><<<grid, SS_NT, smem, h->s_comp>>>(p, h->tmap_frames);
         else if (l == 0)
-            ss_level_kernel<uint16_t><<<grid, SS_NT, smem, h->s_comp>>>(p);
+            ss_level_kernel<uint16_t><<<grid, SS_NT, smem, h->s_comp>>>(p, h->tmap_frames);
         else
-            ss_level_kernel<float><<<grid, SS_NT, smem, h->s_comp>>>(p);
+            ss_level_kernel<float><<<grid, SS_NT, smem, h->s_comp>>>(p, h->tmap_frames);
         h->launches++;
         if (groups > 1) {
             ss_merge_groups_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, h->s_comp>>>(
@@ -789,7 +816,7 @@ static int ss_push_impl(ss_handle *h, const void *src, size_t pitch, cudaMemcpyK
         // the ring wraps: the batch that used these slots must have been consumed
         SS_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_done[slot / h->batch], 0));
     }
-    SS_CUDA(cudaMemcpy2DAsync(h->frames + (size_t)slot * h->frame_bytes, h->frame_pitch, src, pitch, row,
+    SS_CUDA(cudaMemcpy2DAsync(h->frames + (size_t)slot * h->frame_bytes + h->frame_shift, h->frame_pitch, src, pitch, row,
                               h->cfg.height, kind, h->s_copy));
     h->n_pushed++;
     if (h->n_pushed % h->batch == 0) return ss_launch_pending(h, false);

@@ -27,14 +27,14 @@ extern "C" int emu_level(const void *in, int bytes_per_sample /*1,2: interleaved
     p.best_e = best_e; p.best_idx = best_idx; p.fused = fused;
     p.n_frames = n_frames; p.frame_index0 = frame_index0; p.init = init; p.groups = 1; p.group_stride = 0;
     memcpy(p.k25, k25, sizeof(p.k25));
-    float *smem = (float *)malloc(sizeof(float) * SS_SMEM_FLOATS);
+    float *smem = (float *)malloc(SS_SMEM_BYTES);
     // poison shared memory so that any read of a never-written slot shows up as NaN
     for (int ty = 0; ty < (h + SS_TY - 1) / SS_TY; ++ty)
         for (int tx = 0; tx < (w + SS_TX - 1) / SS_TX; ++tx) {
-            memset(smem, 0xff, sizeof(float) * SS_SMEM_FLOATS);
-            if (bytes_per_sample == 1) ss_level_tile<uint8_t>(p, tx, ty, 0, smem);
-            else if (bytes_per_sample == 2) ss_level_tile<uint16_t>(p, tx, ty, 0, smem);
-            else ss_level_tile<float>(p, tx, ty, 0, smem);
+            memset(smem, 0xff, SS_SMEM_BYTES);
+            if (bytes_per_sample == 1) ss_level_tile<uint8_t>(p, nullptr, tx, ty, 0, smem);
+            else if (bytes_per_sample == 2) ss_level_tile<uint16_t>(p, nullptr, tx, ty, 0, smem);
+            else ss_level_tile<float>(p, nullptr, tx, ty, 0, smem);
         }
     free(smem);
     return 0;

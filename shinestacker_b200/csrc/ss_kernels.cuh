@@ -625,43 +625,44 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             SS_THREADS(tid)
             {
                 const int tx = tid & 15, ty = tid >> 4;
-                // own 4x4 block
-                float gsq[16];
-                {
-                    float l3[3][16];
+                // own 4x4 block.  The channel loop is deliberately NOT unrolled (the hot loop must stay small
+                // for the instruction cache); gray = fma(R,.299, fma(B,.114, G*.587)) is accumulated in the
+                // order G, B, R starting from +0 (fma(G,.587,+0) == G*.587 up to the sign of zero, which the
+                // square removes).
+                float gray[16];
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        float win[4][4], acc[16];
+                for (int q = 0; q < 16; ++q) gray[q] = 0.f;
+#pragma unroll 1
+                for (int it = 0; it < 3; ++it) {
+                    const int ch = it == 0 ? 1 : (it == 1 ? 0 : 2);
+                    const float wgt = it == 0 ? 0.587f : (it == 1 ? 0.114f : 0.299f);
+                    float win[4][4], acc[16];
 #pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            const float *src = P1 + ch * SS_P1P + (2 * ty + 1 + a) * SS_P1S + 2 * tx + 1 + SS_P1O;
-                            const ss_f2 u = *(const ss_f2 *)src, v = *(const ss_f2 *)(src + 2);
-                            win[a][0] = u.x; win[a][1] = u.y; win[a][2] = v.x; win[a][3] = v.y;
-                        }
-                        ss_expand_block<4>(win, p.k25, acc);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            float *gp = P0 + ch * SS_P0P + (4 * ty + r + SS_P0Y) * SS_P0S + 4 * tx + SS_P0X;
-                            const ss_f4 g = *(const ss_f4 *)gp;
-                            l3[ch][r * 4 + 0] = ss_fma(-4.f, acc[r * 4 + 0], g.x);
-                            l3[ch][r * 4 + 1] = ss_fma(-4.f, acc[r * 4 + 1], g.y);
-                            l3[ch][r * 4 + 2] = ss_fma(-4.f, acc[r * 4 + 2], g.z);
-                            l3[ch][r * 4 + 3] = ss_fma(-4.f, acc[r * 4 + 3], g.w);
-                            // park the Laplacian in place of g_l: this position is read by no other thread
-                            *(ss_f4 *)gp = ss_mk4(l3[ch][r * 4], l3[ch][r * 4 + 1], l3[ch][r * 4 + 2], l3[ch][r * 4 + 3]);
-                        }
+                    for (int a = 0; a < 4; ++a) {
+                        const float *src = P1 + ch * SS_P1P + (2 * ty + 1 + a) * SS_P1S + 2 * tx + 1 + SS_P1O;
+                        const ss_f2 u = *(const ss_f2 *)src, v = *(const ss_f2 *)(src + 2);
+                        win[a][0] = u.x; win[a][1] = u.y; win[a][2] = v.x; win[a][3] = v.y;
                     }
+                    ss_expand_block<4>(win, p.k25, acc);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const float gray = ss_fma(l3[2][q], 0.299f, ss_fma(l3[0][q], 0.114f, ss_mul(l3[1][q], 0.587f)));
-                        gsq[q] = ss_mul(gray, gray);
+                    for (int r = 0; r < 4; ++r) {
+                        float *gp = P0 + ch * SS_P0P + (4 * ty + r + SS_P0Y) * SS_P0S + 4 * tx + SS_P0X;
+                        const ss_f4 g = *(const ss_f4 *)gp;
+                        const float l0 = ss_fma(-4.f, acc[r * 4 + 0], g.x), l1 = ss_fma(-4.f, acc[r * 4 + 1], g.y);
+                        const float l2 = ss_fma(-4.f, acc[r * 4 + 2], g.z), l3 = ss_fma(-4.f, acc[r * 4 + 3], g.w);
+                        // park the Laplacian in place of g_l: this position is read by no other thread
+                        *(ss_f4 *)gp = ss_mk4(l0, l1, l2, l3);
+                        gray[r * 4 + 0] = ss_fma(l0, wgt, gray[r * 4 + 0]);
+                        gray[r * 4 + 1] = ss_fma(l1, wgt, gray[r * 4 + 1]);
+                        gray[r * 4 + 2] = ss_fma(l2, wgt, gray[r * 4 + 2]);
+                        gray[r * 4 + 3] = ss_fma(l3, wgt, gray[r * 4 + 3]);
                     }
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     float *dst = SQ + (4 * ty + r + 2) * SS_SQS + 4 * tx + 2;
-                    *(ss_f2 *)dst = ss_mk2(gsq[r * 4], gsq[r * 4 + 1]);
-                    *(ss_f2 *)(dst + 2) = ss_mk2(gsq[r * 4 + 2], gsq[r * 4 + 3]);
+                    *(ss_f2 *)dst = ss_mk2(ss_mul(gray[r * 4], gray[r * 4]), ss_mul(gray[r * 4 + 1], gray[r * 4 + 1]));
+                    *(ss_f2 *)(dst + 2) = ss_mk2(ss_mul(gray[r * 4 + 2], gray[r * 4 + 2]), ss_mul(gray[r * 4 + 3], gray[r * 4 + 3]));
                 }
                 // halo ring of SQ (2 pixels wide): 132 aligned 2x2 quads
                 if (tid < 132) {
@@ -670,9 +671,11 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     else if (tid < 68) { qq = SS_SQH - 2; pp = 2 * (tid - 34); }     // bottom strip
                     else if (tid < 100) { qq = 2 + 2 * (tid - 68); pp = 0; }         // left strip
                     else { qq = 2 + 2 * (tid - 100); pp = SS_SQW - 2; }              // right strip
-                    float l3[3][4];
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
+                    float gr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                    for (int it = 0; it < 3; ++it) {
+                        const int ch = it == 0 ? 1 : (it == 1 ? 0 : 2);
+                        const float wgt = it == 0 ? 0.587f : (it == 1 ? 0.114f : 0.299f);
                         float win[3][3], acc[4];
 #pragma unroll
                         for (int a = 0; a < 3; ++a)
@@ -684,14 +687,11 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                         for (int r = 0; r < 2; ++r)
 #pragma unroll
                             for (int c = 0; c < 2; ++c)
-                                l3[ch][r * 2 + c] = ss_fma(-4.f, acc[r * 2 + c],
-                                    P0[ch * SS_P0P + (qq + r + SS_P0Y - 2) * SS_P0S + pp + c + SS_P0X - 2]);
+                                gr[r * 2 + c] = ss_fma(ss_fma(-4.f, acc[r * 2 + c],
+                                    P0[ch * SS_P0P + (qq + r + SS_P0Y - 2) * SS_P0S + pp + c + SS_P0X - 2]), wgt, gr[r * 2 + c]);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float gray = ss_fma(l3[2][q], 0.299f, ss_fma(l3[0][q], 0.114f, ss_mul(l3[1][q], 0.587f)));
-                        SQ[(qq + (q >> 1)) * SS_SQS + pp + (q & 1)] = ss_mul(gray, gray);
-                    }
+                    for (int q = 0; q < 4; ++q) SQ[(qq + (q >> 1)) * SS_SQS + pp + (q & 1)] = ss_mul(gr[q], gr[q]);
                 }
             }
         } else {

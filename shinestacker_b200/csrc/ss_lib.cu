@@ -142,50 +142,59 @@ __device__ float ss_np_pairwise_sum(const float *a, int n)
 
 #define SS_MAX_WINDOW 11
 
-// Base level, step 2 (reference pyramid.py:66-93,102-105): per pixel and frame the window entropy
-// -sum(v*log p[v]) and variance, running strict-'>' arg-max of each over the frames, and the base
-// pixels of the two winners.
-__global__ void ss_base_select_kernel(const int32_t *gray, const float *log_p, const float *base,
-                                      int h, int w, int n_frames, int num_values, int side,
-                                      int frame_index0, float *best_ve, int32_t *best_ie,
-                                      float *best_vd, int32_t *best_id, float *pix_e, float *pix_d)
+// Base level, step 2a (reference pyramid.py:66-93): per (pixel, frame) the window entropy
+// -sum(v*log p[v]) and the window variance, both in numpy's evaluation order.
+__global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, int h, int w, int num_values,
+                                       int side, float *ent_out, float *dev_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
     const int n_px = h * w;
     if (i >= n_px) return;
     const int y = i / w, x = i - y * w;
     const int pad = (side - 1) / 2, n = side * side;
     float buf[SS_MAX_WINDOW * SS_MAX_WINDOW];
     int vals[SS_MAX_WINDOW * SS_MAX_WINDOW];
-    float ve = 0.f, vd = 0.f;
+    const int32_t *g = gray + (size_t)f * n_px;
+    const float *lp = log_p + (size_t)f * num_values;
+    int c = 0;
+    long long s = 0;
+    for (int dy = -pad; dy <= pad; ++dy) {
+        int yy = y + dy;
+        while (yy < 0 || yy >= h) yy = yy < 0 ? -yy : 2 * h - 2 - yy;
+        for (int dx = -pad; dx <= pad; ++dx) {
+            int xx = x + dx;
+            while (xx < 0 || xx >= w) xx = xx < 0 ? -xx : 2 * w - 2 - xx;
+            const int v = g[yy * w + xx];
+            vals[c] = v;
+            buf[c] = __fmul_rn((float)v, lp[v]);
+            s += v;
+            ++c;
+        }
+    }
+    ent_out[(size_t)f * n_px + i] = __fmul_rn(-1.f, ss_np_pairwise_sum(buf, n));
+    const float mean = (float)((double)s / (double)n);
+    for (int k = 0; k < n; ++k) {
+        const float d = __fsub_rn((float)vals[k], mean);
+        buf[k] = __fmul_rn(d, d);
+    }
+    dev_out[(size_t)f * n_px + i] = __fdiv_rn(ss_np_pairwise_sum(buf, n), (float)n);
+}
+
+// Base level, step 2b (reference pyramid.py:102-105): running strict-'>' arg-max of entropy and of
+// deviation over the frames, and the base pixels of the two winners.
+__global__ void ss_base_select_kernel(const float *ent, const float *dev, const float *base, int n_px,
+                                      int n_frames, int frame_index0, float *best_ve, int32_t *best_ie,
+                                      float *best_vd, int32_t *best_id, float *pix_e, float *pix_d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    float ve = ent[i], vd = dev[i];
     int ie = 0, id = 0;
-    for (int f = 0; f < n_frames; ++f) {
-        const int32_t *g = gray + (size_t)f * n_px;
-        const float *lp = log_p + (size_t)f * num_values;
-        int c = 0;
-        long long s = 0;
-        for (int dy = -pad; dy <= pad; ++dy) {
-            int yy = y + dy;
-            while (yy < 0 || yy >= h) yy = yy < 0 ? -yy : 2 * h - 2 - yy;
-            for (int dx = -pad; dx <= pad; ++dx) {
-                int xx = x + dx;
-                while (xx < 0 || xx >= w) xx = xx < 0 ? -xx : 2 * w - 2 - xx;
-                const int v = g[yy * w + xx];
-                vals[c] = v;
-                buf[c] = __fmul_rn((float)v, lp[v]);
-                s += v;
-                ++c;
-            }
-        }
-        const float ent = __fmul_rn(-1.f, ss_np_pairwise_sum(buf, n));
-        const float mean = (float)((double)s / (double)n);
-        for (int k = 0; k < n; ++k) {
-            const float d = __fsub_rn((float)vals[k], mean);
-            buf[k] = __fmul_rn(d, d);
-        }
-        const float dev = __fdiv_rn(ss_np_pairwise_sum(buf, n), (float)n);
-        if (f == 0 || ent > ve) { ve = ent; ie = f; }
-        if (f == 0 || dev > vd) { vd = dev; id = f; }
+    for (int f = 1; f < n_frames; ++f) {
+        const float e = ent[(size_t)f * n_px + i], d = dev[(size_t)f * n_px + i];
+        if (e > ve) { ve = e; ie = f; }
+        if (d > vd) { vd = d; id = f; }
     }
     best_ve[i] = ve; best_ie[i] = frame_index0 + ie;
     best_vd[i] = vd; best_id[i] = frame_index0 + id;
@@ -385,6 +394,7 @@ struct ss_handle {
     unsigned int *counts = nullptr;  // max_frames x num_values
     float *log_p = nullptr;          // max_frames x num_values
     float *best_ve = nullptr, *best_vd = nullptr, *pix_e = nullptr, *pix_d = nullptr;
+    float *ent = nullptr, *dev = nullptr;  // max_frames x hL x wL window entropy / variance
     int32_t *best_ie = nullptr, *best_id = nullptr;
     float *fused_base = nullptr;     // 3 x hL x wL
     float *tmp_a = nullptr, *tmp_b = nullptr;  // collapse ping-pong, 3 x H x W / 4 each... see alloc
@@ -492,6 +502,7 @@ SS_EXPORT void ss_destroy(ss_handle *h)
     }
     cudaFree(h->frames); cudaFree(h->base); cudaFree(h->gray); cudaFree(h->counts);
     cudaFree(h->log_p); cudaFree(h->best_ve); cudaFree(h->best_vd); cudaFree(h->pix_e);
+    cudaFree(h->ent); cudaFree(h->dev);
     cudaFree(h->pix_d); cudaFree(h->best_ie); cudaFree(h->best_id); cudaFree(h->fused_base);
     cudaFree(h->tmp_a); cudaFree(h->tmp_b); cudaFree(h->out_dev); cudaFree(h->keys);
     cudaFree(h->coeffs);
@@ -594,6 +605,8 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     if ((rc = ss_dalloc(&h->gray, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->counts, (size_t)cfg->max_frames * h->num_values))) return rc;
     if ((rc = ss_dalloc(&h->log_p, (size_t)cfg->max_frames * h->num_values))) return rc;
+    if ((rc = ss_dalloc(&h->ent, (size_t)cfg->max_frames * nb))) return rc;
+    if ((rc = ss_dalloc(&h->dev, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->best_ve, nb))) return rc;
     if ((rc = ss_dalloc(&h->best_vd, nb))) return rc;
     if ((rc = ss_dalloc(&h->best_ie, nb))) return rc;
@@ -924,9 +937,14 @@ SS_EXPORT int ss_finish_select_base(ss_handle *h, const float *log_prob)
     if (!tab.empty()) SS_CUDA(cudaStreamSynchronize(h->s_comp));
     int rc;
     if ((rc = ss_timer_begin(h))) return rc;
-    ss_base_select_kernel<<<(nb + 63) / 64, 64, 0, h->s_comp>>>(h->gray, h->log_p, h->base, h->lh[h->L],
-        h->lw[h->L], h->n_pushed, h->num_values, h->side, h->cfg.frame_index_base, h->best_ve, h->best_ie,
-        h->best_vd, h->best_id, h->pix_e, h->pix_d);
+    {
+        dim3 g((nb + 63) / 64, h->n_pushed);
+        ss_base_metrics_kernel<<<g, 64, 0, h->s_comp>>>(h->gray, h->log_p, h->lh[h->L], h->lw[h->L], h->num_values,
+                                                          h->side, h->ent, h->dev);
+        h->launches++;
+    }
+    ss_base_select_kernel<<<(nb + 127) / 128, 128, 0, h->s_comp>>>(h->ent, h->dev, h->base, nb, h->n_pushed,
+        h->cfg.frame_index_base, h->best_ve, h->best_ie, h->best_vd, h->best_id, h->pix_e, h->pix_d);
     h->launches++;
     SS_CUDA(cudaGetLastError());
     if ((rc = ss_timer_end(h))) return rc;

@@ -300,8 +300,9 @@ def main():
                        "parallelism": f"frames sharded over {world} GPU(s)"},
             "clocks": clocks,
             "e2e": {"value": mp / (dt_e2e / a.steps), "unit": UNIT, "ms_per_step": dt_e2e / a.steps * 1e3,
-                    "h2d_bytes_per_step": N * frame_bytes + N * 4 * (256 if b == 1 else 65536),
-                    "d2h_bytes_per_step": frame_bytes + N * 4 * (256 if b == 1 else 65536),
+                    # frames up + log table up; fused image down + histogram (u8) / gray base levels (u16) down
+                    "h2d_bytes_per_step": N * frame_bytes + N * 4 * (256 if b == 1 else 48 * 64),
+                    "d2h_bytes_per_step": frame_bytes + N * 4 * (256 if b == 1 else 48 * 64),
                     "matches_resident_result": same},
             "output_crc32": int(zlib.crc32(out.tobytes())),
             "gpu_launches": launches,

@@ -145,6 +145,12 @@ int ss_rerun_resident(ss_handle *h);
  * them: base-level entropy/deviation arg-max on this rank's frames; then base blend + collapse +
  * conversion + download. */
 int ss_finish_select_base(ss_handle *h, const float *log_prob);
+/* Variant for 16-bit stacks: the log-probability of every base pixel's own gray value
+ * (n_frames x hL x wL float32) instead of a 65536-entry table per frame; ss_get_base_gray delivers the
+ * truncated gray base levels (n_frames x hL x wL int32) the host needs to build it (np.unique per frame,
+ * exactly as PyramidBase.entropy does, pyramid.py:67-69). */
+int ss_get_base_gray(ss_handle *h, int32_t *out);
+int ss_finish_select_base_px(ss_handle *h, const float *log_prob_px);
 int ss_finish_collapse(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
 /* Time of the i-th timed segment (one per launched batch, then histogram, base select, collapse). */
 int ss_segment_time_ms(ss_handle *h, int i, float *ms);

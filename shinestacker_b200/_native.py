@@ -75,6 +75,8 @@ SIGNATURES = {
     "ss_exchange_adopt": (_i, [_vp]),
     "ss_rerun_resident": (_i, [_vp]),
     "ss_finish_select_base": (_i, [_vp, _vp]),
+    "ss_get_base_gray": (_i, [_vp, _vp]),
+    "ss_finish_select_base_px": (_i, [_vp, _vp]),
     "ss_finish_collapse": (_i, [_vp, _vp, _sz]),
     "ss_segment_time_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float)]),
     "ss_get_best_energy": (_i, [_vp, _i, _vp]),

@@ -144,8 +144,8 @@ __device__ float ss_np_pairwise_sum(const float *a, int n)
 
 // Base level, step 2a (reference pyramid.py:66-93): per (pixel, frame) the window entropy
 // -sum(v*log p[v]) and the window variance, both in numpy's evaluation order.
-__global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, int h, int w, int num_values,
-                                       int side, float *ent_out, float *dev_out)
+__global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, int per_px, int h, int w,
+                                       int num_values, int side, float *ent_out, float *dev_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
@@ -156,7 +156,9 @@ __global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, 
     float buf[SS_MAX_WINDOW * SS_MAX_WINDOW];
     int vals[SS_MAX_WINDOW * SS_MAX_WINDOW];
     const int32_t *g = gray + (size_t)f * n_px;
-    const float *lp = log_p + (size_t)f * num_values;
+    // log p[v]: either a per-frame table indexed by the value, or (16-bit stacks) the log-probability of
+    // every base pixel's own value, indexed by the pixel
+    const float *lp = log_p + (size_t)f * (per_px ? n_px : num_values);
     int c = 0;
     long long s = 0;
     for (int dy = -pad; dy <= pad; ++dy) {
@@ -167,7 +169,7 @@ __global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, 
             while (xx < 0 || xx >= w) xx = xx < 0 ? -xx : 2 * w - 2 - xx;
             const int v = g[yy * w + xx];
             vals[c] = v;
-            buf[c] = __fmul_rn((float)v, lp[v]);
+            buf[c] = __fmul_rn((float)v, lp[per_px ? yy * w + xx : v]);
             s += v;
             ++c;
         }
@@ -604,7 +606,7 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     if ((rc = ss_dalloc(&h->base, (size_t)cfg->max_frames * 3 * nb))) return rc;
     if ((rc = ss_dalloc(&h->gray, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->counts, (size_t)cfg->max_frames * h->num_values))) return rc;
-    if ((rc = ss_dalloc(&h->log_p, (size_t)cfg->max_frames * h->num_values))) return rc;
+    if ((rc = ss_dalloc(&h->log_p, (size_t)cfg->max_frames * ((size_t)h->num_values > nb ? (size_t)h->num_values : nb)))) return rc;
     if ((rc = ss_dalloc(&h->ent, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->dev, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->best_ve, nb))) return rc;
@@ -911,20 +913,21 @@ SS_EXPORT int ss_finish_begin(ss_handle *h, int64_t *counts)
 }
 
 // Base-level selection on this rank's frames (entropy / deviation arg-max + winners' pixels).
-SS_EXPORT int ss_finish_select_base(ss_handle *h, const float *log_prob)
+static int ss_select_base_impl(ss_handle *h, const float *log_prob, int per_px)
 {
     if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin must be called first");
     SS_CUDA(cudaSetDevice(h->cfg.device));
     const int nb = h->lh[h->L] * h->lw[h->L];
-    const size_t n = (size_t)h->n_pushed * h->num_values;
+    const size_t n = (size_t)h->n_pushed * (per_px ? (size_t)nb : (size_t)h->num_values);
     std::vector<float> tab;
     if (!log_prob) {
         // C-only callers: logf from libm; numpy's SIMD log can differ from it in the last ulp, which
         // matters only for exact ties-by-rounding of the base-level entropy arg-max.
-        std::vector<unsigned int> cnt(n);
-        SS_CUDA(cudaMemcpyAsync(cnt.data(), h->counts, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_comp));
+        const size_t nc = (size_t)h->n_pushed * h->num_values;
+        std::vector<unsigned int> cnt(nc);
+        SS_CUDA(cudaMemcpyAsync(cnt.data(), h->counts, nc * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_comp));
         SS_CUDA(cudaStreamSynchronize(h->s_comp));
-        tab.resize(n);
+        tab.resize(nc);
         for (int f = 0; f < h->n_pushed; ++f)
             for (int v = 0; v < h->num_values; ++v) {
                 const unsigned int c = cnt[(size_t)f * h->num_values + v];
@@ -932,6 +935,7 @@ SS_EXPORT int ss_finish_select_base(ss_handle *h, const float *log_prob)
                 tab[(size_t)f * h->num_values + v] = c ? logf(pr) : -INFINITY;
             }
         log_prob = tab.data();
+        per_px = 0;
     }
     SS_CUDA(cudaMemcpyAsync(h->log_p, log_prob, n * sizeof(float), cudaMemcpyHostToDevice, h->s_comp));
     if (!tab.empty()) SS_CUDA(cudaStreamSynchronize(h->s_comp));
@@ -939,8 +943,8 @@ SS_EXPORT int ss_finish_select_base(ss_handle *h, const float *log_prob)
     if ((rc = ss_timer_begin(h))) return rc;
     {
         dim3 g((nb + 63) / 64, h->n_pushed);
-        ss_base_metrics_kernel<<<g, 64, 0, h->s_comp>>>(h->gray, h->log_p, h->lh[h->L], h->lw[h->L], h->num_values,
-                                                          h->side, h->ent, h->dev);
+        ss_base_metrics_kernel<<<g, 64, 0, h->s_comp>>>(h->gray, h->log_p, per_px, h->lh[h->L], h->lw[h->L],
+                                                          h->num_values, h->side, h->ent, h->dev);
         h->launches++;
     }
     ss_base_select_kernel<<<(nb + 127) / 128, 128, 0, h->s_comp>>>(h->ent, h->dev, h->base, nb, h->n_pushed,
@@ -948,6 +952,27 @@ SS_EXPORT int ss_finish_select_base(ss_handle *h, const float *log_prob)
     h->launches++;
     SS_CUDA(cudaGetLastError());
     if ((rc = ss_timer_end(h))) return rc;
+    return 0;
+}
+
+SS_EXPORT int ss_finish_select_base(ss_handle *h, const float *log_prob) { return ss_select_base_impl(h, log_prob, 0); }
+
+// Same, with the table given per base pixel: log_prob_px[f][i] = log(probability of the gray value of pixel i
+// of frame f).  Cheap for 16-bit stacks, where a 65536-entry table per frame is mostly empty.
+SS_EXPORT int ss_finish_select_base_px(ss_handle *h, const float *log_prob_px)
+{
+    if (!log_prob_px) return ss_fail(SS_ERR_STATE, "null table");
+    return ss_select_base_impl(h, log_prob_px, 1);
+}
+
+// Truncated gray base level of every pushed frame (n_frames x hL x wL int32), after ss_finish_begin.
+SS_EXPORT int ss_get_base_gray(ss_handle *h, int32_t *out)
+{
+    if (!h || !out || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin must be called first");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->n_pushed * h->lh[h->L] * h->lw[h->L];
+    SS_CUDA(cudaMemcpyAsync(out, h->gray, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_comp));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
     return 0;
 }
 

@@ -15,6 +15,7 @@ GPU every call raises ``NativeLibraryError``.
 """
 import ctypes
 import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -58,6 +59,41 @@ def log_prob_table(counts):
     prob = (counts.astype(np.float32) / total).astype(np.float32)
     with np.errstate(divide="ignore"):
         return np.ascontiguousarray(np.log(prob))
+
+
+def log_prob_per_pixel(gray):
+    """16-bit variant of log_prob_table: for every base pixel the value np.log(probabilities)[its gray value].
+
+    ``gray``: (n_frames, hL, wL) int32 truncated gray base levels.  Per frame this is literally the
+    reference's expression (pyramid.py:67-69): np.unique(..., return_counts=True), counts.astype(float32) /
+    counts.sum() (evaluated in float64, stored as float32), np.log.
+    """
+    gray = np.asarray(gray)
+    out = np.empty(gray.shape, dtype=np.float32)
+    for f in range(gray.shape[0]):
+        _, inverse, counts = np.unique(gray[f].ravel(), return_inverse=True, return_counts=True)
+        prob = np.zeros(counts.shape, dtype=np.float32)
+        prob[...] = counts.astype(np.float32) / counts.sum()
+        out[f] = np.log(prob)[inverse].reshape(gray.shape[1:])
+    return out
+
+
+def select_base(lib, h, n_frames, num_values):
+    """ss_finish_begin + host-side log table (numpy) + base-level arg-max on the device."""
+    if num_values <= 256:
+        counts = np.empty((n_frames, num_values), dtype=np.int64)
+        _check(lib.ss_finish_begin(h, counts.ctypes.data_as(ctypes.c_void_p)))
+        table = log_prob_table(counts)
+        _check(lib.ss_finish_select_base(h, table.ctypes.data_as(ctypes.c_void_p)))
+    else:
+        _check(lib.ss_finish_begin(h, None))
+        L = lib.ss_num_levels(h)
+        hh, ww = ctypes.c_int32(), ctypes.c_int32()
+        _check(lib.ss_level_size(h, L, ctypes.byref(hh), ctypes.byref(ww)))
+        gray = np.empty((n_frames, hh.value, ww.value), dtype=np.int32)
+        _check(lib.ss_get_base_gray(h, gray.ctypes.data_as(ctypes.c_void_p)))
+        table = log_prob_per_pixel(gray)
+        _check(lib.ss_finish_select_base_px(h, table.ctypes.data_as(ctypes.c_void_p)))
 
 
 def _check(rc):
@@ -119,12 +155,13 @@ class PyramidStack(PyramidBase):
     """Drop-in replacement of the reference ``PyramidStack`` (pyramid.py:114-179) running on a B200.
 
     Extra keywords (all optional): ``device`` CUDA ordinal, ``batch_frames`` frames fused per kernel
-    chain launch, ``keep_depth_maps`` download the integer arg-max maps after each stack.
+    chain launch, ``keep_depth_maps`` download the integer arg-max maps after each stack,
+    ``decode_threads`` files decoded ahead of the upload.
     """
 
     def __init__(self, min_size=DEFAULT_PY_MIN_SIZE, kernel_size=DEFAULT_PY_KERNEL_SIZE,
                  gen_kernel=DEFAULT_PY_GEN_KERNEL, float_type=DEFAULT_PY_FLOAT,
-                 device=0, batch_frames=8, keep_depth_maps=True, frame_index_base=0):
+                 device=0, batch_frames=8, keep_depth_maps=True, frame_index_base=0, decode_threads=4):
         super().__init__(min_size, kernel_size, gen_kernel, float_type)
         self.offset = np.arange(-self.pad_amount, self.pad_amount + 1)
         self.dtype = None
@@ -134,6 +171,7 @@ class PyramidStack(PyramidBase):
         self.batch_frames = int(batch_frames)
         self.keep_depth_maps = keep_depth_maps
         self.frame_index_base = int(frame_index_base)
+        self.decode_threads = int(decode_threads)   # files decoded ahead of the upload (0 = inline)
         self.depth_maps = None     # dict(best=[level 0..L-1], best_e, best_d) after focus_stack
         self.last_kernel_ms = None
         self.last_launches = None
@@ -233,12 +271,9 @@ class PyramidStack(PyramidBase):
 
     def _finish(self, n, shape):
         lib, h = self._lib, self._h
-        counts = np.empty((n, self.num_pixel_values), dtype=np.int64)
-        _check(lib.ss_finish_begin(h, counts.ctypes.data_as(ctypes.c_void_p)))
-        table = log_prob_table(counts)
+        select_base(lib, h, n, self.num_pixel_values)
         out = np.empty((shape[0], shape[1], 3), dtype=self.dtype)
-        _check(lib.ss_finish_end(h, table.ctypes.data_as(ctypes.c_void_p),
-                                 out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+        _check(lib.ss_finish_collapse(h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
         ms = ctypes.c_float()
         _check(lib.ss_kernel_time_ms(h, ctypes.byref(ms)))
         self.last_kernel_ms = ms.value
@@ -283,10 +318,22 @@ class PyramidStack(PyramidBase):
         n = len(filenames)
         metadata = None
         ring = None
+        # decode ahead on worker threads (cv2.imread releases the GIL); frames are consumed in stack order
+        pool = ThreadPoolExecutor(max_workers=self.decode_threads) if self.decode_threads > 0 and n > 1 else None
+        pending = {}
+
+        def fetch(i):
+            if pool is None:
+                return read_img(filenames[i])
+            for j in range(i, min(n, i + self.decode_threads + 1)):
+                if j not in pending:
+                    pending[j] = pool.submit(read_img, filenames[j])
+            return pending.pop(i).result()
+
         try:
             for i, img_path in enumerate(filenames):
                 self.print_message(f": validating file {img_path.split('/')[-1]}")
-                img = read_img(img_path)
+                img = fetch(i)
                 if img is None:
                     raise ImageLoadError(img_path)
                 if metadata is None:
@@ -310,6 +357,11 @@ class PyramidStack(PyramidBase):
             if self._h is not None:
                 self._lib.ss_reset(self._h)
             raise
+        finally:
+            if pool is not None:
+                for fut in pending.values():
+                    fut.cancel()
+                pool.shutdown(wait=True)
 
     def focus_stack_arrays(self, frames):
         """In-memory entry point: iterable of H x W x 3 BGR uint8/uint16 arrays -> fused image."""

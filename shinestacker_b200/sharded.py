@@ -17,7 +17,7 @@ import ctypes
 import numpy as np
 
 from . import _native
-from .pyramid import PyramidStack, log_prob_table, _check
+from .pyramid import PyramidStack, select_base, _check
 
 
 def shard_range(n_frames, rank, world):
@@ -90,10 +90,7 @@ class ShardedPyramidStack:
         import torch
         a = self.algo
         lib, h = a._lib, a._h
-        counts = np.empty((n_local, a.num_pixel_values), dtype=np.int64)
-        _check(lib.ss_finish_begin(h, counts.ctypes.data_as(ctypes.c_void_p)))
-        table = log_prob_table(counts)
-        _check(lib.ss_finish_select_base(h, table.ctypes.data_as(ctypes.c_void_p)))
+        select_base(lib, h, n_local, a.num_pixel_values)
         if self.world > 1:
             ptr, cnt = ctypes.c_void_p(), ctypes.c_size_t()
             _check(lib.ss_exchange_keys(h, ctypes.byref(ptr), ctypes.byref(cnt)))

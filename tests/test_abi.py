@@ -83,6 +83,16 @@ def test_log_prob_table_matches_reference_expression(oracle):
             assert np.array_equal(tab[i], np.log(prob))
 
 
+def test_log_prob_per_pixel_matches_table(oracle):
+    rng = np.random.default_rng(4)
+    gray = rng.integers(0, 65536, size=(2, 20, 30)).astype(np.int32)
+    gray[0, :5, :5] = 777
+    px = pyramid.log_prob_per_pixel(gray)
+    for f in range(2):
+        tab = oracle.log_prob_table(gray[f], 65536)
+        assert np.array_equal(px[f], tab[gray[f]])
+
+
 def test_read_img_contract(tmp_path):
     import cv2
     with pytest.raises(RuntimeError):

@@ -217,3 +217,24 @@ def test_frame_sharding_merge_on_one_gpu(oracle):
     maps = root.get_depth_maps()
     golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
                                                best_d=info["best_d"], levels=info["levels"]), "sharded")
+
+
+def test_config4_geometry_tail_columns_u16(oracle):
+    """BASELINE config 4 geometry (6000x4000 RGB16: tail columns at 1500/750/375/188/94 and at the expand
+    widths), few frames so that the oracle stays fast."""
+    frames = synthetic.make_noise_stack(3, 4000, 6000, np.uint16, 97)
+    ref, info = oracle.focus_stack(frames)
+    out, maps, _ = run_gpu(frames, batch_frames=2)
+    golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
+                                               best_d=info["best_d"], levels=info["levels"]), "config4")
+
+
+def test_many_frames_u8_groups(oracle):
+    """More frames than any frame-split group count, small image: exercises the group merge order."""
+    frames = synthetic.make_noise_stack(70, 96, 160, np.uint8, 98)
+    for i in (5, 17, 40, 69):
+        frames[i] = frames[3].copy()          # exact ties far apart in the stack
+    ref, info = oracle.focus_stack(frames)
+    out, maps, _ = run_gpu(frames, batch_frames=70)
+    golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
+                                               best_d=info["best_d"], levels=info["levels"]), "groups")

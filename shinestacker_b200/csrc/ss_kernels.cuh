@@ -466,10 +466,11 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
     const bool interior = (x0 >= SS_P0X) && (y0 >= SS_P0Y) && (x0 + SS_TX + 8 <= p.w) &&
                           (y0 + SS_TY + 6 <= p.h) && (x0 / 2 + SS_TX / 2 + 2 <= p.w2) &&
                           (y0 / 2 + SS_TY / 2 + 2 <= p.h2);
-    // no output of this tile in any stage falls on a tail (mul+add) column?  Then the register-blocked
-    // stages are used; at image borders they also evaluate out-of-image positions (finite junk computed
-    // from clamped data) which the fix-up passes overwrite or which are never stored.
-    const bool fast = (x0 + SS_TX + 4 <= w_vec) && (x0 + SS_TX + 4 <= wz_vec);
+    // no IN-IMAGE output of this tile in any stage falls on a tail (mul+add) column?  (An image whose widths
+    // are multiples of 8 has no tail columns at all.)  Then the register-blocked stages are used; at image
+    // borders they also evaluate out-of-image positions (finite junk computed from clamped data) which the
+    // fix-up passes overwrite or which are never stored.
+    const bool fast = (w_vec == p.w && wz_vec == wz) || ((x0 + SS_TX + 4 <= w_vec) && (x0 + SS_TX + 4 <= wz_vec));
     const bool full = (x0 + SS_TX <= p.w) && (y0 + SS_TY <= p.h);
     const long long plane_px = (long long)p.h * p.w;
     const int f_begin = p.groups > 1 ? (int)((long long)group * p.n_frames / p.groups) : 0;

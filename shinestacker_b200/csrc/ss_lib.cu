@@ -586,7 +586,9 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
             // frame-split so that every level launch has >= ~6 waves of CTAs (2 CTAs/SM x 148 SMs per wave):
             // border tiles run longer than interior ones and few waves leave the SMs idle at the tail
             const int tiles = ((v.w + SS_TX - 1) / SS_TX) * ((v.h + SS_TY - 1) / SS_TY);
-            int g = (6 * 2 * 148 + tiles - 1) / tiles;
+            const char *wenv = getenv("SS_TARGET_WAVES");   // tuning knob (default 6)
+            const int waves = wenv && atoi(wenv) > 0 ? atoi(wenv) : (tiles >= 2000 ? 6 : 20);
+            int g = (waves * 2 * 148 + tiles - 1) / tiles;
             if (g < 1) g = 1;
             if (g > h->batch) g = h->batch;
             v.max_groups = g;

@@ -39,7 +39,7 @@ UNIT = "MP/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=64)
@@ -220,13 +220,15 @@ def main():
         _check(lib.ss_rerun_resident(algo._h))
         return res.finish(n_local, (H, W), out=out)
 
-    for _ in range(a.warmup):
-        step_resident()
+    # nvidia-smi needs ~100 ms to deliver its first sample: start it before the warm-up steps so that it is
+    # sampling during the timed region; only samples taken under load (power) enter the median
     sampler = ClockSampler(local)
-    lvl0_ms, lvl0_n, chain_ms, launches = 0.0, 0, 0.0, 0
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(a.warmup):
+        step_resident()
+    lvl0_ms, lvl0_n, chain_ms, launches = 0.0, 0, 0.0, 0
+    barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step_resident()
@@ -283,6 +285,16 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one level-0 launch (ncu --set full, profiles/)
+            txt = open(os.path.join(ROOT, "profiles", "r1_final_level0_summary.txt")).read().split()
+            def _val(key):
+                i = txt.index(key)
+                return float(txt[i + 1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[txt[i + 2]]
+            if N == 64 and H == 3072 and W == 4096 and dtype == np.uint8 and world == 1:
+                traffic = _val("dram__bytes_read.sum") + _val("dram__bytes_write.sum")
+        except (OSError, ValueError, KeyError):
+            pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"
         # the dominant kernel: level-0 fused kernel; one launch covers this rank's n_local frames
@@ -310,7 +322,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "ss_level_kernel (level 0: reduce + expand/Laplacian + "
                                                    "energy + arg-max select, all frames of the launch)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_launch,
+                         "traffic": traffic, "traffic_source": "profiles/r1_final_level0_summary.txt (ncu --set full, "
+                         "one launch)" if traffic else None, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_launch,
                          "peak_source": peak_src},
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -633,21 +633,22 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                 float gray[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) gray[q] = 0.f;
+                // channel order G, B, R = planes 1, 0, 2: the plane pointers advance by -1 and then +2 planes
+                const float *p1c = P1 + SS_P1P + (2 * ty + 1) * SS_P1S + 2 * tx + 1 + SS_P1O;
+                float *p0c = P0 + SS_P0P + (4 * ty + SS_P0Y) * SS_P0S + 4 * tx + SS_P0X;
 #pragma unroll 1
                 for (int it = 0; it < 3; ++it) {
-                    const int ch = it == 0 ? 1 : (it == 1 ? 0 : 2);
                     const float wgt = it == 0 ? 0.587f : (it == 1 ? 0.114f : 0.299f);
                     float win[4][4], acc[16];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const float *src = P1 + ch * SS_P1P + (2 * ty + 1 + a) * SS_P1S + 2 * tx + 1 + SS_P1O;
-                        const ss_f2 u = *(const ss_f2 *)src, v = *(const ss_f2 *)(src + 2);
+                        const ss_f2 u = *(const ss_f2 *)(p1c + a * SS_P1S), v = *(const ss_f2 *)(p1c + a * SS_P1S + 2);
                         win[a][0] = u.x; win[a][1] = u.y; win[a][2] = v.x; win[a][3] = v.y;
                     }
                     ss_expand_block<4>(win, p.k25, acc);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        float *gp = P0 + ch * SS_P0P + (4 * ty + r + SS_P0Y) * SS_P0S + 4 * tx + SS_P0X;
+                        float *gp = p0c + r * SS_P0S;
                         const ss_f4 g = *(const ss_f4 *)gp;
                         const float l0 = ss_fma(-4.f, acc[r * 4 + 0], g.x), l1 = ss_fma(-4.f, acc[r * 4 + 1], g.y);
                         const float l2 = ss_fma(-4.f, acc[r * 4 + 2], g.z), l3 = ss_fma(-4.f, acc[r * 4 + 3], g.w);
@@ -658,6 +659,9 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                         gray[r * 4 + 2] = ss_fma(l2, wgt, gray[r * 4 + 2]);
                         gray[r * 4 + 3] = ss_fma(l3, wgt, gray[r * 4 + 3]);
                     }
+                    const int step = it == 0 ? -1 : 2;
+                    p1c += step * SS_P1P;
+                    p0c += step * SS_P0P;
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -673,23 +677,25 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     else if (tid < 100) { qq = 2 + 2 * (tid - 68); pp = 0; }         // left strip
                     else { qq = 2 + 2 * (tid - 100); pp = SS_SQW - 2; }              // right strip
                     float gr[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float *r1c = P1 + SS_P1P + (qq / 2) * SS_P1S + pp / 2 + SS_P1O;
+                    const float *r0c = P0 + SS_P0P + (qq + SS_P0Y - 2) * SS_P0S + pp + SS_P0X - 2;
 #pragma unroll 1
                     for (int it = 0; it < 3; ++it) {
-                        const int ch = it == 0 ? 1 : (it == 1 ? 0 : 2);
                         const float wgt = it == 0 ? 0.587f : (it == 1 ? 0.114f : 0.299f);
                         float win[3][3], acc[4];
 #pragma unroll
                         for (int a = 0; a < 3; ++a)
 #pragma unroll
-                            for (int b = 0; b < 3; ++b)
-                                win[a][b] = P1[ch * SS_P1P + (qq / 2 + a) * SS_P1S + pp / 2 + b + SS_P1O];
+                            for (int b = 0; b < 3; ++b) win[a][b] = r1c[a * SS_P1S + b];
                         ss_expand_block<2>(win, p.k25, acc);
 #pragma unroll
                         for (int r = 0; r < 2; ++r)
 #pragma unroll
                             for (int c = 0; c < 2; ++c)
-                                gr[r * 2 + c] = ss_fma(ss_fma(-4.f, acc[r * 2 + c],
-                                    P0[ch * SS_P0P + (qq + r + SS_P0Y - 2) * SS_P0S + pp + c + SS_P0X - 2]), wgt, gr[r * 2 + c]);
+                                gr[r * 2 + c] = ss_fma(ss_fma(-4.f, acc[r * 2 + c], r0c[r * SS_P0S + c]), wgt, gr[r * 2 + c]);
+                        const int step = it == 0 ? -1 : 2;
+                        r1c += step * SS_P1P;
+                        r0c += step * SS_P0P;
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) SQ[(qq + (q >> 1)) * SS_SQS + pp + (q & 1)] = ss_mul(gr[q], gr[q]);
@@ -790,13 +796,22 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     e[q] = ss_conv25_generic(SQ + yy * SS_SQS + xx, SS_SQS, p.k25, x0 + xx >= w_vec);
                 }
             }
+            // branch-free compare/update (one FSETP + FSEL + predicated OR per pixel)
             unsigned won = 0;
+            if (full) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const bool inb = full || ((x0 + 4 * tx + (q & 3) < p.w) && (y0 + 4 * ty + (q >> 2) < p.h));
-                if (inb && (take_all || e[q] > SS_PT(be)[q])) {
-                    SS_PT(be)[q] = e[q];
-                    won |= 1u << q;
+                for (int q = 0; q < 16; ++q) {
+                    const bool w = take_all | (e[q] > SS_PT(be)[q]);
+                    SS_PT(be)[q] = w ? e[q] : SS_PT(be)[q];
+                    won |= w ? (1u << q) : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const bool inb = (x0 + 4 * tx + (q & 3) < p.w) & (y0 + 4 * ty + (q >> 2) < p.h);
+                    const bool w = inb & (take_all | (e[q] > SS_PT(be)[q]));
+                    SS_PT(be)[q] = w ? e[q] : SS_PT(be)[q];
+                    won |= w ? (1u << q) : 0u;
                 }
             }
             if (won) {

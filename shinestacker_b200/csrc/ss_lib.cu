@@ -332,8 +332,10 @@ __global__ void ss_finalize_kernel(const float *img, int h, int w, int bytes, vo
 }
 
 // ---- multi-GPU exchange helpers ---------------------------------------------
+// The running state of all levels and of the base level lives in three contiguous arrays in exchange
+// order (values, indices, 3-plane coefficients), so the exchange needs ONE kernel per step and no copies.
 // key = (float bits of the non-negative value, canonical +0) << 32 | (0xFFFFFFFF - global frame index):
-// unsigned max over ranks == "largest value, ties to the lowest global frame index" == np.argmax.
+// max over ranks == "largest value, ties to the lowest global frame index" == np.argmax.
 __global__ void ss_pack_keys_kernel(const float *val, const int32_t *idx, size_t n,
                                     unsigned long long *keys)
 {
@@ -345,9 +347,14 @@ __global__ void ss_pack_keys_kernel(const float *val, const int32_t *idx, size_t
               (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx[i]);
 }
 
+struct SsSegments {        // per plane-group (pyramid level / base plane): pixel offset, pixel count, coefficient offset
+    int count;
+    unsigned long long px_off[12], n_px[12], coef_off[12];
+};
+
 // After the max-reduction: adopt the winning (value, index); zero this rank's coefficients where it
 // lost, so that a float32 sum over ranks reproduces the winner exactly (x + 0 + ... + 0).
-__global__ void ss_adopt_keys_kernel(const unsigned long long *keys, size_t n, int planes,
+__global__ void ss_adopt_keys_kernel(const unsigned long long *keys, size_t n, const __grid_constant__ SsSegments seg,
                                      float *val, int32_t *idx, float *coeff)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,8 +364,12 @@ __global__ void ss_adopt_keys_kernel(const unsigned long long *keys, size_t n, i
     const bool mine = (win == idx[i]);
     val[i] = __uint_as_float((unsigned int)(k >> 32));
     idx[i] = win;
-    if (!mine)
-        for (int c = 0; c < planes; ++c) coeff[(size_t)c * n + i] = 0.f;
+    if (!mine) {
+        int s = 0;
+        while (s + 1 < seg.count && i >= seg.px_off[s + 1]) ++s;
+        float *c = coeff + seg.coef_off[s] + (i - seg.px_off[s]);
+        c[0] = 0.f; c[seg.n_px[s]] = 0.f; c[2 * seg.n_px[s]] = 0.f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -395,7 +406,12 @@ struct ss_handle {
     int32_t *gray = nullptr;         // max_frames x hL x wL
     unsigned int *counts = nullptr;  // max_frames x num_values
     float *log_p = nullptr;          // max_frames x num_values
-    float *best_ve = nullptr, *best_vd = nullptr, *pix_e = nullptr, *pix_d = nullptr;
+    // contiguous running state in exchange order: [level 0 .. L-1 | base entropy | base deviation]
+    float *state_val = nullptr;      // n_keys floats
+    int32_t *state_idx = nullptr;    // n_keys
+    float *state_coef = nullptr;     // n_coeffs floats: 3 planes per segment
+    SsSegments seg;
+    float *best_ve = nullptr, *best_vd = nullptr, *pix_e = nullptr, *pix_d = nullptr;   // views into the above
     float *ent = nullptr, *dev = nullptr;  // max_frames x hL x wL window entropy / variance
     int32_t *best_ie = nullptr, *best_id = nullptr;
     float *fused_base = nullptr;     // 3 x hL x wL
@@ -403,7 +419,6 @@ struct ss_handle {
     void *out_dev = nullptr;         // interleaved output image
     size_t out_pitch = 0;
     unsigned long long *keys = nullptr;  // exchange buffer
-    float *coeffs = nullptr;             // exchange buffer (packed coefficients)
     size_t n_keys = 0, n_coeffs = 0;
     // streams / events
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -499,15 +514,14 @@ SS_EXPORT void ss_destroy(ss_handle *h)
     if (h->s_comp) cudaStreamSynchronize(h->s_comp);
     if (h->s_copy) cudaStreamSynchronize(h->s_copy);
     for (auto &l : h->lv) {
-        cudaFree(l.best_e); cudaFree(l.best_idx); cudaFree(l.fused); cudaFree(l.gnext);
+        cudaFree(l.gnext);
         cudaFree(l.grp_e); cudaFree(l.grp_idx); cudaFree(l.grp_fused);
     }
     cudaFree(h->frames); cudaFree(h->base); cudaFree(h->gray); cudaFree(h->counts);
-    cudaFree(h->log_p); cudaFree(h->best_ve); cudaFree(h->best_vd); cudaFree(h->pix_e);
+    cudaFree(h->log_p); cudaFree(h->state_val); cudaFree(h->state_idx); cudaFree(h->state_coef);
     cudaFree(h->ent); cudaFree(h->dev);
-    cudaFree(h->pix_d); cudaFree(h->best_ie); cudaFree(h->best_id); cudaFree(h->fused_base);
+    cudaFree(h->fused_base);
     cudaFree(h->tmp_a); cudaFree(h->tmp_b); cudaFree(h->out_dev); cudaFree(h->keys);
-    cudaFree(h->coeffs);
     for (auto e : h->ev_copied) cudaEventDestroy(e);
     for (auto e : h->ev_done) cudaEventDestroy(e);
     for (auto &t : h->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
@@ -572,15 +586,34 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return ss_fail(SS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
     }
+    if (h->L + 2 > 12) return ss_fail(SS_ERR_SHAPE, "pyramid with %d levels is not supported (max 10)", h->L);
     h->lv.resize(h->L);
-    h->n_keys = 0;
+    {
+        // segments of the contiguous state: every level, then the two base planes
+        const size_t nbase = (size_t)h->lh[h->L] * h->lw[h->L];
+        memset(&h->seg, 0, sizeof(h->seg));
+        size_t px = 0, co = 0;
+        for (int l = 0; l < h->L + 2; ++l) {
+            const size_t n = l < h->L ? (size_t)h->lh[l] * h->lw[l] : nbase;
+            h->seg.px_off[l] = px; h->seg.n_px[l] = n; h->seg.coef_off[l] = co;
+            px += n; co += 3 * n;
+        }
+        h->seg.count = h->L + 2;
+        h->n_keys = px; h->n_coeffs = co;
+        if ((rc = ss_dalloc(&h->state_val, px))) return rc;
+        if ((rc = ss_dalloc(&h->state_idx, px))) return rc;
+        if ((rc = ss_dalloc(&h->state_coef, co))) return rc;
+        h->best_ve = h->state_val + h->seg.px_off[h->L];     h->best_ie = h->state_idx + h->seg.px_off[h->L];
+        h->best_vd = h->state_val + h->seg.px_off[h->L + 1]; h->best_id = h->state_idx + h->seg.px_off[h->L + 1];
+        h->pix_e = h->state_coef + h->seg.coef_off[h->L];    h->pix_d = h->state_coef + h->seg.coef_off[h->L + 1];
+    }
     for (int l = 0; l < h->L; ++l) {
         SsLevel &v = h->lv[l];
         v.h = h->lh[l]; v.w = h->lw[l];
         const size_t n = (size_t)v.h * v.w;
-        if ((rc = ss_dalloc(&v.best_e, n))) return rc;
-        if ((rc = ss_dalloc(&v.best_idx, n))) return rc;
-        if ((rc = ss_dalloc(&v.fused, 3 * n))) return rc;
+        v.best_e = h->state_val + h->seg.px_off[l];
+        v.best_idx = h->state_idx + h->seg.px_off[l];
+        v.fused = h->state_coef + h->seg.coef_off[l];
         v.gpitch = (h->lw[l + 1] + 3) / 4 * 4;
         {
             // frame-split so that every level launch has >= ~6 waves of CTAs (2 CTAs/SM x 148 SMs per wave):
@@ -600,23 +633,14 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
         }
         if (l + 1 < h->L)
             if ((rc = ss_dalloc(&v.gnext, (size_t)h->batch * 3 * h->lh[l + 1] * v.gpitch))) return rc;
-        h->n_keys += n;
     }
     const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
-    h->n_coeffs = 3 * h->n_keys + 6 * nb;
-    h->n_keys += 2 * nb;
     if ((rc = ss_dalloc(&h->base, (size_t)cfg->max_frames * 3 * nb))) return rc;
     if ((rc = ss_dalloc(&h->gray, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->counts, (size_t)cfg->max_frames * h->num_values))) return rc;
     if ((rc = ss_dalloc(&h->log_p, (size_t)cfg->max_frames * ((size_t)h->num_values > nb ? (size_t)h->num_values : nb)))) return rc;
     if ((rc = ss_dalloc(&h->ent, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->dev, (size_t)cfg->max_frames * nb))) return rc;
-    if ((rc = ss_dalloc(&h->best_ve, nb))) return rc;
-    if ((rc = ss_dalloc(&h->best_vd, nb))) return rc;
-    if ((rc = ss_dalloc(&h->best_ie, nb))) return rc;
-    if ((rc = ss_dalloc(&h->best_id, nb))) return rc;
-    if ((rc = ss_dalloc(&h->pix_e, 3 * nb))) return rc;
-    if ((rc = ss_dalloc(&h->pix_d, 3 * nb))) return rc;
     if ((rc = ss_dalloc(&h->fused_base, 3 * nb))) return rc;
     if (h->L >= 2) {
         // collapse intermediates: the largest one is level 1
@@ -1153,33 +1177,16 @@ SS_EXPORT int ss_launch_count(ss_handle *h, int64_t *launches)
 }
 
 // ---- multi-GPU exchange ---------------------------------------------------------------------------
-// Packed layout: keys = [level 0 .. L-1 energies | base entropy | base deviation];
-// coeffs = [level 0 .. L-1 fused (3 planes each) | pix_e (3 planes) | pix_d (3 planes)].
-static int ss_ensure_exchange(ss_handle *h)
-{
-    int rc;
-    if (!h->keys && (rc = ss_dalloc(&h->keys, h->n_keys))) return rc;
-    if (!h->coeffs && (rc = ss_dalloc(&h->coeffs, h->n_coeffs))) return rc;
-    return 0;
-}
-
+// Packed layout (== the layout of the running state itself): keys = [level 0 .. L-1 energies | base entropy |
+// base deviation]; coeffs = [level 0 .. L-1 fused (3 planes each) | pix_e (3 planes) | pix_d (3 planes)].
 SS_EXPORT int ss_exchange_keys(ss_handle *h, uint64_t **d_keys, size_t *count)
 {
     if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin/select_base first");
     SS_CUDA(cudaSetDevice(h->cfg.device));
-    int rc = ss_ensure_exchange(h);
-    if (rc) return rc;
-    size_t off = 0;
-    for (int l = 0; l < h->L; ++l) {
-        const size_t n = (size_t)h->lh[l] * h->lw[l];
-        ss_pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->s_comp>>>(h->lv[l].best_e, h->lv[l].best_idx, n, h->keys + off);
-        off += n;
-    }
-    const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
-    ss_pack_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->s_comp>>>(h->best_ve, h->best_ie, nb, h->keys + off);
-    off += nb;
-    ss_pack_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->s_comp>>>(h->best_vd, h->best_id, nb, h->keys + off);
-    h->launches += h->L + 2;
+    int rc;
+    if (!h->keys && (rc = ss_dalloc(&h->keys, h->n_keys))) return rc;
+    ss_pack_keys_kernel<<<(unsigned)((h->n_keys + 255) / 256), 256, 0, h->s_comp>>>(h->state_val, h->state_idx, h->n_keys, h->keys);
+    h->launches++;
     SS_CUDA(cudaGetLastError());
     SS_CUDA(cudaStreamSynchronize(h->s_comp));
     if (d_keys) *d_keys = (uint64_t *)h->keys;
@@ -1191,44 +1198,20 @@ SS_EXPORT int ss_exchange_mask_losers(ss_handle *h, float **d_coeffs, size_t *co
 {
     if (!h || !h->keys) return ss_fail(SS_ERR_STATE, "ss_exchange_keys first");
     SS_CUDA(cudaSetDevice(h->cfg.device));
-    size_t off = 0, coff = 0;
-    for (int l = 0; l < h->L; ++l) {
-        const size_t n = (size_t)h->lh[l] * h->lw[l];
-        ss_adopt_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->s_comp>>>(h->keys + off, n, 3, h->lv[l].best_e,
-                                                                               h->lv[l].best_idx, h->lv[l].fused);
-        SS_CUDA(cudaMemcpyAsync(h->coeffs + coff, h->lv[l].fused, 3 * n * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
-        off += n;
-        coff += 3 * n;
-    }
-    const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
-    ss_adopt_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->s_comp>>>(h->keys + off, nb, 3, h->best_ve, h->best_ie, h->pix_e);
-    SS_CUDA(cudaMemcpyAsync(h->coeffs + coff, h->pix_e, 3 * nb * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
-    off += nb; coff += 3 * nb;
-    ss_adopt_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->s_comp>>>(h->keys + off, nb, 3, h->best_vd, h->best_id, h->pix_d);
-    SS_CUDA(cudaMemcpyAsync(h->coeffs + coff, h->pix_d, 3 * nb * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
-    h->launches += h->L + 2;
+    ss_adopt_keys_kernel<<<(unsigned)((h->n_keys + 255) / 256), 256, 0, h->s_comp>>>(h->keys, h->n_keys, h->seg, h->state_val,
+                                                                                       h->state_idx, h->state_coef);
+    h->launches++;
     SS_CUDA(cudaGetLastError());
     SS_CUDA(cudaStreamSynchronize(h->s_comp));
-    if (d_coeffs) *d_coeffs = h->coeffs;
+    if (d_coeffs) *d_coeffs = h->state_coef;   // the running coefficients themselves: reduced in place
     if (count) *count = h->n_coeffs;
     return 0;
 }
 
 SS_EXPORT int ss_exchange_adopt(ss_handle *h)
 {
-    if (!h || !h->coeffs) return ss_fail(SS_ERR_STATE, "ss_exchange_mask_losers first");
-    SS_CUDA(cudaSetDevice(h->cfg.device));
-    size_t coff = 0;
-    for (int l = 0; l < h->L; ++l) {
-        const size_t n = (size_t)h->lh[l] * h->lw[l];
-        SS_CUDA(cudaMemcpyAsync(h->lv[l].fused, h->coeffs + coff, 3 * n * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
-        coff += 3 * n;
-    }
-    const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
-    SS_CUDA(cudaMemcpyAsync(h->pix_e, h->coeffs + coff, 3 * nb * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
-    coff += 3 * nb;
-    SS_CUDA(cudaMemcpyAsync(h->pix_d, h->coeffs + coff, 3 * nb * sizeof(float), cudaMemcpyDeviceToDevice, h->s_comp));
-    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    // the sum-reduction wrote straight into the root's running state: nothing to copy
+    if (!h || !h->keys) return ss_fail(SS_ERR_STATE, "ss_exchange_mask_losers first");
     return 0;
 }
 

@@ -326,6 +326,15 @@ def main():
                          "one launch)" if traffic else None, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_launch,
                          "peak_source": peak_src},
         }
+        # the bound that actually limits this kernel: bit-exact sequential FP32 chains.
+        # Algorithmic chain steps per level-0 pixel and frame: reduce 25*3/4, expand 6.25*3 + 3, gray^2 4,
+        # energy 25, convert 3, compare 1 = 73.5; peak = scalar FFMA rate measured on this pool's B200s with
+        # tools/microbench.cu (profiles/r1_microbench_fp32_issue.txt): 36.2 TFMA/s.
+        fp32_ops = 73.5 * n_local * H * W
+        fp32_rate = fp32_ops / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+        line["roofline_fp32"] = {"bound": "fp32 issue", "achieved": fp32_rate, "peak": 36.2, "unit": "TFMA/s",
+                                 "frac": fp32_rate / 36.2, "algorithmic_chain_steps_per_pixel": 73.5,
+                                 "peak_source": "tools/microbench.cu on B200 (scalar FFMA, 124.5 of 128 lanes/clk/SM)"}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline(a, max(1, min(a.cpu_sample_frames, N)))
         print(json.dumps(line))

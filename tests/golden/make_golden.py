@@ -35,6 +35,7 @@ CASES = [
     ("syn_u8_4x96x150_ks3", "stack", 4, 96, 150, "uint8", 8, {"kernel_size": 3}),
     ("noise_u8_6x257x385", "noise", 6, 257, 385, "uint8", 9, {}),
     ("syn_u8_2x40x50_nolevels", "stack", 2, 40, 50, "uint8", 10, {}),
+    ("noise_u8_64x96x136", "noise", 64, 96, 136, "uint8", 11, {}),
 ]
 
 
@@ -62,7 +63,8 @@ def main():
     import cv2
     ex = "/root/reference/examples/input"
     for sub, flag, y0, x0, hh, ww in (("img-jpg", cv2.IMREAD_COLOR, 500, 800, 256, 384),
-                                      ("img-tif", cv2.IMREAD_UNCHANGED, 520, 760, 200, 264)):
+                                      ("img-tif", cv2.IMREAD_UNCHANGED, 520, 760, 200, 264),
+                                      ("amber-flies", cv2.IMREAD_COLOR, 300, 500, 192, 272)):
         files = sorted(os.listdir(os.path.join(ex, sub)))
         frames = [np.ascontiguousarray(cv2.imread(os.path.join(ex, sub, f), flag)[y0:y0 + hh, x0:x0 + ww])
                   for f in files]

@@ -46,7 +46,7 @@ typedef struct ss_config {
     int32_t min_size;          /* PyramidStack(min_size=32): levels = int(log2(min(H,W)/min_size))  */
     int32_t kernel_size;       /* PyramidStack(kernel_size=5): base-level entropy/variance window   */
     double gen_kernel;         /* PyramidStack(gen_kernel=0.4): Burt-Adelson 'a'                    */
-    int32_t float_bits;        /* PyramidStack(float_type): 32 ('float-32'); 64 is rejected         */
+    int32_t float_bits;        /* PyramidStack(float_type): 32 ('float-32') or 64 ('float-64')      */
     int32_t device;            /* CUDA device ordinal                                               */
     int32_t max_frames;        /* capacity of the device-resident frame store (>= frames pushed)    */
     int32_t batch_frames;      /* frames fused per kernel-chain launch (0 = default)                */
@@ -150,6 +150,10 @@ int ss_finish_select_base(ss_handle *h, const float *log_prob);
  * truncated gray base levels (n_frames x hL x wL int32) the host needs to build it (np.unique per frame,
  * exactly as PyramidBase.entropy does, pyramid.py:67-69). */
 int ss_get_base_gray(ss_handle *h, int32_t *out);
+/* float_type = 'float-64' (reference base_stack_algo.py:15-16): the same step with the float64 table
+ * np.log(probabilities) (n_frames x num_values, or per base pixel when per_px != 0; NULL -> libm log); it
+ * also blends the base level.  ss_finish_collapse follows as usual. */
+int ss_finish_select_base_f64(ss_handle *h, const double *log_prob, int per_px);
 int ss_finish_select_base_px(ss_handle *h, const float *log_prob_px);
 int ss_finish_collapse(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
 /* Time of the i-th timed segment (one per launched batch, then histogram, base select, collapse). */

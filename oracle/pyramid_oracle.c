@@ -377,3 +377,153 @@ SO_API int so_set_threads(int n)
     return 1;
 #endif
 }
+
+/* ======================= float_type = 'float-64' (reference base_stack_algo.py:15-16) =======================
+ * With float64 images cv2.filter2D accumulates the 25 taps sequentially with separate multiply and add in
+ * float64 (no FMA, no tail rule; probed against cv2 4.13.0), using the float64 kernel as given.  Gray,
+ * energy and the arg-max stay float32 (pyramid.py:49: lap.astype(np.float32)). */
+SO_API void so_make_kernel_f64(double gen_kernel, double *k25)
+{
+    double k[5] = {0.25 - gen_kernel / 2.0, 0.25, gen_kernel, 0.25, 0.25 - gen_kernel / 2.0};
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 5; ++j) k25[i * 5 + j] = k[i] * k[j];
+}
+
+SO_API void so_reduce_f64(const double *src, int h, int w, const double *k25, double *dst)
+{
+    const int h2 = (h + 1) / 2, w2 = (w + 1) / 2;
+#pragma omp parallel for schedule(static)
+    for (int yo = 0; yo < h2; ++yo)
+        for (int xo = 0; xo < w2; ++xo) {
+            double acc = 0.0;
+            for (int dy = 0; dy < 5; ++dy)
+                for (int dx = 0; dx < 5; ++dx)
+                    acc = acc + src[(size_t)refl101(2 * yo + dy - 2, h) * w + refl101(2 * xo + dx - 2, w)] * k25[dy * 5 + dx];
+            dst[(size_t)yo * w2 + xo] = acc;
+        }
+}
+
+SO_API void so_expand_f64(const double *src, int h, int w, const double *k25, double *dst, int out_h, int out_w)
+{
+    const int H = 2 * h, W = 2 * w;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < out_h; ++y)
+        for (int x = 0; x < out_w; ++x) {
+            double acc = 0.0;
+            for (int dy = 0; dy < 5; ++dy) {
+                int yy = refl101(y + dy - 2, H);
+                if (yy & 1) continue;
+                for (int dx = 0; dx < 5; ++dx) {
+                    int xx = refl101(x + dx - 2, W);
+                    if (xx & 1) continue;
+                    acc = acc + src[(size_t)(yy >> 1) * w + (xx >> 1)] * k25[dy * 5 + dx];
+                }
+            }
+            dst[(size_t)y * out_w + x] = 4.0 * acc;
+        }
+}
+
+SO_API void so_laplacian_f64(const double *g, int h, int w, const double *g_next, int h2, int w2,
+                             const double *k25, double *lap)
+{
+    so_expand_f64(g_next, h2, w2, k25, lap, h, w);
+    size_t n = (size_t)h * w;
+    for (size_t i = 0; i < n; ++i) lap[i] = g[i] - lap[i];
+}
+
+SO_API void so_collapse_step_f64(const double *img, int h_in, int w_in, const double *layer, int h, int w,
+                                 const double *k25, double *out)
+{
+    so_expand_f64(img, h_in, w_in, k25, out, h, w);
+    size_t n = (size_t)h * w;
+    for (size_t i = 0; i < n; ++i) out[i] = out[i] + layer[i];
+}
+
+SO_API void so_split_planes_f64(const void *img, size_t n, int bytes_per_sample, double *b, double *g, double *r)
+{
+    for (size_t i = 0; i < n; ++i) {
+        if (bytes_per_sample == 1) {
+            const uint8_t *p = (const uint8_t *)img + i * 3;
+            b[i] = p[0]; g[i] = p[1]; r[i] = p[2];
+        } else {
+            const uint16_t *p = (const uint16_t *)img + i * 3;
+            b[i] = p[0]; g[i] = p[1]; r[i] = p[2];
+        }
+    }
+}
+
+SO_API void so_finalize_plane_f64(const double *img, size_t n, int bytes_per_sample, int channel, void *out_interleaved)
+{
+    const double maxv = bytes_per_sample == 1 ? 255.0 : 65535.0;
+    for (size_t i = 0; i < n; ++i) {
+        double v = fabs(img[i]);
+        v = v < 0.0 ? 0.0 : (v > maxv ? maxv : v);
+        if (bytes_per_sample == 1) ((uint8_t *)out_interleaved)[i * 3 + channel] = (uint8_t)v;
+        else ((uint16_t *)out_interleaved)[i * 3 + channel] = (uint16_t)v;
+    }
+}
+
+static double np_pairwise_sum_f64(const double *a, int n)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return np_pairwise_sum_f64(a, n2) + np_pairwise_sum_f64(a + n2, n - n2);
+    }
+}
+
+/* entropy / deviation with float_type = float64 (pyramid.py:66-93): same expressions, float64 throughout. */
+SO_API void so_entropy_map_f64(const int32_t *gray, int h, int w, int ksize, const double *log_p, double *out)
+{
+    const int pad = (ksize - 1) / 2, side = 2 * pad + 1, n = side * side;
+    for (int y = 0; y < h; ++y) {
+        double buf[1024];
+        for (int x = 0; x < w; ++x) {
+            int c = 0;
+            for (int dy = -pad; dy <= pad; ++dy)
+                for (int dx = -pad; dx <= pad; ++dx) {
+                    int v = gray[(size_t)refl101(y + dy, h) * w + refl101(x + dx, w)];
+                    buf[c++] = (double)v * log_p[v];
+                }
+            out[(size_t)y * w + x] = -1.0 * np_pairwise_sum_f64(buf, n);
+        }
+    }
+}
+
+SO_API void so_deviation_map_f64(const int32_t *gray, int h, int w, int ksize, double *out)
+{
+    const int pad = (ksize - 1) / 2, side = 2 * pad + 1, n = side * side;
+    for (int y = 0; y < h; ++y) {
+        double buf[1024];
+        int32_t vals[1024];
+        for (int x = 0; x < w; ++x) {
+            int c = 0;
+            int64_t s = 0;
+            for (int dy = -pad; dy <= pad; ++dy)
+                for (int dx = -pad; dx <= pad; ++dx) {
+                    int v = gray[(size_t)refl101(y + dy, h) * w + refl101(x + dx, w)];
+                    vals[c++] = v;
+                    s += v;
+                }
+            double mean = (double)s / (double)n;
+            for (int i = 0; i < n; ++i) {
+                double d = (double)vals[i] - mean;
+                buf[i] = d * d;
+            }
+            out[(size_t)y * w + x] = np_pairwise_sum_f64(buf, n) / (double)n;
+        }
+    }
+}

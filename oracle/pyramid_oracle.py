@@ -186,6 +186,106 @@ def deviation_map(gray, ksize=5):
     return out
 
 
+class StreamingStack64:
+    """float_type='float-64' variant (reference base_stack_algo.py:15-16): Gaussian / Laplacian pyramids,
+    base blend and collapse in float64 with cv2's float64 filter2D order (sequential multiply + add); gray,
+    energy and the per-level arg-max stay float32 (pyramid.py:49); entropy / deviation are float64."""
+
+    def __init__(self, min_size=32, kernel_size=5, gen_kernel=0.4):
+        self.min_size, self.kernel_size = min_size, kernel_size
+        self.k32 = make_kernel(gen_kernel)
+        self.k64 = np.zeros(25, dtype=np.float64)
+        lib().so_make_kernel_f64(ctypes.c_double(gen_kernel), _p(self.k64))
+        self.n = 0
+        self.state = None
+
+    def _pyramid(self, img):
+        L = lib()
+        h, w, _ = img.shape
+        planes = np.empty((3, h, w), np.float64)
+        L.so_split_planes_f64(_p(np.ascontiguousarray(img)), ctypes.c_size_t(h * w), img.dtype.itemsize,
+                              _p(planes[0]), _p(planes[1]), _p(planes[2]))
+        gp = [planes]
+        for _ in range(self.levels):
+            cur = gp[-1]
+            hh, ww = cur.shape[1:]
+            nxt = np.empty((3, (hh + 1) // 2, (ww + 1) // 2), np.float64)
+            for c in range(3):
+                L.so_reduce_f64(_p(cur[c]), hh, ww, _p(self.k64), _p(nxt[c]))
+            if min(nxt.shape[1:]) < 4:
+                break
+            gp.append(nxt)
+        out = []
+        for l in range(len(gp) - 1):
+            g, gn = gp[l], gp[l + 1]
+            lap = np.empty_like(g)
+            for c in range(3):
+                L.so_laplacian_f64(_p(g[c]), g.shape[1], g.shape[2], _p(gn[c]), gn.shape[1], gn.shape[2],
+                                   _p(self.k64), _p(lap[c]))
+            out.append(lap)
+        out.append(gp[-1])
+        return out
+
+    def push(self, img):
+        if self.n == 0:
+            self.shape, self.dtype = img.shape, img.dtype
+            self.levels = num_levels(img.shape[0], img.shape[1], self.min_size)
+        pyr = self._pyramid(img)
+        first = self.n == 0
+        if first:
+            self.state = [dict(e=np.empty(l.shape[1:], np.float32), idx=np.empty(l.shape[1:], np.int32),
+                               fused=np.empty(l.shape, np.float64)) for l in pyr[:-1]]
+            sh = pyr[-1].shape
+            self.base = dict(ve=np.empty(sh[1:], np.float64), ie=np.empty(sh[1:], np.int32),
+                             vd=np.empty(sh[1:], np.float64), id=np.empty(sh[1:], np.int32),
+                             pe=np.empty(sh, np.float64), pd=np.empty(sh, np.float64))
+        for lap, st in zip(pyr[:-1], self.state):
+            e = energy(np.ascontiguousarray(lap.astype(np.float32)), self.k32)
+            upd = np.ones(e.shape, bool) if first else e > st["e"]
+            st["e"][upd] = e[upd]
+            st["idx"][upd] = self.n
+            st["fused"][:, upd] = 0.0 + lap[:, upd]
+        base = pyr[-1]
+        gray = base_gray(np.ascontiguousarray(base.astype(np.float32)))
+        nvals = 256 if self.dtype == np.uint8 else 65536
+        counts = np.bincount(gray.ravel(), minlength=nvals).astype(np.int64)
+        prob = np.zeros(nvals, dtype=np.float64)
+        nz = counts > 0
+        prob[nz] = counts[nz].astype(np.float64) / counts.sum()
+        with np.errstate(divide="ignore"):
+            logp = np.log(prob)
+        h, w = gray.shape
+        ent = np.empty((h, w), np.float64)
+        dev = np.empty((h, w), np.float64)
+        lib().so_entropy_map_f64(_p(gray), h, w, int(self.kernel_size), _p(logp), _p(ent))
+        lib().so_deviation_map_f64(_p(gray), h, w, int(self.kernel_size), _p(dev))
+        b = self.base
+        for val, bv, bi, bp in ((ent, b["ve"], b["ie"], b["pe"]), (dev, b["vd"], b["id"], b["pd"])):
+            upd = np.ones(val.shape, bool) if first else val > bv
+            bv[upd] = val[upd]
+            bi[upd] = self.n
+            bp[:, upd] = base[:, upd]
+        self.n += 1
+
+    def finish(self):
+        L = lib()
+        b = self.base
+        img = ((0.0 + b["pe"]) + b["pd"]) / 2
+        for st in self.state[::-1]:
+            lay = st["fused"]
+            nxt = np.empty_like(lay)
+            for c in range(3):
+                L.so_collapse_step_f64(_p(np.ascontiguousarray(img[c])), img.shape[1], img.shape[2], _p(lay[c]),
+                                       lay.shape[1], lay.shape[2], _p(self.k64), _p(nxt[c]))
+            img = nxt
+        _, H, W = img.shape
+        out = np.empty((H, W, 3), dtype=self.dtype)
+        for c in range(3):
+            L.so_finalize_plane_f64(_p(np.ascontiguousarray(img[c])), ctypes.c_size_t(H * W), self.dtype.itemsize, c, _p(out))
+        info = dict(best=[st["idx"] for st in self.state], best_e=b["ie"], best_d=b["id"], levels=len(self.state))
+        return out, info
+
+
 class StreamingStack:
     """Streaming restatement of PyramidStack.focus_stack (pyramid.py:150-179).
 
@@ -267,9 +367,9 @@ class StreamingStack:
         return out, info
 
 
-def focus_stack(frames, min_size=32, kernel_size=5, gen_kernel=0.4):
+def focus_stack(frames, min_size=32, kernel_size=5, gen_kernel=0.4, float_type='float-32'):
     """Oracle entry point: list/iterable of HxWx3 u8/u16 BGR frames -> (fused image, info)."""
-    s = StreamingStack(min_size, kernel_size, gen_kernel)
+    s = (StreamingStack64 if float_type == 'float-64' else StreamingStack)(min_size, kernel_size, gen_kernel)
     for f in frames:
         s.push(f)
     return s.finish()

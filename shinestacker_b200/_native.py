@@ -76,6 +76,7 @@ SIGNATURES = {
     "ss_rerun_resident": (_i, [_vp]),
     "ss_finish_select_base": (_i, [_vp, _vp]),
     "ss_get_base_gray": (_i, [_vp, _vp]),
+    "ss_finish_select_base_f64": (_i, [_vp, _vp, _i]),
     "ss_finish_select_base_px": (_i, [_vp, _vp]),
     "ss_finish_collapse": (_i, [_vp, _vp, _sz]),
     "ss_segment_time_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float)]),

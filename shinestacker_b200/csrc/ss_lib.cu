@@ -13,6 +13,7 @@
 
 #include "../../include/shinestack_b200.h"
 #include "ss_kernels.cuh"
+#include "ss_f64.cuh"
 
 #define SS_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -435,6 +436,16 @@ struct ss_handle {
     bool finished_begin = false;
     bool have_state = false;
     long long launches = 0;
+    // ---- float_type = 'float-64' path (ss_f64.cuh): one frame at a time, all state in global memory -----
+    bool f64 = false;
+    Ss64Kernel k64;
+    std::vector<double *> g64;        // Gaussian pyramid of the current frame, levels 0..L-1 (3 planes each)
+    std::vector<double *> fused64;    // running winner coefficients per level (3 planes)
+    double *lap64 = nullptr;          // Laplacian of the current frame / level (3 planes of level 0)
+    float *sq64 = nullptr;            // gray^2 plane
+    double *base64 = nullptr;         // max_frames x 3 x hL x wL
+    double *logp64 = nullptr, *ent64 = nullptr, *dev64 = nullptr, *fusedbase64 = nullptr;
+    double *tmp64_a = nullptr, *tmp64_b = nullptr;
 };
 
 static int ss_levels_for(int h, int w, int min_size, std::vector<int> &lh, std::vector<int> &lw)
@@ -526,6 +537,10 @@ SS_EXPORT void ss_destroy(ss_handle *h)
     for (auto e : h->ev_done) cudaEventDestroy(e);
     for (auto &t : h->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
     for (auto &t : h->ltimers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto p64 : h->g64) cudaFree(p64);
+    for (auto p64 : h->fused64) cudaFree(p64);
+    cudaFree(h->lap64); cudaFree(h->sq64); cudaFree(h->base64); cudaFree(h->logp64); cudaFree(h->ent64);
+    cudaFree(h->dev64); cudaFree(h->fusedbase64); cudaFree(h->tmp64_a); cudaFree(h->tmp64_b);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     delete h;
@@ -544,7 +559,7 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     ss_make_kernel(cfg->gen_kernel, h->k25);
     h->side = 2 * ((cfg->kernel_size - 1) / 2) + 1;  // len(arange(-pad, pad+1)), pyramid.py:18,120
     h->num_values = cfg->bytes_per_sample == 1 ? 256 : 65536;
-    h->batch = cfg->batch_frames > 0 ? cfg->batch_frames : 8;
+    h->batch = cfg->float_bits == 64 ? 1 : (cfg->batch_frames > 0 ? cfg->batch_frames : 8);   // float-64: frame by frame
     if (h->batch > cfg->max_frames) h->batch = cfg->max_frames;
     // frame ring: all frames resident when they fit the request, else two batches
     h->n_slots = cfg->resident_frames > 0 ? cfg->resident_frames : 2 * h->batch;
@@ -650,6 +665,35 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     }
     h->out_pitch = (size_t)cfg->width * 3 * cfg->bytes_per_sample;
     if ((rc = ss_dalloc((char **)&h->out_dev, h->out_pitch * cfg->height))) return rc;
+    if (cfg->float_bits == 64) {
+        h->f64 = true;
+        const double a = cfg->gen_kernel;
+        const double k1[5] = {0.25 - a / 2.0, 0.25, a, 0.25, 0.25 - a / 2.0};
+        for (int i = 0; i < 5; ++i)
+            for (int j = 0; j < 5; ++j) {
+                h->k64.k[i * 5 + j] = k1[i] * k1[j];
+                h->k64.kf[i * 5 + j] = (float)(k1[i] * k1[j]);
+            }
+        h->g64.assign(h->L + 1, nullptr);
+        h->fused64.assign(h->L, nullptr);
+        for (int l = 0; l <= h->L; ++l)
+            if ((rc = ss_dalloc(&h->g64[l], 3 * (size_t)h->lh[l] * h->lw[l]))) return rc;
+        for (int l = 0; l < h->L; ++l)
+            if ((rc = ss_dalloc(&h->fused64[l], 3 * (size_t)h->lh[l] * h->lw[l]))) return rc;
+        const size_t n0 = (size_t)h->lh[0] * h->lw[0];
+        if ((rc = ss_dalloc(&h->lap64, 3 * n0))) return rc;
+        if ((rc = ss_dalloc(&h->sq64, n0))) return rc;
+        if ((rc = ss_dalloc(&h->base64, (size_t)cfg->max_frames * 3 * nb))) return rc;
+        if ((rc = ss_dalloc(&h->logp64, (size_t)cfg->max_frames * ((size_t)h->num_values > nb ? (size_t)h->num_values : nb)))) return rc;
+        if ((rc = ss_dalloc(&h->ent64, (size_t)cfg->max_frames * nb))) return rc;
+        if ((rc = ss_dalloc(&h->dev64, (size_t)cfg->max_frames * nb))) return rc;
+        if ((rc = ss_dalloc(&h->fusedbase64, 3 * nb))) return rc;
+        if (h->L >= 2) {
+            const size_t n1 = 3 * (size_t)h->lh[1] * h->lw[1];
+            if ((rc = ss_dalloc(&h->tmp64_a, n1))) return rc;
+            if ((rc = ss_dalloc(&h->tmp64_b, n1))) return rc;
+        }
+    }
     SS_CUDA(cudaFuncSetAttribute(ss_level_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)SS_SMEM_BYTES));
     SS_CUDA(cudaFuncSetAttribute(ss_level_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -663,9 +707,9 @@ SS_EXPORT int ss_create(const ss_config *cfg, ss_handle **out)
 {
     if (!cfg || !out) return ss_fail(SS_ERR_INVALID_OPTION, "null argument");
     *out = nullptr;
-    if (cfg->float_bits != 32)
-        return ss_fail(SS_ERR_INVALID_OPTION, "float_type: only float-32 is implemented on the GPU "
-                       "path (got %d bits)", cfg->float_bits);
+    if (cfg->float_bits != 32 && cfg->float_bits != 64)
+        return ss_fail(SS_ERR_INVALID_OPTION, "float_type: valid values are float-32 and float-64 (got %d bits)",
+                       cfg->float_bits);
     if (cfg->bytes_per_sample != 1 && cfg->bytes_per_sample != 2)
         return ss_fail(SS_ERR_BIT_DEPTH, "bytes_per_sample must be 1 or 2 (got %d)", cfg->bytes_per_sample);
     if (cfg->width < 4 || cfg->height < 4)
@@ -732,9 +776,55 @@ SS_EXPORT int ss_host_free(void *ptr)
     return 0;
 }
 
+// float-64 path: the chain of one frame (ss_f64.cuh).
+static int ss64_launch_frame(ss_handle *h, int f)
+{
+    const int L = h->L;
+    const size_t nb = (size_t)h->lh[L] * h->lw[L];
+    const char *src = h->frames + (size_t)(f % h->n_slots) * h->frame_bytes + h->frame_shift;
+    int rc;
+    if ((rc = ss_timer_begin(h))) return rc;
+    {
+        dim3 g((h->cfg.width + 127) / 128, h->cfg.height);
+        if (h->cfg.bytes_per_sample == 1)
+            ss64_convert_kernel<uint8_t><<<g, 128, 0, h->s_comp>>>((const uint8_t *)src, (int)h->frame_pitch, h->cfg.height,
+                                                                    h->cfg.width, h->g64[0]);
+        else
+            ss64_convert_kernel<uint16_t><<<g, 128, 0, h->s_comp>>>((const uint16_t *)src, (int)h->frame_pitch, h->cfg.height,
+                                                                     h->cfg.width, h->g64[0]);
+        h->launches++;
+    }
+    for (int l = 0; l < L; ++l) {
+        dim3 g((h->lw[l + 1] + 127) / 128, h->lh[l + 1], 3);
+        ss64_reduce_kernel<<<g, 128, 0, h->s_comp>>>(h->g64[l], h->lh[l], h->lw[l], h->g64[l + 1], h->lh[l + 1], h->lw[l + 1], h->k64);
+        h->launches++;
+    }
+    for (int l = 0; l < L; ++l) {
+        dim3 g((h->lw[l] + 127) / 128, h->lh[l]);
+        ss64_lap_kernel<<<g, 128, 0, h->s_comp>>>(h->g64[l], h->lh[l], h->lw[l], h->g64[l + 1], h->lh[l + 1], h->lw[l + 1],
+                                                   h->k64, h->lap64, h->sq64);
+        ss64_energy_select_kernel<<<g, 128, 0, h->s_comp>>>(h->sq64, h->lh[l], h->lw[l], h->k64, h->lap64,
+                                                             h->cfg.frame_index_base + f, h->have_state ? 0 : 1,
+                                                             h->lv[l].best_e, h->lv[l].best_idx, h->fused64[l]);
+        h->launches += 2;
+    }
+    SS_CUDA(cudaMemcpyAsync(h->base64 + (size_t)f * 3 * nb, h->g64[L], 3 * nb * sizeof(double), cudaMemcpyDeviceToDevice, h->s_comp));
+    SS_CUDA(cudaGetLastError());
+    if ((rc = ss_timer_end(h))) return rc;
+    h->have_state = true;
+    return 0;
+}
+
 // Launch the per-level kernel chain for frames [f0, f1) (all inside one batch slot).
 static int ss_launch_batch(ss_handle *h, int f0, int f1)
 {
+    if (h->f64) {
+        for (int f = f0; f < f1; ++f) {
+            const int rc = ss64_launch_frame(h, f);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     const int nf = f1 - f0;
     const int slot0 = f0 % h->n_slots;
     const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
@@ -921,9 +1011,17 @@ SS_EXPORT int ss_finish_begin(ss_handle *h, int64_t *counts)
         const int nb = h->lh[h->L] * h->lw[h->L];
         if ((rc = ss_timer_begin(h))) return rc;
         SS_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(unsigned int) * h->num_values * h->n_pushed, h->s_comp));
-        dim3 g((nb + 255) / 256, h->n_pushed);
-        ss_base_gray_hist_kernel<<<g, 256, 0, h->s_comp>>>(h->base, nb, h->gray, h->counts, h->num_values);
-        h->launches++;
+        if (h->f64) {
+            for (int f = 0; f < h->n_pushed; ++f) {
+                ss64_base_gray_hist_kernel<<<(nb + 255) / 256, 256, 0, h->s_comp>>>(h->base64 + (size_t)f * 3 * nb, nb,
+                    h->gray + (size_t)f * nb, h->counts + (size_t)f * h->num_values, h->num_values);
+                h->launches++;
+            }
+        } else {
+            dim3 g((nb + 255) / 256, h->n_pushed);
+            ss_base_gray_hist_kernel<<<g, 256, 0, h->s_comp>>>(h->base, nb, h->gray, h->counts, h->num_values);
+            h->launches++;
+        }
         SS_CUDA(cudaGetLastError());
         if ((rc = ss_timer_end(h))) return rc;
         h->finished_begin = true;
@@ -942,6 +1040,7 @@ SS_EXPORT int ss_finish_begin(ss_handle *h, int64_t *counts)
 static int ss_select_base_impl(ss_handle *h, const float *log_prob, int per_px)
 {
     if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin must be called first");
+    if (h->f64) return ss_fail(SS_ERR_STATE, "float-64 handle: use ss_finish_select_base_f64");
     SS_CUDA(cudaSetDevice(h->cfg.device));
     const int nb = h->lh[h->L] * h->lw[h->L];
     const size_t n = (size_t)h->n_pushed * (per_px ? (size_t)nb : (size_t)h->num_values);
@@ -991,6 +1090,41 @@ SS_EXPORT int ss_finish_select_base_px(ss_handle *h, const float *log_prob_px)
     return ss_select_base_impl(h, log_prob_px, 1);
 }
 
+// float_type = 'float-64': the table np.log(probabilities) in float64 (n_frames x num_values, or per base pixel
+// when per_px != 0); NULL -> libm log.  Also blends the base (the float-64 state is not exchangeable).
+SS_EXPORT int ss_finish_select_base_f64(ss_handle *h, const double *log_prob, int per_px)
+{
+    if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin must be called first");
+    if (!h->f64) return ss_fail(SS_ERR_STATE, "not a float-64 handle");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const int nb = h->lh[h->L] * h->lw[h->L];
+    std::vector<double> tab;
+    if (!log_prob) {
+        const size_t nc = (size_t)h->n_pushed * h->num_values;
+        std::vector<unsigned int> cnt(nc);
+        SS_CUDA(cudaMemcpyAsync(cnt.data(), h->counts, nc * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_comp));
+        SS_CUDA(cudaStreamSynchronize(h->s_comp));
+        tab.resize(nc);
+        for (size_t i = 0; i < nc; ++i) tab[i] = cnt[i] ? log((double)cnt[i] / (double)nb) : -INFINITY;
+        log_prob = tab.data();
+        per_px = 0;
+    }
+    const size_t n = (size_t)h->n_pushed * (per_px ? (size_t)nb : (size_t)h->num_values);
+    SS_CUDA(cudaMemcpyAsync(h->logp64, log_prob, n * sizeof(double), cudaMemcpyHostToDevice, h->s_comp));
+    if (!tab.empty()) SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    int rc;
+    if ((rc = ss_timer_begin(h))) return rc;
+    dim3 g((nb + 63) / 64, h->n_pushed);
+    ss64_base_metrics_kernel<<<g, 64, 0, h->s_comp>>>(h->gray, h->logp64, per_px, h->lh[h->L], h->lw[h->L], h->num_values,
+                                                        h->side, h->ent64, h->dev64);
+    ss64_base_select_fuse_kernel<<<(nb + 127) / 128, 128, 0, h->s_comp>>>(h->ent64, h->dev64, h->base64, nb, h->n_pushed,
+        h->cfg.frame_index_base, h->best_ie, h->best_id, h->fusedbase64);
+    h->launches += 2;
+    SS_CUDA(cudaGetLastError());
+    if ((rc = ss_timer_end(h))) return rc;
+    return 0;
+}
+
 // Truncated gray base level of every pushed frame (n_frames x hL x wL int32), after ss_finish_begin.
 SS_EXPORT int ss_get_base_gray(ss_handle *h, int32_t *out)
 {
@@ -1011,6 +1145,35 @@ SS_EXPORT int ss_finish_collapse(ss_handle *h, void *out_bgr, size_t out_row_pit
     const int L = h->L;
     const size_t nb = (size_t)h->lh[L] * h->lw[L];
     int rc;
+    if (h->f64) {
+        if ((rc = ss_timer_begin(h))) return rc;
+        const double *img = h->fusedbase64;
+        if (L == 0) {
+            dim3 g((h->cfg.width + 127) / 128, h->cfg.height);
+            ss64_finalize_kernel<<<g, 128, 0, h->s_comp>>>(img, h->cfg.height, h->cfg.width, h->cfg.bytes_per_sample,
+                                                            h->out_dev, (int)h->out_pitch);
+            h->launches++;
+        }
+        for (int l = L - 1; l >= 0; --l) {
+            double *dst = l == 0 ? nullptr : ((img == h->tmp64_a) ? h->tmp64_b : h->tmp64_a);
+            dim3 g((h->lw[l] + 127) / 128, h->lh[l]);
+            ss64_collapse_kernel<<<g, 128, 0, h->s_comp>>>(img, h->lh[l + 1], h->lw[l + 1], h->fused64[l], h->lh[l], h->lw[l],
+                                                            h->k64, dst, h->out_dev, (int)h->out_pitch,
+                                                            l == 0 ? h->cfg.bytes_per_sample : 0);
+            h->launches++;
+            img = dst;
+        }
+        SS_CUDA(cudaGetLastError());
+        if ((rc = ss_timer_end(h))) return rc;
+        if (out_bgr) {
+            const size_t row = (size_t)h->cfg.width * 3 * h->cfg.bytes_per_sample;
+            if (out_row_pitch_bytes < row) return ss_fail(SS_ERR_SHAPE, "output pitch too small");
+            SS_CUDA(cudaMemcpy2DAsync(out_bgr, out_row_pitch_bytes, h->out_dev, h->out_pitch, row, h->cfg.height,
+                                      cudaMemcpyDeviceToHost, h->s_comp));
+        }
+        SS_CUDA(cudaStreamSynchronize(h->s_comp));
+        return 0;
+    }
     if ((rc = ss_timer_begin(h))) return rc;
     ss_base_fuse_kernel<<<(unsigned)((3 * nb + 255) / 256), 256, 0, h->s_comp>>>(h->pix_e, h->pix_d, 3 * nb, h->fused_base);
     h->launches++;
@@ -1054,7 +1217,8 @@ SS_EXPORT int ss_finish_collapse(ss_handle *h, void *out_bgr, size_t out_row_pit
 
 SS_EXPORT int ss_finish_end(ss_handle *h, const float *log_prob, void *out_bgr, size_t out_row_pitch_bytes)
 {
-    int rc = ss_finish_select_base(h, log_prob);
+    if (h && h->f64 && log_prob) return ss_fail(SS_ERR_STATE, "float-64 handle: use ss_finish_select_base_f64");
+    int rc = (h && h->f64) ? ss_finish_select_base_f64(h, nullptr, 0) : ss_finish_select_base(h, log_prob);
     if (rc) return rc;
     return ss_finish_collapse(h, out_bgr, out_row_pitch_bytes);
 }
@@ -1092,6 +1256,7 @@ SS_EXPORT int ss_get_best_energy(ss_handle *h, int level, float *out)
 SS_EXPORT int ss_get_fused_level(ss_handle *h, int level, float *out)
 {
     if (!h || !out || level < 0 || level > h->L) return ss_fail(SS_ERR_STATE, "bad argument");
+    if (h->f64) return ss_fail(SS_ERR_STATE, "not available on a float-64 handle");
     SS_CUDA(cudaSetDevice(h->cfg.device));
     const size_t n = (size_t)h->lh[level] * h->lw[level];
     const float *src = level < h->L ? h->lv[level].fused : h->fused_base;
@@ -1108,6 +1273,7 @@ SS_EXPORT int ss_get_fused_level(ss_handle *h, int level, float *out)
 SS_EXPORT int ss_get_gauss_level(ss_handle *h, int level, int frame, float *out_planes)
 {
     if (!h || !out_planes || level < 1 || level > h->L) return ss_fail(SS_ERR_STATE, "bad argument");
+    if (h->f64) return ss_fail(SS_ERR_STATE, "not available on a float-64 handle");
     SS_CUDA(cudaSetDevice(h->cfg.device));
     const size_t rows = 3 * (size_t)h->lh[level], wbytes = (size_t)h->lw[level] * sizeof(float);
     const size_t pitch = level < h->L ? (size_t)h->lv[level - 1].gpitch : (size_t)h->lw[level];
@@ -1182,6 +1348,7 @@ SS_EXPORT int ss_launch_count(ss_handle *h, int64_t *launches)
 SS_EXPORT int ss_exchange_keys(ss_handle *h, uint64_t **d_keys, size_t *count)
 {
     if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin/select_base first");
+    if (h->f64) return ss_fail(SS_ERR_STATE, "the multi-GPU exchange is implemented for float-32 only");
     SS_CUDA(cudaSetDevice(h->cfg.device));
     int rc;
     if (!h->keys && (rc = ss_dalloc(&h->keys, h->n_keys))) return rc;

@@ -46,7 +46,7 @@ def read_img(file_path):
     return img
 
 
-def log_prob_table(counts):
+def log_prob_table(counts, dtype=np.float32):
     """np.log(probabilities) of PyramidBase.entropy (reference pyramid.py:67-69,77) for every frame.
 
     ``counts``: (n_frames, num_values) int64 histogram of each frame's truncated gray base level.
@@ -56,12 +56,12 @@ def log_prob_table(counts):
     """
     counts = np.asarray(counts, dtype=np.int64)
     total = counts.sum(axis=1, keepdims=True)
-    prob = (counts.astype(np.float32) / total).astype(np.float32)
+    prob = (counts.astype(dtype) / total).astype(dtype)
     with np.errstate(divide="ignore"):
         return np.ascontiguousarray(np.log(prob))
 
 
-def log_prob_per_pixel(gray):
+def log_prob_per_pixel(gray, dtype=np.float32):
     """16-bit variant of log_prob_table: for every base pixel the value np.log(probabilities)[its gray value].
 
     ``gray``: (n_frames, hL, wL) int32 truncated gray base levels.  Per frame this is literally the
@@ -69,22 +69,26 @@ def log_prob_per_pixel(gray):
     counts.sum() (evaluated in float64, stored as float32), np.log.
     """
     gray = np.asarray(gray)
-    out = np.empty(gray.shape, dtype=np.float32)
+    out = np.empty(gray.shape, dtype=dtype)
     for f in range(gray.shape[0]):
         _, inverse, counts = np.unique(gray[f].ravel(), return_inverse=True, return_counts=True)
-        prob = np.zeros(counts.shape, dtype=np.float32)
-        prob[...] = counts.astype(np.float32) / counts.sum()
+        prob = np.zeros(counts.shape, dtype=dtype)
+        prob[...] = counts.astype(dtype) / counts.sum()
         out[f] = np.log(prob)[inverse].reshape(gray.shape[1:])
     return out
 
 
-def select_base(lib, h, n_frames, num_values):
+def select_base(lib, h, n_frames, num_values, float_type=np.float32):
     """ss_finish_begin + host-side log table (numpy) + base-level arg-max on the device."""
+    f64 = float_type == np.float64
     if num_values <= 256:
         counts = np.empty((n_frames, num_values), dtype=np.int64)
         _check(lib.ss_finish_begin(h, counts.ctypes.data_as(ctypes.c_void_p)))
-        table = log_prob_table(counts)
-        _check(lib.ss_finish_select_base(h, table.ctypes.data_as(ctypes.c_void_p)))
+        table = log_prob_table(counts, float_type)
+        if f64:
+            _check(lib.ss_finish_select_base_f64(h, table.ctypes.data_as(ctypes.c_void_p), 0))
+        else:
+            _check(lib.ss_finish_select_base(h, table.ctypes.data_as(ctypes.c_void_p)))
     else:
         _check(lib.ss_finish_begin(h, None))
         L = lib.ss_num_levels(h)
@@ -92,8 +96,11 @@ def select_base(lib, h, n_frames, num_values):
         _check(lib.ss_level_size(h, L, ctypes.byref(hh), ctypes.byref(ww)))
         gray = np.empty((n_frames, hh.value, ww.value), dtype=np.int32)
         _check(lib.ss_get_base_gray(h, gray.ctypes.data_as(ctypes.c_void_p)))
-        table = log_prob_per_pixel(gray)
-        _check(lib.ss_finish_select_base_px(h, table.ctypes.data_as(ctypes.c_void_p)))
+        table = log_prob_per_pixel(gray, float_type)
+        if f64:
+            _check(lib.ss_finish_select_base_f64(h, table.ctypes.data_as(ctypes.c_void_p), 1))
+        else:
+            _check(lib.ss_finish_select_base_px(h, table.ctypes.data_as(ctypes.c_void_p)))
 
 
 def _check(rc):
@@ -117,9 +124,7 @@ class PyramidBase:
         if float_type == FLOAT_32:
             self.float_type = np.float32
         elif float_type == FLOAT_64:
-            raise InvalidOptionError(
-                "float_type", float_type,
-                details=" the B200 path implements FLOAT_32 only")
+            self.float_type = np.float64
         else:
             raise InvalidOptionError(
                 "float_type", float_type,
@@ -195,7 +200,7 @@ class PyramidStack(PyramidBase):
         cfg.width, cfg.height, cfg.bytes_per_sample = w, h, bps
         cfg.min_size, cfg.kernel_size = int(self.min_size), int(self.kernel_size)
         cfg.gen_kernel = self.gen_kernel_param
-        cfg.float_bits = 32
+        cfg.float_bits = 64 if self.float_type == np.float64 else 32
         cfg.device = self.device
         cfg.max_frames = max(int(n_frames), 1)
         cfg.batch_frames = self.batch_frames
@@ -271,7 +276,7 @@ class PyramidStack(PyramidBase):
 
     def _finish(self, n, shape):
         lib, h = self._lib, self._h
-        select_base(lib, h, n, self.num_pixel_values)
+        select_base(lib, h, n, self.num_pixel_values, self.float_type)
         out = np.empty((shape[0], shape[1], 3), dtype=self.dtype)
         _check(lib.ss_finish_collapse(h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
         ms = ctypes.c_float()
@@ -299,7 +304,7 @@ class PyramidStack(PyramidBase):
         return dict(best=maps[:L], best_e=maps[L], best_d=maps[L + 1], levels=L)
 
     def get_fused_pyramid(self):
-        """Fused Laplacian levels + fused base of the last stack, H_l x W_l x 3 float32 (tests)."""
+        """Fused Laplacian levels + fused base of the last stack, H_l x W_l x 3 float32 (tests; float-32 only)."""
         lib, h = self._lib, self._h
         L = lib.ss_num_levels(h)
         out = []

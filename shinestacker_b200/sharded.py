@@ -90,7 +90,7 @@ class ShardedPyramidStack:
         import torch
         a = self.algo
         lib, h = a._lib, a._h
-        select_base(lib, h, n_local, a.num_pixel_values)
+        select_base(lib, h, n_local, a.num_pixel_values, a.float_type)
         if self.world > 1:
             ptr, cnt = ctypes.c_void_p(), ctypes.c_size_t()
             _check(lib.ss_exchange_keys(h, ctypes.byref(ptr), ctypes.byref(cnt)))

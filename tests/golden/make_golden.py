@@ -36,6 +36,9 @@ CASES = [
     ("noise_u8_6x257x385", "noise", 6, 257, 385, "uint8", 9, {}),
     ("syn_u8_2x40x50_nolevels", "stack", 2, 40, 50, "uint8", 10, {}),
     ("noise_u8_64x96x136", "noise", 64, 96, 136, "uint8", 11, {}),
+    ("f64_noise_u8_4x150x210", "noise", 4, 150, 210, "uint8", 12, {"float_type": "float-64"}),
+    ("f64_syn_u16_3x133x260", "stack", 3, 133, 260, "uint16", 13, {"float_type": "float-64"}),
+    ("f64_syn_u8_2x40x50_nolevels", "stack", 2, 40, 50, "uint8", 14, {"float_type": "float-64", "kernel_size": 3}),
 ]
 
 

@@ -40,8 +40,7 @@ def test_float_type_contract():
     # reference base_stack_algo.py:13-22
     with pytest.raises(InvalidOptionError):
         PyramidStack(float_type="float-16")
-    with pytest.raises(InvalidOptionError):
-        PyramidStack(float_type="float-64")   # documented gap: FLOAT_32 only on the B200 path
+    assert PyramidStack(float_type="float-64").float_type is np.float64
     a = PyramidStack()
     assert a.name() == "pyramid" and a.steps_per_frame() == 2
     assert a.float_type is np.float32 and a.do_step_callback is False
@@ -52,7 +51,7 @@ def test_float_type_contract():
 def test_invalid_options_reported_by_native_layer():
     lib = _native.load()
     cfg = _native.SsConfig(width=64, height=64, bytes_per_sample=1, min_size=32, kernel_size=5,
-                           gen_kernel=0.4, float_bits=64, device=0, max_frames=2)
+                           gen_kernel=0.4, float_bits=16, device=0, max_frames=2)
     h = ctypes.c_void_p()
     assert lib.ss_create(ctypes.byref(cfg), ctypes.byref(h)) == _native.SS_ERR_INVALID_OPTION
     assert b"float" in lib.ss_last_error()

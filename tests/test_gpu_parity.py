@@ -238,3 +238,17 @@ def test_many_frames_u8_groups(oracle):
     out, maps, _ = run_gpu(frames, batch_frames=70)
     golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
                                                best_d=info["best_d"], levels=info["levels"]), "groups")
+
+
+@pytest.mark.parametrize("gen,n,h,w,dtype,seed", [
+    ("noise", 5, 300, 407, np.uint8, 101),          # tail columns in the float32 energy filter
+    ("stack", 4, 515, 750, np.uint16, 102),
+])
+def test_float64_matches_oracle(oracle, gen, n, h, w, dtype, seed):
+    """float_type='float-64' (reference base_stack_algo.py:15-16): float64 pyramids, float32 energy."""
+    f = synthetic.make_stack if gen == "stack" else synthetic.make_noise_stack
+    frames = f(n, h, w, dtype, seed)
+    ref, info = oracle.focus_stack(frames, float_type="float-64")
+    out, maps, _ = run_gpu(frames, float_type="float-64")
+    golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
+                                               best_d=info["best_d"], levels=info["levels"]), "float-64")

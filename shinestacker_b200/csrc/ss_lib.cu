@@ -72,22 +72,23 @@ __global__ void ss_merge_groups_kernel(size_t n, int groups, const float *g_e, c
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float e, c0, c1, c2;
-    int idx, g = 0;
-    if (have_state) {
-        e = best_e[i]; idx = best_idx[i]; c0 = fused[i]; c1 = fused[n + i]; c2 = fused[2 * n + i];
-    } else {
-        e = g_e[i]; idx = g_idx[i]; c0 = g_fused[i]; c1 = g_fused[n + i]; c2 = g_fused[2 * n + i];
-        g = 1;
-    }
-    for (; g < groups; ++g) {
+    // pass 1: the winning group (energies only; the loads of a batch of 8 groups are independent)
+    float e;
+    int win, g0;
+    if (have_state) { e = best_e[i]; win = -1; g0 = 0; }
+    else { e = g_e[i]; win = 0; g0 = 1; }
+#pragma unroll 8
+    for (int g = g0; g < groups; ++g) {
         const float eg = g_e[(size_t)g * n + i];
-        if (eg > e) {
-            const float *gf = g_fused + 3 * (size_t)g * n;
-            e = eg; idx = g_idx[(size_t)g * n + i]; c0 = gf[i]; c1 = gf[n + i]; c2 = gf[2 * n + i];
-        }
+        if (eg > e) { e = eg; win = g; }
     }
-    best_e[i] = e; best_idx[i] = idx; fused[i] = c0; fused[n + i] = c1; fused[2 * n + i] = c2;
+    // pass 2: index and coefficients of the winner only
+    if (win >= 0) {
+        const float *gf = g_fused + 3 * (size_t)win * n;
+        best_e[i] = e;
+        best_idx[i] = g_idx[(size_t)win * n + i];
+        fused[i] = gf[i]; fused[n + i] = gf[n + i]; fused[2 * n + i] = gf[2 * n + i];
+    }
 }
 
 // img.astype(float32) (reference pyramid.py:126) into planes; only needed when the pyramid has no

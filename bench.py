@@ -167,13 +167,15 @@ def main():
     import torch
     import torch.distributed as dist
     from shinestacker_b200 import synthetic, _native
-    from shinestacker_b200.sharded import ShardedPyramidStack, shard_range
+    from shinestacker_b200.sharded import ShardedPyramidStack, shard_range, bind_to_gpu_numa_node
     from shinestacker_b200.pyramid import _check
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_node = None
     if world > 1:
+        numa_node = bind_to_gpu_numa_node(local)   # before any pinned allocation
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     lib = _native.load()
@@ -309,7 +311,8 @@ def main():
             "config": {"workload": workload_name(a), "levels": 6, "frames_per_gpu": n_local,
                        "l2": f"inputs ({N * frame_bytes / 1e9:.2f} GB) larger than the 126 MB L2; every "
                              "step re-reads all frames from HBM",
-                       "parallelism": f"frames sharded over {world} GPU(s)"},
+                       "parallelism": f"frames sharded over {world} GPU(s)",
+                       "numa_node_rank0": numa_node},
             "clocks": clocks,
             "e2e": {"value": mp / (dt_e2e / a.steps), "unit": UNIT, "ms_per_step": dt_e2e / a.steps * 1e3,
                     # frames up + log table up; fused image down + histogram (u8) / gray base levels (u16) down

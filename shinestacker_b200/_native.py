@@ -9,7 +9,8 @@ import os
 from .exceptions import NativeLibraryError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshinestack_b200.so")
+# SHINESTACK_B200_LIB selects an alternative build of the same ABI (kernel A/B experiments)
+LIB_PATH = os.environ.get("SHINESTACK_B200_LIB") or os.path.join(_HERE, "libshinestack_b200.so")
 
 
 class SsConfig(ctypes.Structure):

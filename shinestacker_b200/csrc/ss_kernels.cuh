@@ -626,8 +626,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             SS_THREADS(tid)
             {
                 const int tx = tid & 15, ty = tid >> 4;
-                // own 4x4 block.  The channel loop is deliberately NOT unrolled (the hot loop must stay small
-                // for the instruction cache); gray = fma(R,.299, fma(B,.114, G*.587)) is accumulated in the
+                // own 4x4 block; gray = fma(R,.299, fma(B,.114, G*.587)) is accumulated in the
                 // order G, B, R starting from +0 (fma(G,.587,+0) == G*.587 up to the sign of zero, which the
                 // square removes).
                 float gray[16];
@@ -636,7 +635,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                 // channel order G, B, R = planes 1, 0, 2: the plane pointers advance by -1 and then +2 planes
                 const float *p1c = P1 + SS_P1P + (2 * ty + 1) * SS_P1S + 2 * tx + 1 + SS_P1O;
                 float *p0c = P0 + SS_P0P + (4 * ty + SS_P0Y) * SS_P0S + 4 * tx + SS_P0X;
-#pragma unroll 1
+#pragma unroll
                 for (int it = 0; it < 3; ++it) {
                     const float wgt = it == 0 ? 0.587f : (it == 1 ? 0.114f : 0.299f);
                     float win[4][4], acc[16];
@@ -679,7 +678,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     float gr[4] = {0.f, 0.f, 0.f, 0.f};
                     const float *r1c = P1 + SS_P1P + (qq / 2) * SS_P1S + pp / 2 + SS_P1O;
                     const float *r0c = P0 + SS_P0P + (qq + SS_P0Y - 2) * SS_P0S + pp + SS_P0X - 2;
-#pragma unroll 1
+#pragma unroll
                     for (int it = 0; it < 3; ++it) {
                         const float wgt = it == 0 ? 0.587f : (it == 1 ? 0.114f : 0.299f);
                         float win[3][3], acc[4];

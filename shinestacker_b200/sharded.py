@@ -28,6 +28,32 @@ def shard_range(n_frames, rank, world):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers
+    (allocated afterwards) and the upload traffic stay on that socket.  Best effort: returns the node or None."""
+    import os
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
+                             capture_output=True, text=True, check=True).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # pylint: disable=broad-except
+        pass
+    return None
+
+
 def pack_keys(values, indices):
     """numpy restatement of ss_pack_keys_kernel (csrc/ss_lib.cu) for the CPU (gloo) tests."""
     v = np.asarray(values, dtype=np.float32).copy()

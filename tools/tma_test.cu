@@ -1,4 +1,6 @@
-// standalone check of the TMA path used by ss_level_kernel<uint8_t>
+// standalone check of the TMA path used by ss_level_kernel<uint8_t>.  Finding (B200): the byte column of a box
+// origin must be a multiple of 16 -- c0 = 168 raises "illegal instruction", c0 = 0 / 176 work; hence the frame
+// store keeps every row 8 bytes into its pitch (8 + 3*(x0-8) = 16*k for x0 = 64*j).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -39,7 +41,7 @@ int main()
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("encode rc=%d\n", (int)r);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
-    for (int c0 : {0, 168, 169}) {
+    for (int c0 : {0, 176, 368}) {
         k<<<1, 256, 40000>>>(tm, c0, 58, o, 0);
         cudaError_t e = cudaDeviceSynchronize();
         printf("c0=%d launch: %s\n", c0, cudaGetErrorString(e));

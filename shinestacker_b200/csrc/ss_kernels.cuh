@@ -163,8 +163,8 @@ struct SsLevelParams {
     // ss_merge_groups_kernel folds the slices into the running state in frame order.
     int groups;
     long long group_stride;
-    int tma_row0;        // uint8 level 0: row of the batch's first frame in the frame-store tensor map (rows of
-                         // that store begin 8 bytes into their pitch, so byte column 8 + 3*(x0-8) is 16-byte aligned)
+    int tma_row0;        // uint8 level 0: row of the batch's first frame in the frame-store tensor map (the store
+                         // begins 8 bytes into its allocation, so byte column 8 + 3*(x0-8) is 16-byte aligned)
     float k25[25];
 };
 
@@ -465,7 +465,9 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
     // every patch position inside the images?  (else REFLECT101 loads + fix-up passes)
     const bool interior = (x0 >= SS_P0X) && (y0 >= SS_P0Y) && (x0 + SS_TX + 8 <= p.w) &&
                           (y0 + SS_TY + 6 <= p.h) && (x0 / 2 + SS_TX / 2 + 2 <= p.w2) &&
-                          (y0 / 2 + SS_TY / 2 + 2 <= p.h2);
+                          (y0 / 2 + SS_TY / 2 + 2 <= p.h2) &&
+                          // uint8: the TMA box [8 + 3*(x0-8), +240) must lie inside one row of the tensor map
+                          (sizeof(InT) != 1 || 3 * (x0 + SS_TX + 8) + 8 <= p.in_pitch);
     // no IN-IMAGE output of this tile in any stage falls on a tail (mul+add) column?  (An image whose widths
     // are multiples of 8 has no tail columns at all.)  Then the register-blocked stages are used; at image
     // borders they also evaluate out-of-image positions (finite junk computed from clamped data) which the

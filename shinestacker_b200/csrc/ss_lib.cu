@@ -566,10 +566,12 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     h->n_slots = cfg->resident_frames > 0 ? cfg->resident_frames : 2 * h->batch;
     if (h->n_slots < h->batch) h->n_slots = h->batch;
     h->n_slots = (h->n_slots + h->batch - 1) / h->batch * h->batch;
-    // uint8 rows start 8 bytes into their pitch: the byte column of pixel x0-8 (x0 a multiple of 64) is then
-    // a multiple of 16, which TMA requires of a box origin
+    // uint8: the whole store starts 8 bytes into its allocation and every row pitch is a multiple of 16, so every
+    // row starts at 8 mod 16: the byte column of pixel x0-8 (x0 a multiple of 64) in the tensor map is then a
+    // multiple of 16, which TMA requires of a box origin.  Rows stay contiguous when W*3 is already a multiple of
+    // 16 (one 1-D DMA per frame).
     h->frame_shift = cfg->bytes_per_sample == 1 ? 8 : 0;
-    h->frame_pitch = ((size_t)cfg->width * 3 * cfg->bytes_per_sample + h->frame_shift + 15) / 16 * 16;
+    h->frame_pitch = ((size_t)cfg->width * 3 * cfg->bytes_per_sample + 15) / 16 * 16;
     h->frame_bytes = h->frame_pitch * cfg->height;
     SS_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     SS_CUDA(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
@@ -581,7 +583,7 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
         SS_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
     }
     int rc;
-    if ((rc = ss_dalloc(&h->frames, h->frame_bytes * h->n_slots))) return rc;
+    if ((rc = ss_dalloc(&h->frames, h->frame_bytes * h->n_slots + 16))) return rc;
     memset(&h->tmap_frames, 0, sizeof(h->tmap_frames));
     if (cfg->bytes_per_sample == 1) {
         typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -948,8 +950,11 @@ static int ss_push_impl(ss_handle *h, const void *src, size_t pitch, cudaMemcpyK
         // the ring wraps: the batch that used these slots must have been consumed
         SS_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_done[slot / h->batch], 0));
     }
-    SS_CUDA(cudaMemcpy2DAsync(h->frames + (size_t)slot * h->frame_bytes + h->frame_shift, h->frame_pitch, src, pitch, row,
-                              h->cfg.height, kind, h->s_copy));
+    char *dst = h->frames + (size_t)slot * h->frame_bytes + h->frame_shift;
+    if (pitch == row && h->frame_pitch == row)   // contiguous on both sides: one 1-D transfer
+        SS_CUDA(cudaMemcpyAsync(dst, src, row * h->cfg.height, kind, h->s_copy));
+    else
+        SS_CUDA(cudaMemcpy2DAsync(dst, h->frame_pitch, src, pitch, row, h->cfg.height, kind, h->s_copy));
     h->n_pushed++;
     if (h->n_pushed % h->batch == 0) return ss_launch_pending(h, false);
     return 0;

@@ -137,6 +137,16 @@ int ss_exchange_keys(ss_handle *h, uint64_t **d_keys, size_t *count);
 int ss_exchange_mask_losers(ss_handle *h, float **d_coeffs, size_t *count);
 /* On the root after both reductions: unpack winners' indices from the reduced keys. */
 int ss_exchange_adopt(ss_handle *h);
+/* Alternative to ss_exchange_mask_losers + sum-reduce + ss_exchange_adopt: the root gathers the winners'
+ * coefficients itself over NVLink peer memory.  Every rank publishes the 64-byte CUDA IPC handle of its
+ * coefficient state; after the key max-reduction the root calls ss_exchange_pull with all handles and the
+ * world+1 shard boundaries (global frame indices); the other ranks only wait. */
+int ss_exchange_ipc_handle(ss_handle *h, void *handle64);
+int ss_exchange_pull(ss_handle *h, const void *handles, const int32_t *shard_start, int world, int rank);
+/* The same gather with the ranks' coefficient states given as device pointers addressable from this device
+ * (several handles in one process; tests), and the accessor that yields such a pointer. */
+int ss_exchange_pull_ptrs(ss_handle *h, const void *const *coef_ptrs, const int32_t *shard_start, int world, int rank);
+int ss_exchange_coef_ptr(ss_handle *h, float **d_coeffs, size_t *count);
 
 /* Re-run the kernel chain over the frames still resident in HBM (requires resident_frames >= frames
  * pushed).  Used by bench.py for the "inputs already in HBM" throughput. */

@@ -74,6 +74,10 @@ SIGNATURES = {
     "ss_exchange_keys": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ss_exchange_mask_losers": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ss_exchange_adopt": (_i, [_vp]),
+    "ss_exchange_ipc_handle": (_i, [_vp, _vp]),
+    "ss_exchange_pull": (_i, [_vp, _vp, _vp, _i, _i]),
+    "ss_exchange_pull_ptrs": (_i, [_vp, _vp, _vp, _i, _i]),
+    "ss_exchange_coef_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ss_rerun_resident": (_i, [_vp]),
     "ss_finish_select_base": (_i, [_vp, _vp]),
     "ss_get_base_gray": (_i, [_vp, _vp]),

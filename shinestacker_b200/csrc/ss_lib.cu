@@ -374,6 +374,36 @@ __global__ void ss_adopt_keys_kernel(const unsigned long long *keys, size_t n, c
     }
 }
 
+// Root-side gather over NVLink peer memory: after the key max-reduction the root knows every pixel's winning
+// global frame index, hence the owning rank (contiguous frame shards); it reads the three winning coefficients
+// straight from that rank's running state (peer pointer obtained through CUDA IPC) -- no masking pass on the
+// other ranks, no sum-reduction, 12 bytes per pixel cross NVLink exactly once.
+struct SsPeers {
+    int world, rank;
+    int shard_start[17];          // frame index where rank r's shard begins; [world] = total frames
+    const float *coef[16];        // state_coef of every rank (own pointer at [rank])
+};
+
+__global__ void ss_pull_winners_kernel(const unsigned long long *keys, size_t n, const __grid_constant__ SsSegments seg,
+                                       const __grid_constant__ SsPeers peers, float *val, int32_t *idx, float *coeff)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    const int win = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull));
+    val[i] = __uint_as_float((unsigned int)(k >> 32));
+    idx[i] = win;
+    int r = 0;
+    while (r + 1 < peers.world && win >= peers.shard_start[r + 1]) ++r;
+    if (r == peers.rank) return;   // the root's own coefficients are already in place
+    int s = 0;
+    while (s + 1 < seg.count && i >= seg.px_off[s + 1]) ++s;
+    const size_t o = seg.coef_off[s] + (i - seg.px_off[s]);
+    const float *src = peers.coef[r] + o;
+    float *dst = coeff + o;
+    dst[0] = src[0]; dst[seg.n_px[s]] = src[seg.n_px[s]]; dst[2 * seg.n_px[s]] = src[2 * seg.n_px[s]];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------------
@@ -420,6 +450,8 @@ struct ss_handle {
     float *tmp_a = nullptr, *tmp_b = nullptr;  // collapse ping-pong, 3 x H x W / 4 each... see alloc
     void *out_dev = nullptr;         // interleaved output image
     size_t out_pitch = 0;
+    void *peer_mapped[16] = {};          // state_coef of the other ranks, opened through CUDA IPC (root only)
+    char peer_handle[16][64] = {};       // ... and the IPC handles they were opened from
     unsigned long long *keys = nullptr;  // exchange buffer
     size_t n_keys = 0, n_coeffs = 0;
     // streams / events
@@ -533,6 +565,8 @@ SS_EXPORT void ss_destroy(ss_handle *h)
     cudaFree(h->log_p); cudaFree(h->state_val); cudaFree(h->state_idx); cudaFree(h->state_coef);
     cudaFree(h->ent); cudaFree(h->dev);
     cudaFree(h->fused_base);
+    for (void *pm : h->peer_mapped)
+        if (pm) cudaIpcCloseMemHandle(pm);
     cudaFree(h->tmp_a); cudaFree(h->tmp_b); cudaFree(h->out_dev); cudaFree(h->keys);
     for (auto e : h->ev_copied) cudaEventDestroy(e);
     for (auto e : h->ev_done) cudaEventDestroy(e);
@@ -1385,6 +1419,84 @@ SS_EXPORT int ss_exchange_adopt(ss_handle *h)
 {
     // the sum-reduction wrote straight into the root's running state: nothing to copy
     if (!h || !h->keys) return ss_fail(SS_ERR_STATE, "ss_exchange_mask_losers first");
+    return 0;
+}
+
+// CUDA IPC handle (64 bytes) of this rank's coefficient state, for the root's peer gather.
+SS_EXPORT int ss_exchange_ipc_handle(ss_handle *h, void *handle64)
+{
+    if (!h || !handle64) return ss_fail(SS_ERR_STATE, "null argument");
+    if (h->f64) return ss_fail(SS_ERR_STATE, "the multi-GPU exchange is implemented for float-32 only");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    cudaIpcMemHandle_t mh;
+    SS_CUDA(cudaIpcGetMemHandle(&mh, h->state_coef));
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &mh, 64);
+    return 0;
+}
+
+// Root only, after the key max-reduction: adopt the winners and pull their coefficients from the owning ranks'
+// memory.  handles = world x 64 bytes (ss_exchange_ipc_handle of every rank, own entry ignored); shard_start =
+// world + 1 frame indices.  The other ranks must keep their state untouched until the root returns.
+static int ss_pull_launch(ss_handle *h, const SsPeers &peers)
+{
+    ss_pull_winners_kernel<<<(unsigned)((h->n_keys + 255) / 256), 256, 0, h->s_comp>>>(h->keys, h->n_keys, h->seg, peers,
+                                                                                       h->state_val, h->state_idx, h->state_coef);
+    h->launches++;
+    SS_CUDA(cudaGetLastError());
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    return 0;
+}
+
+SS_EXPORT int ss_exchange_pull(ss_handle *h, const void *handles, const int32_t *shard_start, int world, int rank)
+{
+    if (!h || !h->keys || !handles || !shard_start) return ss_fail(SS_ERR_STATE, "ss_exchange_keys first");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return ss_fail(SS_ERR_COMM, "bad world/rank");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SsPeers peers;
+    memset(&peers, 0, sizeof(peers));
+    peers.world = world; peers.rank = rank;
+    for (int r = 0; r <= world; ++r) peers.shard_start[r] = shard_start[r];
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { peers.coef[r] = h->state_coef; continue; }
+        if (h->peer_mapped[r] && memcmp(h->peer_handle[r], (const char *)handles + 64 * r, 64) != 0) {
+            cudaIpcCloseMemHandle(h->peer_mapped[r]);   // the peer re-created its state
+            h->peer_mapped[r] = nullptr;
+        }
+        if (!h->peer_mapped[r]) {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, (const char *)handles + 64 * r, 64);
+            SS_CUDA(cudaIpcOpenMemHandle(&h->peer_mapped[r], mh, cudaIpcMemLazyEnablePeerAccess));
+            memcpy(h->peer_handle[r], (const char *)handles + 64 * r, 64);
+        }
+        peers.coef[r] = (const float *)h->peer_mapped[r];
+    }
+    return ss_pull_launch(h, peers);
+}
+
+// Same gather with the ranks' coefficient states given as device pointers that are directly addressable from
+// this device (several handles inside one process, or memory mapped by the caller) -- used by the tests.
+SS_EXPORT int ss_exchange_pull_ptrs(ss_handle *h, const void *const *coef_ptrs, const int32_t *shard_start, int world,
+                                    int rank)
+{
+    if (!h || !h->keys || !coef_ptrs || !shard_start) return ss_fail(SS_ERR_STATE, "ss_exchange_keys first");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return ss_fail(SS_ERR_COMM, "bad world/rank");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SsPeers peers;
+    memset(&peers, 0, sizeof(peers));
+    peers.world = world; peers.rank = rank;
+    for (int r = 0; r <= world; ++r) peers.shard_start[r] = shard_start[r];
+    for (int r = 0; r < world; ++r) peers.coef[r] = r == rank ? h->state_coef : (const float *)coef_ptrs[r];
+    return ss_pull_launch(h, peers);
+}
+
+// Device address and length of this handle's coefficient state (exchange layout).
+SS_EXPORT int ss_exchange_coef_ptr(ss_handle *h, float **d_coeffs, size_t *count)
+{
+    if (!h || !d_coeffs) return ss_fail(SS_ERR_STATE, "null argument");
+    if (h->f64) return ss_fail(SS_ERR_STATE, "the multi-GPU exchange is implemented for float-32 only");
+    *d_coeffs = h->state_coef;
+    if (count) *count = h->n_coeffs;
     return 0;
 }
 

@@ -91,8 +91,11 @@ class ShardedPyramidStack:
     """One per rank.  ``focus_stack_arrays(local_frames, n_total)`` returns the fused image on the
     root rank and None elsewhere."""
 
-    def __init__(self, rank, world, device=0, group=None, root=0, **kwargs):
+    def __init__(self, rank, world, device=0, group=None, root=0, exchange="p2p", **kwargs):
+        """``exchange``: "p2p" = key max all-reduce (NCCL) + root-side gather of the winners' coefficients
+        over NVLink peer memory (CUDA IPC); "nccl" = key max all-reduce + masked float32 sum-reduce."""
         self.rank, self.world, self.device, self.group, self.root = rank, world, device, group, root
+        self.exchange_mode = exchange
         self.kwargs = kwargs
         self.algo = None
         self.n_total = None
@@ -129,10 +132,25 @@ class ShardedPyramidStack:
                 _check(lib.ss_exchange_mask_losers(h, ctypes.byref(p2), ctypes.byref(c2)))
                 return torch.as_tensor(_DevArray(p2.value, c2.value, "<f4"), device=dev)
 
-            exchange(keys, mask, self.root, self.group)
-            torch.cuda.synchronize(self.device)
-            if self.rank == self.root:
-                _check(lib.ss_exchange_adopt(h))
+            if self.exchange_mode == "p2p":
+                import torch.distributed as dist
+                dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=self.group)
+                mine = torch.empty(64, dtype=torch.uint8)
+                _check(lib.ss_exchange_ipc_handle(h, ctypes.c_void_p(mine.data_ptr())))
+                allh = torch.empty(64 * self.world, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(allh, mine.to(dev), group=self.group)
+                allh = allh.cpu()                       # also waits for the key reduction
+                if self.rank == self.root:
+                    starts = np.array([shard_range(self.n_total, r, self.world)[0] for r in range(self.world)]
+                                      + [self.n_total], dtype=np.int32)
+                    _check(lib.ss_exchange_pull(h, ctypes.c_void_p(allh.data_ptr()),
+                                                starts.ctypes.data_as(ctypes.c_void_p), self.world, self.rank))
+                dist.barrier(group=self.group)          # peers keep their state until the root has gathered it
+            else:
+                exchange(keys, mask, self.root, self.group)
+                torch.cuda.synchronize(self.device)
+                if self.rank == self.root:
+                    _check(lib.ss_exchange_adopt(h))
         if self.rank != self.root:
             return None
         if out is None:

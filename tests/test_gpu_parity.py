@@ -252,3 +252,44 @@ def test_float64_matches_oracle(oracle, gen, n, h, w, dtype, seed):
     out, maps, _ = run_gpu(frames, float_type="float-64")
     golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
                                                best_d=info["best_d"], levels=info["levels"]), "float-64")
+
+
+def test_frame_sharding_peer_gather_on_one_gpu(oracle):
+    """The NVLink-peer variant of the exchange (ss_exchange_pull): three handles play three ranks on one
+    device; after the key max-reduction the root gathers the winners' coefficients from the other handles'
+    state with ONE kernel (no masking, no sum).  Must equal the single-handle result bit for bit."""
+    import torch
+    from shinestacker_b200.sharded import shard_range, _DevArray
+    from shinestacker_b200.pyramid import select_base, _check
+    n, h, w, world = 8, 260, 390, 3
+    frames = synthetic.make_noise_stack(n, h, w, np.uint8, 96)
+    frames[5][:70, :90] = frames[1][:70, :90]          # exact ties across shard boundaries
+    ref, info = oracle.focus_stack(frames)
+    lib = _native.load()
+    shards, keys, ptrs = [], [], (ctypes.c_void_p * world)()
+    starts = np.array([shard_range(n, r, world)[0] for r in range(world)] + [n], dtype=np.int32)
+    for r in range(world):
+        f0, f1 = shard_range(n, r, world)
+        a = PyramidStack(device=0, frame_index_base=f0, keep_depth_maps=False, batch_frames=2)
+        a._set_metadata(frames[0])
+        a._ensure_handle(frames[0].shape, frames[0].dtype, f1 - f0)
+        ring = a._staging(frames[0].nbytes, 4)
+        for i, f in enumerate(frames[f0:f1]):
+            a._push(i, f, ring)
+        select_base(lib, a._h, f1 - f0, 256)
+        ptr, cnt = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(lib.ss_exchange_keys(a._h, ctypes.byref(ptr), ctypes.byref(cnt)))
+        keys.append(torch.as_tensor(_DevArray(ptr.value, cnt.value, "<i8"), device="cuda:0"))
+        cp, cn = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(lib.ss_exchange_coef_ptr(a._h, ctypes.byref(cp), ctypes.byref(cn)))
+        ptrs[r] = cp.value
+        shards.append(a)
+    red = torch.maximum(torch.maximum(keys[0], keys[1]), keys[2])
+    root = shards[0]
+    keys[0].copy_(red)
+    torch.cuda.synchronize()
+    _check(lib.ss_exchange_pull_ptrs(root._h, ptrs, starts.ctypes.data_as(ctypes.c_void_p), world, 0))
+    out = np.empty((h, w, 3), np.uint8)
+    _check(lib.ss_finish_collapse(root._h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+    golden_util.assert_matches(out, root.get_depth_maps(), dict(fused=ref, best=info["best"], best_e=info["best_e"],
+                                                                best_d=info["best_d"], levels=info["levels"]), "peer gather")

@@ -103,6 +103,22 @@ SS_DEV void ss_mbar_wait(uint64_t *bar, unsigned parity)
 SS_DEV ss_f2 ss_mk2(float a, float b) { ss_f2 r; r.x = a; r.y = b; return r; }
 SS_DEV ss_f4 ss_mk4(float a, float b, float c, float d) { ss_f4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 
+// Exact integer -> float conversion of byte k / half-word k of a 32-bit word.  Device: one PRMT builds the
+// float 2^23 + v (0x4B000000 | v), one FADD removes the 2^23 -- both full-rate pipes, unlike I2F (quarter rate).
+#if defined(SS_HOST_EMU) || defined(SS_CVT_I2F)
+SS_DEV float ss_u8_to_f32(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+SS_DEV float ss_u16_to_f32(uint32_t w, int k) { return (float)((w >> (16 * k)) & 0xffffu); }
+#else
+SS_DEV float ss_u8_to_f32(uint32_t w, int k)
+{
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + k)), 8388608.0f);
+}
+SS_DEV float ss_u16_to_f32(uint32_t w, int k)
+{
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, k ? 0x7532u : 0x7510u)), 8388608.0f);
+}
+#endif
+
 // ---- tile geometry of the fused level kernel --------------------------------------------------------
 #define SS_NT 256            // threads per CTA; thread (tx,ty) = (tid&15, tid>>4) owns a 4x4 pixel block
 #define SS_TX 64             // output tile (pixels of level l)
@@ -360,7 +376,7 @@ SS_DEV void ss_s0_convert_u16(float *P0, int tid, const char *raw)
         const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
         float v[3][8];
 #pragma unroll
-        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = ss_u16_to_f32(wd[k >> 1], k & 1);
         ss_s0_store_unit(P0, r, u, v);
     }
 }
@@ -391,7 +407,7 @@ SS_DEV void ss_s0_convert_u8(float *P0, int tid, const char *raw)
         const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
         float v[3][8];
 #pragma unroll
-        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = ss_u8_to_f32(wd[k >> 2], k & 3);
         ss_s0_store_unit(P0, r, u, v);
     }
 }
@@ -415,13 +431,13 @@ SS_DEV void ss_s0_border(const SsLevelParams &p, const char *frame, int x0, int 
                 const ss_u2 a = *(const ss_u2 *)src, b = *(const ss_u2 *)(src + 8), c = *(const ss_u2 *)(src + 16);
                 const uint32_t wd[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
 #pragma unroll
-                for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = ss_u8_to_f32(wd[k >> 2], k & 3);
             } else if constexpr (sizeof(InT) == 2) {
                 const char *src = frame + (long long)y * p.in_pitch + X * 6;
                 const ss_u4 a = *(const ss_u4 *)src, b = *(const ss_u4 *)(src + 16), c = *(const ss_u4 *)(src + 32);
                 const uint32_t wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-                for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = (float)((wd[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+                for (int k = 0; k < 24; ++k) v[k % 3][k / 3] = ss_u16_to_f32(wd[k >> 1], k & 1);
             } else {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {

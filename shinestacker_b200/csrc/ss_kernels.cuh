@@ -92,6 +92,18 @@ SS_DEV void ss_tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t
                  ::"r"(ss_saddr(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(ss_saddr(bar))
                  : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
+SS_DEV void ss_bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ss_saddr(dst)), "l"(src), "r"(bytes), "r"(ss_saddr(bar))
+                 : "memory");
+}
+SS_DEV void ss_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ss_saddr(bar)), "r"(bytes) : "memory");
+}
 SS_DEV void ss_mbar_wait(uint64_t *bar, unsigned parity)
 {
     asm volatile("{\n\t.reg .pred p;\n\tSS_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
@@ -179,6 +191,9 @@ struct SsLevelParams {
     // ss_merge_groups_kernel folds the slices into the running state in frame order.
     int groups;
     long long group_stride;
+    float *lap_scratch;  // float32 levels: per-CTA 3 x 64 x 64 floats (own-block Laplacians of the current frame,
+                         // written and re-read by the same thread; stays in L2) so that P0 is free for the
+                         // next frame's patch while the energy stage runs
     int tma_row0;        // uint8 level 0: row of the batch's first frame in the frame-store tensor map (the store
                          // begins 8 bytes into its allocation, so byte column 8 + 3*(x0-8) is 16-byte aligned)
     float k25[25];
@@ -381,6 +396,23 @@ SS_DEV void ss_s0_convert_u16(float *P0, int tid, const char *raw)
     }
 }
 
+// float32 planes, prefetch form: the 3 x 76 patch rows are 228 bulk copies of 320 bytes, one per thread, completing
+// on the CTA's mbarrier (device) / plain copies (host emulation).
+SS_DEV void ss_s0_bulk_f32(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0, void *mbar)
+{
+    if (tid >= 3 * SS_P0H) return;
+    const int ch = tid / SS_P0H, r = tid - ch * SS_P0H;
+    const char *src = frame + ch * p.in_plane_stride + (long long)(y0 - SS_P0Y + r) * p.in_pitch + (x0 - SS_P0X) * 4;
+    float *dst = P0 + ch * SS_P0P + r * SS_P0S;
+#ifdef SS_HOST_EMU
+    (void)mbar;
+    memcpy(dst, src, SS_P0W * 4);
+#else
+    if (tid == 0) ss_mbar_expect_tx((uint64_t *)mbar, 3 * SS_P0H * SS_P0W * 4);
+    ss_bulk_load(dst, src, SS_P0W * 4, (uint64_t *)mbar);
+#endif
+}
+
 // float32 planes: the patch rows are copied straight into P0 (16-byte chunks, all in flight at once).
 SS_DEV void ss_s0_async_f32(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0)
 {
@@ -469,7 +501,8 @@ __device__ __forceinline__
 #else
 static inline
 #endif
-void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int tile_y, int group, float *smem)
+void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int tile_y, int group, int cta_linear,
+                   float *smem)
 {
     float *P0 = smem;
     float *P1 = P0 + SS_P1OFF;
@@ -500,15 +533,26 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
 
     SS_PT_DECL(float, be, 16);
 
+    // float32 levels, interior fast tiles: own-block Laplacians go to a per-CTA global scratch instead of being
+    // parked in P0, and the NEXT frame's patch is bulk-copied into P0 while the energy stage runs
+    const bool pref32 = sizeof(InT) == 4 && interior && fast && p.lap_scratch != nullptr;
+    float *const scratch = pref32 ? p.lap_scratch + (long long)cta_linear * (3 * SS_TX * SS_TY) : nullptr;
     // uint8, interior tiles: raw patch of frame f arrives by TMA (device) / memcpy (host emulation)
 #ifndef SS_HOST_EMU
     uint64_t *mbar = (uint64_t *)(smem + SS_SMEM_FLOATS);
     unsigned mbar_phase = 0;
-    if (interior && sizeof(InT) == 1) {
+    if ((interior && sizeof(InT) == 1) || pref32) {
         if (threadIdx.x == 0) {
             ss_mbar_init(mbar, 1);
         }
         __syncthreads();
+    }
+    if (pref32) {
+        ss_s0_bulk_f32(p, (const char *)p.in + (long long)f_begin * p.in_frame_stride, x0, y0, threadIdx.x, P0, mbar);
+        ss_mbar_wait(mbar, mbar_phase);
+        mbar_phase ^= 1;
+    }
+    if (interior && sizeof(InT) == 1) {
         if (threadIdx.x == 0)
             ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + f_begin * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
         ss_mbar_wait(mbar, mbar_phase);
@@ -516,6 +560,13 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
     }
 #else
     (void)tmap;
+    void *mbar = nullptr;
+    if (pref32) {
+        SS_THREADS(tid)
+        {
+            ss_s0_bulk_f32(p, (const char *)p.in + (long long)f_begin * p.in_frame_stride, x0, y0, tid, P0, mbar);
+        }
+    }
     if (interior && sizeof(InT) == 1) {
         SS_THREADS(tid)
         {
@@ -552,7 +603,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                 } else if constexpr (sizeof(InT) == 2) {
                     ss_s0_async_u16(p, frame, x0, y0, tid, (char *)P1);
                     ss_cp_async_wait();
-                } else {
+                } else if (!pref32) {
                     ss_s0_async_f32(p, frame, x0, y0, tid, P0);
                     ss_cp_async_wait();
                 }
@@ -669,8 +720,11 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                         const ss_f4 g = *(const ss_f4 *)gp;
                         const float l0 = ss_fma(-4.f, acc[r * 4 + 0], g.x), l1 = ss_fma(-4.f, acc[r * 4 + 1], g.y);
                         const float l2 = ss_fma(-4.f, acc[r * 4 + 2], g.z), l3 = ss_fma(-4.f, acc[r * 4 + 3], g.w);
-                        // park the Laplacian in place of g_l: this position is read by no other thread
-                        *(ss_f4 *)gp = ss_mk4(l0, l1, l2, l3);
+                        if (pref32)   // own-block Laplacian -> per-CTA global scratch (re-read by this thread only)
+                            *(ss_f4 *)(scratch + ((it == 0 ? 1 : (it == 1 ? 0 : 2)) * SS_TY + 4 * ty + r) * SS_TX + 4 * tx) =
+                                ss_mk4(l0, l1, l2, l3);
+                        else          // park it in place of g_l: this position is read by no other thread
+                            *(ss_f4 *)gp = ss_mk4(l0, l1, l2, l3);
                         gray[r * 4 + 0] = ss_fma(l0, wgt, gray[r * 4 + 0]);
                         gray[r * 4 + 1] = ss_fma(l1, wgt, gray[r * 4 + 1]);
                         gray[r * 4 + 2] = ss_fma(l2, wgt, gray[r * 4 + 2]);
@@ -768,6 +822,8 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             const int tx = tid & 15, ty = tid >> 4;
             const int gidx = p.frame_index0 + f;
             const bool take_all = fresh && f == f_begin;
+            if (pref32 && f + 1 < f_end)   // P0 is not read any more in this frame
+                ss_s0_bulk_f32(p, frame + p.in_frame_stride, x0, y0, tid, P0, mbar);
             if (interior && sizeof(InT) == 1 && f + 1 < f_end) {   // P1 is dead until the next S1
 #ifndef SS_HOST_EMU
                 if (tid == 0)
@@ -838,11 +894,18 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                 for (int q = 0; q < 16; ++q) {
                     if (won & (1u << q)) {
                         const long long o = o0 + (long long)(q >> 2) * p.w + (q & 3);
-                        const float *ls = lsrc + (q >> 2) * SS_P0S + (q & 3);
                         st_idx[o] = gidx;
-                        st_fused[o] = ss_add(0.f, ls[0]);
-                        st_fused[plane_px + o] = ss_add(0.f, ls[SS_P0P]);
-                        st_fused[2 * plane_px + o] = ss_add(0.f, ls[2 * SS_P0P]);
+                        float l0, l1, l2;
+                        if (pref32) {
+                            const float *ls = scratch + (4 * ty + (q >> 2)) * SS_TX + 4 * tx + (q & 3);
+                            l0 = ls[0]; l1 = ls[SS_TX * SS_TY]; l2 = ls[2 * SS_TX * SS_TY];
+                        } else {
+                            const float *ls = lsrc + (q >> 2) * SS_P0S + (q & 3);
+                            l0 = ls[0]; l1 = ls[SS_P0P]; l2 = ls[2 * SS_P0P];
+                        }
+                        st_fused[o] = ss_add(0.f, l0);
+                        st_fused[plane_px + o] = ss_add(0.f, l1);
+                        st_fused[2 * plane_px + o] = ss_add(0.f, l2);
                     }
                 }
             }
@@ -850,7 +913,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
         // S3 reads the parked Laplacians from P0, so it must finish before the next frame's S0; the
         // asynchronous copies of the next frame's raw patch must have landed as well
 #ifndef SS_HOST_EMU
-        if (interior && sizeof(InT) == 1 && f + 1 < f_end) {
+        if (((interior && sizeof(InT) == 1) || pref32) && f + 1 < f_end) {
             ss_mbar_wait(mbar, mbar_phase);
             mbar_phase ^= 1;
         }

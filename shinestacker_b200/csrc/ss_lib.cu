@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(SS_NT, 2) ss_level_kernel(const __grid_constan
     extern __shared__ __align__(128) float ss_smem[];
     int tx, ty;
     ss_tile_of_block(blockIdx.y * gridDim.x + blockIdx.x, gridDim.x, gridDim.y, tx, ty);
-    ss_level_tile<InT>(p, &tmap, tx, ty, blockIdx.z, ss_smem);
+    ss_level_tile<InT>(p, &tmap, tx, ty, blockIdx.z,
+                       (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, ss_smem);
 }
 
 // Folds the per-group partial states of a frame-split level launch into the running state, groups in
@@ -431,6 +432,8 @@ struct ss_handle {
     // frame store (ring of n_slots device frames)
     char *frames = nullptr;
     size_t frame_pitch = 0, frame_bytes = 0, frame_shift = 0;
+    float *lap_scratch = nullptr;    // float32 levels: 3 x 64 x 64 floats per CTA of the largest level >= 1 launch
+    size_t lap_scratch_ctas = 0;
     CUtensorMap tmap_frames;         // uint8 frame store as a 2-D byte tensor [n_slots * H rows][pitch]: TMA boxes
     int n_slots = 0, batch = 0;
     // base level
@@ -561,6 +564,7 @@ SS_EXPORT void ss_destroy(ss_handle *h)
         cudaFree(l.gnext);
         cudaFree(l.grp_e); cudaFree(l.grp_idx); cudaFree(l.grp_fused);
     }
+    cudaFree(h->lap_scratch);
     cudaFree(h->frames); cudaFree(h->base); cudaFree(h->gray); cudaFree(h->counts);
     cudaFree(h->log_p); cudaFree(h->state_val); cudaFree(h->state_idx); cudaFree(h->state_coef);
     cudaFree(h->ent); cudaFree(h->dev);
@@ -686,6 +690,11 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
         if (l + 1 < h->L)
             if ((rc = ss_dalloc(&v.gnext, (size_t)h->batch * 3 * h->lh[l + 1] * v.gpitch))) return rc;
     }
+    for (int l = 1; l < h->L; ++l) {
+        const size_t ctas = (size_t)((h->lv[l].w + SS_TX - 1) / SS_TX) * ((h->lv[l].h + SS_TY - 1) / SS_TY) * h->lv[l].max_groups;
+        if (ctas > h->lap_scratch_ctas) h->lap_scratch_ctas = ctas;
+    }
+    if (h->lap_scratch_ctas && (rc = ss_dalloc(&h->lap_scratch, h->lap_scratch_ctas * 3 * SS_TX * SS_TY))) return rc;
     const size_t nb = (size_t)h->lh[h->L] * h->lw[h->L];
     if ((rc = ss_dalloc(&h->base, (size_t)cfg->max_frames * 3 * nb))) return rc;
     if ((rc = ss_dalloc(&h->gray, (size_t)cfg->max_frames * nb))) return rc;
@@ -892,6 +901,7 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
             p.in_pitch = (int)h->frame_pitch;
         } else {
             p.in = h->lv[l - 1].gnext;
+            p.lap_scratch = h->lap_scratch;
             p.in_pitch = h->lv[l - 1].gpitch * 4;
             p.in_plane_stride = (long long)v.h * p.in_pitch;
             p.in_frame_stride = 3 * p.in_plane_stride;

@@ -28,14 +28,17 @@ extern "C" int emu_level(const void *in, int bytes_per_sample /*1,2: interleaved
     p.n_frames = n_frames; p.frame_index0 = frame_index0; p.init = init; p.groups = 1; p.group_stride = 0;
     memcpy(p.k25, k25, sizeof(p.k25));
     float *smem = (float *)malloc(SS_SMEM_BYTES);
+    float *scratch = (float *)malloc(sizeof(float) * 3 * SS_TX * SS_TY);
+    p.lap_scratch = scratch;
     // poison shared memory so that any read of a never-written slot shows up as NaN
     for (int ty = 0; ty < (h + SS_TY - 1) / SS_TY; ++ty)
         for (int tx = 0; tx < (w + SS_TX - 1) / SS_TX; ++tx) {
             memset(smem, 0xff, SS_SMEM_BYTES);
-            if (bytes_per_sample == 1) ss_level_tile<uint8_t>(p, nullptr, tx, ty, 0, smem);
-            else if (bytes_per_sample == 2) ss_level_tile<uint16_t>(p, nullptr, tx, ty, 0, smem);
-            else ss_level_tile<float>(p, nullptr, tx, ty, 0, smem);
+            if (bytes_per_sample == 1) ss_level_tile<uint8_t>(p, nullptr, tx, ty, 0, 0, smem);
+            else if (bytes_per_sample == 2) ss_level_tile<uint16_t>(p, nullptr, tx, ty, 0, 0, smem);
+            else ss_level_tile<float>(p, nullptr, tx, ty, 0, 0, smem);
         }
     free(smem);
+    free(scratch);
     return 0;
 }

@@ -451,8 +451,11 @@ SS_DEV void ss_s0_convert_u8(float *P0, int tid, const char *raw)
 template <typename InT>
 SS_DEV void ss_s0_border(const SsLevelParams &p, const char *frame, int x0, int y0, int tid, float *P0)
 {
-#pragma unroll 1
-    for (int i = tid; i < SS_P0H * 10; i += SS_NT) {
+    // three independent items per thread, unrolled: all their global loads are in flight together
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+        const int i = tid + kk * SS_NT;
+        if (i >= SS_P0H * 10) break;
         const int u = i / SS_P0H, r = i - u * SS_P0H;
         const int y = ss_reflect_clamp(y0 - SS_P0Y + r, p.h);
         const int X = x0 - SS_P0X + 8 * u;
@@ -530,6 +533,8 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
     float *const st_e = p.best_e + group * p.group_stride;
     int32_t *const st_idx = p.best_idx + group * p.group_stride;
     float *const st_fused = p.fused + 3 * group * p.group_stride;
+    // rows of the coefficient planes 16-byte aligned?  (vector stores of the first frame's coefficients)
+    const bool state_vec4 = ((p.w & 3) == 0) && ((plane_px & 3) == 0) && ((((unsigned long long)st_fused) & 15) == 0);
 
     SS_PT_DECL(float, be, 16);
 
@@ -592,6 +597,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
 
     for (int f = f_begin; f < f_end; ++f) {
         const char *frame = (const char *)p.in + (long long)f * p.in_frame_stride;
+        const bool first_frame = fresh && f == f_begin;   // every in-image pixel takes this frame
         // ---- S0: g_l patch -------------------------------------------------------------------------
         if (interior) {
             SS_THREADS(tid)
@@ -720,7 +726,16 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                         const ss_f4 g = *(const ss_f4 *)gp;
                         const float l0 = ss_fma(-4.f, acc[r * 4 + 0], g.x), l1 = ss_fma(-4.f, acc[r * 4 + 1], g.y);
                         const float l2 = ss_fma(-4.f, acc[r * 4 + 2], g.z), l3 = ss_fma(-4.f, acc[r * 4 + 3], g.w);
-                        if (pref32)   // own-block Laplacian -> per-CTA global scratch (re-read by this thread only)
+                        if (pref32 && first_frame) {   // all pixels win: straight into the running state (0 + lap)
+                            float *fd = st_fused + (it == 0 ? 1 : (it == 1 ? 0 : 2)) * plane_px +
+                                        (long long)(y0 + 4 * ty + r) * p.w + x0 + 4 * tx;
+                            if (state_vec4) {
+                                *(ss_f4 *)fd = ss_mk4(ss_add(0.f, l0), ss_add(0.f, l1), ss_add(0.f, l2), ss_add(0.f, l3));
+                            } else {
+                                fd[0] = ss_add(0.f, l0); fd[1] = ss_add(0.f, l1);
+                                fd[2] = ss_add(0.f, l2); fd[3] = ss_add(0.f, l3);
+                            }
+                        } else if (pref32)   // own-block Laplacian -> per-CTA global scratch (re-read by this thread only)
                             *(ss_f4 *)(scratch + ((it == 0 ? 1 : (it == 1 ? 0 : 2)) * SS_TY + 4 * ty + r) * SS_TX + 4 * tx) =
                                 ss_mk4(l0, l1, l2, l3);
                         else          // park it in place of g_l: this position is read by no other thread
@@ -821,7 +836,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
         {
             const int tx = tid & 15, ty = tid >> 4;
             const int gidx = p.frame_index0 + f;
-            const bool take_all = fresh && f == f_begin;
+            const bool take_all = first_frame;
             if (pref32 && f + 1 < f_end)   // P0 is not read any more in this frame
                 ss_s0_bulk_f32(p, frame + p.in_frame_stride, x0, y0, tid, P0, mbar);
             if (interior && sizeof(InT) == 1 && f + 1 < f_end) {   // P1 is dead until the next S1
@@ -895,6 +910,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     if (won & (1u << q)) {
                         const long long o = o0 + (long long)(q >> 2) * p.w + (q & 3);
                         st_idx[o] = gidx;
+                        if (pref32 && first_frame) continue;   // coefficients were stored by S2
                         float l0, l1, l2;
                         if (pref32) {
                             const float *ls = scratch + (4 * ty + (q >> 2)) * SS_TX + 4 * tx + (q & 3);

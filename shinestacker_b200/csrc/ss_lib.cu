@@ -672,11 +672,11 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
         v.fused = h->state_coef + h->seg.coef_off[l];
         v.gpitch = (h->lw[l + 1] + 3) / 4 * 4;
         {
-            // frame-split so that every level launch has >= ~6 waves of CTAs (2 CTAs/SM x 148 SMs per wave):
-            // border tiles run longer than interior ones and few waves leave the SMs idle at the tail
+            // frame-split so that every level launch has >= ~6 waves of CTAs (2 CTAs/SM x 148 SMs per wave): fewer
+            // waves leave SMs idle at the tail, more groups cost extra first-frame stores and merge work
             const int tiles = ((v.w + SS_TX - 1) / SS_TX) * ((v.h + SS_TY - 1) / SS_TY);
             const char *wenv = getenv("SS_TARGET_WAVES");   // tuning knob (default 6)
-            const int waves = wenv && atoi(wenv) > 0 ? atoi(wenv) : (tiles >= 2000 ? 6 : 20);
+            const int waves = wenv && atoi(wenv) > 0 ? atoi(wenv) : 6;   // measured best on B200 (sweep 6..28)
             int g = (waves * 2 * 148 + tiles - 1) / tiles;
             if (g < 1) g = 1;
             if (g > h->batch) g = h->batch;

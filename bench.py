@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--width", type=int, default=4096)
     ap.add_argument("--dtype", default="uint8", choices=["uint8", "uint16"])
     ap.add_argument("--batch", type=int, default=8, help="frames per kernel-chain launch on the e2e path")
-    ap.add_argument("--cpu-sample-frames", type=int, default=8)
+    ap.add_argument("--cpu-sample-frames", type=int, default=64,
+                    help="frames of the stack the CPU baseline fuses (64 = the whole workload, ~10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -108,14 +109,16 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": float(max(power))}
 
 
-def cpu_baseline(a, n_sample, threads=None):
+def cpu_baseline(a, n_sample, threads=None, frames=None):
     """The oracle (CPU port of the reference arithmetic) on a bounded sample: the first n_sample
     frames of the same synthetic stack.  The oracle is O(frames), so MP/s is representative."""
     from oracle import pyramid_oracle as po
     from shinestacker_b200 import synthetic
     po.build()
     cores = po.set_threads(threads or os.cpu_count() or 1)
-    frames = synthetic.make_stack(a.frames, a.height, a.width, np.dtype(a.dtype), seed=2)[:n_sample]
+    if frames is None:
+        frames = synthetic.make_stack(a.frames, a.height, a.width, np.dtype(a.dtype), seed=2)
+    frames = frames[:n_sample]
     t0 = time.perf_counter()
     po.focus_stack(frames)
     dt = time.perf_counter() - t0
@@ -137,7 +140,7 @@ def run_reference(a):
     from shinestacker_b200 import synthetic
     po.build()
     cores = po.set_threads(os.cpu_count() or 1)
-    n_sample = max(1, min(a.cpu_sample_frames, a.frames))
+    n_sample = max(1, min(a.cpu_sample_frames, a.frames, 16))   # bounded: K + W steps must end within minutes
     frames = synthetic.make_stack(a.frames, a.height, a.width, np.dtype(a.dtype), seed=2)[:n_sample]
     for _ in range(a.warmup):
         po.focus_stack(frames[:1])
@@ -339,7 +342,7 @@ def main():
                                  "frac": fp32_rate / 36.2, "algorithmic_chain_steps_per_pixel": 73.5,
                                  "peak_source": "tools/microbench.cu on B200 (scalar FFMA, 124.5 of 128 lanes/clk/SM)"}
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_baseline(a, max(1, min(a.cpu_sample_frames, N)))
+            line["cpu_baseline"], _ = cpu_baseline(a, max(1, min(a.cpu_sample_frames, N)), frames=list(host))
         print(json.dumps(line))
     lib.ss_host_free(pin)
     lib.ss_host_free(out_pin)

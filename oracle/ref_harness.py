@@ -112,3 +112,57 @@ def reference_stack_arrays(frames, **kwargs):
                 levels=len(pyrs[0]) - 1, fused_pyramid=algo.rec_fused,
                 entropy=algo.rec_entropy, deviation=algo.rec_deviation)
     return out, info
+
+
+def import_reference_depthmap():
+    """Return the reference's ``shinestacker.algorithms.depth_map`` module."""
+    import_reference()
+    import shinestacker.algorithms.depth_map as dm  # pylint: disable=import-outside-toplevel
+    return dm
+
+
+def reference_depthmap_arrays(frames, **kwargs):
+    """Run the reference ``DepthMapStack`` (depth_map.py:10-123) on in-memory BGR frames.
+
+    ``focus_stack`` reads every file twice through ``read_img`` (depth_map.py:70,96); the harness feeds the
+    arrays through those two hooks instead of files, everything else is the unmodified reference code.
+    Returns ``(fused_image, dict(energy=..., smoothed=..., weights=...))`` (stages recorded by overriding
+    ``smooth_energy`` / ``get_focus_map``).
+    """
+    dm = import_reference_depthmap()
+    frames = list(frames)
+    names = [f"/virtual/{i:04d}.tif" for i in range(len(frames))]
+    lookup = dict(zip(names, frames))
+    rec = {}
+
+    class RecordingDepthMapStack(dm.DepthMapStack):
+        def read_image_and_update_metadata(self, img_path, metadata):
+            img = lookup[img_path]
+            if metadata is None:
+                return img, (img.shape[:2], img.dtype), True
+            return img, metadata, False
+
+        def smooth_energy(self, energy_map):
+            rec["normalized"] = np.array(energy_map)
+            out = super().smooth_energy(energy_map)
+            rec["smoothed"] = np.array(out)
+            return out
+
+        def get_focus_map(self, energies):
+            if "smoothed" not in rec:
+                rec["smoothed"] = np.array(energies)
+            out = super().get_focus_map(energies)
+            rec["weights"] = np.array(out)
+            return out
+
+    algo = RecordingDepthMapStack(**kwargs)
+    algo.process = MagicMock()
+    algo.process.callback.return_value = True
+    algo.print_message = MagicMock()
+    saved = dm.read_img
+    dm.read_img = lambda p: lookup[p]
+    try:
+        out = algo.focus_stack(names)
+    finally:
+        dm.read_img = saved
+    return out, rec

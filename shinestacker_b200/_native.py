@@ -32,6 +32,26 @@ class SsConfig(ctypes.Structure):
     ]
 
 
+class SsdmConfig(ctypes.Structure):
+    """struct ssdm_config (include/shinestack_b200_depthmap.h)."""
+    _fields_ = [
+        ("width", ctypes.c_int32),
+        ("height", ctypes.c_int32),
+        ("bytes_per_sample", ctypes.c_int32),
+        ("map_type", ctypes.c_int32),
+        ("energy", ctypes.c_int32),
+        ("kernel_size", ctypes.c_int32),
+        ("blur_size", ctypes.c_int32),
+        ("smooth_size", ctypes.c_int32),
+        ("temperature", ctypes.c_double),
+        ("levels", ctypes.c_int32),
+        ("float_bits", ctypes.c_int32),
+        ("device", ctypes.c_int32),
+        ("max_frames", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 4),
+    ]
+
+
 SS_OK = 0
 SS_ERR_INVALID_OPTION = -1
 SS_ERR_SHAPE = -2
@@ -90,6 +110,24 @@ SIGNATURES = {
     "ss_test_collapse_step": (_i, [_vp, _i, _i, _vp, _i, _i, ctypes.c_double, _vp]),
 }
 
+# every symbol declared in include/shinestack_b200_depthmap.h
+SIGNATURES_DEPTHMAP = {
+    "ssdm_create": (_i, [ctypes.POINTER(SsdmConfig), ctypes.POINTER(_vp)]),
+    "ssdm_destroy": (None, [_vp]),
+    "ssdm_reset": (_i, [_vp]),
+    "ssdm_push_frame": (_i, [_vp, _vp, _sz]),
+    "ssdm_push_frame_device": (_i, [_vp, _vp, _sz]),
+    "ssdm_sync_copies": (_i, [_vp]),
+    "ssdm_finish_begin": (_i, [_vp]),
+    "ssdm_blend_frame": (_i, [_vp, _i]),
+    "ssdm_finish_end": (_i, [_vp, _vp, _sz]),
+    "ssdm_finish": (_i, [_vp, _vp, _sz]),
+    "ssdm_rerun_resident": (_i, [_vp]),
+    "ssdm_get_plane": (_i, [_vp, _i, _i, _vp]),
+    "ssdm_kernel_time_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "ssdm_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),
+}
+
 _LIB = None
 
 
@@ -106,7 +144,7 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as e:
         raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(SIGNATURES_DEPTHMAP.items()):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

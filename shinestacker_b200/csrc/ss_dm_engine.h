@@ -1,0 +1,351 @@
+// ss_dm_engine.h -- launch sequence of the depth-map stacker (reference depth_map.py:64-123), written
+// against a tiny backend (allocate / copy / launch a pixel functor) so that the very same sequence runs
+// on the GPU in the product (CudaBackend, ss_dm_lib.cuh) and in plain loops in the CPU emulation used by
+// the tests (tests/emu/emu_depthmap.cpp).  No arithmetic lives here: every pixel is computed by the
+// functors of ss_dm_kernels.cuh.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "ss_dm_kernels.cuh"
+
+enum { DM_OK = 0, DM_ERR_INVALID_OPTION = -1, DM_ERR_CUDA = -4, DM_ERR_STATE = -6, DM_ERR_NOMEM = -7 };
+
+struct DmOptions {          // DepthMapStack.__init__ (depth_map.py:11-26) + frame geometry
+    int width, height, bytes_per_sample;
+    int map_type;           // 0 'average', 1 'max'
+    int energy;             // 0 'laplacian', 1 'sobel'
+    int kernel_size, blur_size, smooth_size;
+    double temperature;
+    int levels;
+    int max_frames;
+};
+
+// cv2.getGaussianKernel(n, sigma <= 0, CV_32F): fixed tables up to 9 taps, else sigma = 0.3*((n-1)*0.5-1)+0.8
+static inline void dm_gaussian_kernel(int n, std::vector<float> &k)
+{
+    static const float t1[] = {1.f}, t3[] = {0.25f, 0.5f, 0.25f}, t5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f},
+                       t7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f},
+                       t9[] = {4 / 256.f, 13 / 256.f, 30 / 256.f, 51 / 256.f, 60 / 256.f, 51 / 256.f, 30 / 256.f,
+                               13 / 256.f, 4 / 256.f};
+    const float *tabs[] = {t1, t3, t5, t7, t9};
+    k.resize(n);
+    if (n <= 9) { memcpy(k.data(), tabs[n / 2], n * sizeof(float)); return; }
+    const double sigma = 0.3 * ((n - 1) * 0.5 - 1) + 0.8, s2 = -0.5 / (sigma * sigma);
+    std::vector<double> d(n);
+    double sum = 0;
+    for (int i = 0; i < n; ++i) { const double x = i - (n - 1) * 0.5; d[i] = exp(s2 * x * x); sum += d[i]; }
+    for (int i = 0; i < n; ++i) k[i] = (float)(d[i] / sum);
+}
+
+// cv2.getDerivKernels / getSobelKernels(order, ksize > 3): integer binomial construction
+static inline void dm_sobel_kernel(int ksize, int order, std::vector<float> &k)
+{
+    std::vector<long long> ker(ksize + 1, 0);
+    ker[0] = 1;
+    for (int i = 0; i < ksize - order - 1; ++i) {
+        long long oldval = ker[0];
+        for (int j = 1; j <= ksize; ++j) { const long long nv = ker[j] + ker[j - 1]; ker[j - 1] = oldval; oldval = nv; }
+    }
+    for (int i = 0; i < order; ++i) {
+        long long oldval = -ker[0];
+        for (int j = 1; j <= ksize; ++j) { const long long nv = ker[j - 1] - ker[j]; ker[j - 1] = oldval; oldval = nv; }
+    }
+    k.resize(ksize);
+    for (int i = 0; i < ksize; ++i) k[i] = (float)ker[i];
+}
+
+static inline DmTaps dm_make_taps(const std::vector<float> &k)
+{
+    DmTaps t;
+    memset(&t, 0, sizeof(t));
+    const int n = (int)k.size();
+    t.r = n / 2;
+    t.anti = (t.r > 0 && k[t.r] == 0.f && k[0] == -k[n - 1] && k[0] != 0.f) ? 1 : 0;
+    for (int j = 0; j <= t.r; ++j) t.k[j] = k[t.r + j];
+    return t;
+}
+
+template <class Backend>
+struct DmEngine {
+    Backend be;
+    DmOptions o;
+    int h = 0, w = 0, bps = 0, L = 1, n = 0, finished = 0, blended = 0, collapsed = 0;
+    long long plane = 0;
+    size_t frame_pitch = 0, frame_bytes = 0;
+    char err[256];
+    uint8_t *d_frames = nullptr, *d_out = nullptr;
+    float *d_energy = nullptr, *d_smooth = nullptr, *d_t1 = nullptr, *d_t2 = nullptr, *d_t3 = nullptr, *d_sw = nullptr;
+    float *weights = nullptr;      // the buffer that holds the focus maps after finish_begin
+    unsigned *d_stats = nullptr;
+    std::vector<int> lh, lw;
+    std::vector<float *> gp, acc;  // gp[l] (l >= 1): 4 planes; acc[l]: 3 planes
+    DmTaps t_blur, t_a, t_b;
+    int bil_r = 0;
+    float gmax = 0.f;
+
+    int fail(int code, const char *msg) { snprintf(err, sizeof(err), "%s", msg); return code; }
+
+    int create(const DmOptions &opt)
+    {
+        o = opt;
+        err[0] = 0;
+        h = o.height; w = o.width; bps = o.bytes_per_sample;
+        if (w < 1 || h < 1 || (bps != 1 && bps != 2)) return fail(DM_ERR_INVALID_OPTION, "invalid frame geometry");
+        if (o.map_type != 0 && o.map_type != 1) return fail(DM_ERR_INVALID_OPTION, "map_type: valid values are average and max");
+        if (o.energy != 0 && o.energy != 1) return fail(DM_ERR_INVALID_OPTION, "energy: valid values are laplacian and sobel");
+        if (o.levels < 1 || o.levels > 16) return fail(DM_ERR_INVALID_OPTION, "levels must be in 1..16");
+        if (o.max_frames < 1 || o.max_frames > 65535) return fail(DM_ERR_INVALID_OPTION, "max_frames must be in 1..65535");
+        std::vector<float> k;
+        if (o.energy == 0) {
+            if (o.blur_size < 1 || o.blur_size > 31 || !(o.blur_size & 1))
+                return fail(DM_ERR_INVALID_OPTION, "blur_size must be odd and in 1..31");
+            // cv2.Laplacian(float32 -> CV_64F) with ksize 1/3 raises in the reference's cv2; ksize must be odd
+            if (o.kernel_size < 5 || o.kernel_size > 31 || !(o.kernel_size & 1))
+                return fail(DM_ERR_INVALID_OPTION, "kernel_size must be odd and in 5..31 (cv2.Laplacian float32 -> CV_64F)");
+            dm_gaussian_kernel(o.blur_size, k); t_blur = dm_make_taps(k);
+            dm_sobel_kernel(o.kernel_size, 2, k); t_a = dm_make_taps(k);
+            dm_sobel_kernel(o.kernel_size, 0, k); t_b = dm_make_taps(k);
+        } else {
+            k.assign(1, 1.f); t_blur = dm_make_taps(k);
+            const float kd[] = {-1.f, 0.f, 1.f}, ks[] = {1.f, 2.f, 1.f};
+            k.assign(kd, kd + 3); t_a = dm_make_taps(k);
+            k.assign(ks, ks + 3); t_b = dm_make_taps(k);
+        }
+        L = o.levels;
+        lh.assign(L, 0); lw.assign(L, 0);
+        lh[0] = h; lw[0] = w;
+        for (int l = 1; l < L; ++l) { lh[l] = (lh[l - 1] + 1) / 2; lw[l] = (lw[l - 1] + 1) / 2; }
+        plane = (long long)h * w;
+        frame_pitch = (size_t)w * 3 * bps;
+        frame_bytes = frame_pitch * h;
+        const size_t nf = (size_t)o.max_frames;
+        int rc;
+        if ((rc = be.alloc((void **)&d_frames, nf * frame_bytes))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_out, frame_bytes))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_energy, nf * plane * sizeof(float)))) return fail(rc, be.last_error());
+        if (o.smooth_size > 0 && (rc = be.alloc((void **)&d_smooth, nf * plane * sizeof(float)))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_t1, plane * sizeof(float)))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_t2, plane * sizeof(float)))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_t3, plane * sizeof(float)))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_stats, nf * 2 * sizeof(unsigned)))) return fail(rc, be.last_error());
+        gp.assign(L, nullptr); acc.assign(L, nullptr);
+        for (int l = 0; l < L; ++l) {
+            const size_t px = (size_t)lh[l] * lw[l];
+            if (l > 0 && (rc = be.alloc((void **)&gp[l], 4 * px * sizeof(float)))) return fail(rc, be.last_error());
+            if ((rc = be.alloc((void **)&acc[l], 3 * px * sizeof(float)))) return fail(rc, be.last_error());
+        }
+        if (o.smooth_size > 0) {
+            // cv2.bilateralFilter: radius = max(d/2, 1); space weight exp(-r^2 / (2*25^2)) inside the disc
+            bil_r = o.smooth_size / 2 > 1 ? o.smooth_size / 2 : 1;
+            if (bil_r > 32) return fail(DM_ERR_INVALID_OPTION, "smooth_size must be <= 65");
+            const int d = 2 * bil_r + 1;
+            std::vector<float> sw((size_t)d * d, 0.f);
+            const double gs = -0.5 / (25.0 * 25.0);
+            for (int i = -bil_r; i <= bil_r; ++i)
+                for (int j = -bil_r; j <= bil_r; ++j) {
+                    const double r = sqrt((double)i * i + (double)j * j);
+                    if (r > bil_r) continue;
+                    sw[(size_t)(i + bil_r) * d + (j + bil_r)] = (float)exp(r * r * gs);
+                }
+            if ((rc = be.alloc((void **)&d_sw, sw.size() * sizeof(float)))) return fail(rc, be.last_error());
+            if ((rc = be.upload_small(d_sw, sw.data(), sw.size() * sizeof(float)))) return fail(rc, be.last_error());
+        }
+        return reset();
+    }
+
+    void destroy()
+    {
+        be.sync();
+        void *ptrs[] = {d_frames, d_out, d_energy, d_smooth, d_t1, d_t2, d_t3, d_stats, d_sw};
+        for (void *p : ptrs) if (p) be.free(p);
+        for (float *p : gp) if (p) be.free(p);
+        for (float *p : acc) if (p) be.free(p);
+        d_frames = d_out = nullptr; d_energy = d_smooth = d_t1 = d_t2 = d_t3 = d_sw = nullptr; d_stats = nullptr;
+        gp.clear(); acc.clear();
+    }
+
+    int reset()
+    {
+        int rc = be.sync();
+        if (rc) return fail(rc, be.last_error());
+        n = 0; finished = 0; blended = 0; collapsed = 0; weights = nullptr; gmax = 0.f;
+        be.reset_counters();
+        std::vector<unsigned> init(2 * (size_t)o.max_frames);
+        for (size_t i = 0; i < init.size(); i += 2) { init[i] = 0x7f800000u; init[i + 1] = 0u; }  // min = +inf, max = 0
+        if ((rc = be.upload_small(d_stats, init.data(), init.size() * sizeof(unsigned)))) return fail(rc, be.last_error());
+        return DM_OK;
+    }
+
+    // pass 1 of one frame that already sits in slot i of the frame store
+    template <typename InT>
+    int energy_of_frame(int i)
+    {
+        int rc;
+        const void *frame = d_frames + (size_t)i * frame_bytes;
+        float *e = d_energy + (size_t)i * plane;
+        unsigned *st = d_stats + 2 * (size_t)i;
+        if (o.energy == 0) {
+            DmGrayRowFilter<InT> a{frame, (long long)frame_pitch, h, w, t_blur, d_t1};
+            if ((rc = be.launch(a, w, h, 1))) return rc;
+            DmColFilter b{d_t1, h, w, t_blur, d_t3};
+            if ((rc = be.launch(b, w, h, 1))) return rc;
+            DmRowPair c{d_t3, h, w, t_a, t_b, d_t1, d_t2};
+            if ((rc = be.launch(c, w, h, 1))) return rc;
+        } else {
+            DmGrayRowFilter<InT> a{frame, (long long)frame_pitch, h, w, t_blur, d_t3};
+            if ((rc = be.launch(a, w, h, 1))) return rc;
+            DmRowPair c{d_t3, h, w, t_a, t_b, d_t1, d_t2};
+            if ((rc = be.launch(c, w, h, 1))) return rc;
+        }
+        DmColCombine d{d_t1, d_t2, h, w, t_a, t_b, o.energy, e, st};
+        return be.launch(d, w, h, 1);
+    }
+
+    // replaces one iteration of the first loop of focus_stack (depth_map.py:68-77) + that frame's share
+    // of get_sobel_map / get_laplacian_map (depth_map.py:28-42)
+    int push_frame(const void *bgr, size_t pitch, int on_device)
+    {
+        if (finished) return fail(DM_ERR_STATE, "push after finish: call reset first");
+        if (n >= o.max_frames) return fail(DM_ERR_STATE, "more frames than max_frames");
+        if (pitch < frame_pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
+        if (n == 0) be.mark_start();
+        int rc = be.upload_frame(d_frames + (size_t)n * frame_bytes, frame_pitch, bgr, pitch, frame_pitch, h, on_device);
+        if (rc) return fail(rc, be.last_error());
+        rc = bps == 1 ? energy_of_frame<uint8_t>(n) : energy_of_frame<uint16_t>(n);
+        if (rc) return fail(rc, be.last_error());
+        ++n;
+        return DM_OK;
+    }
+
+    // depth_map.py:88-93: global normalisation, bilateral smoothing, focus map
+    int finish_begin()
+    {
+        if (n == 0) return fail(DM_ERR_STATE, "no frames");
+        if (finished) return fail(DM_ERR_STATE, "already finished");
+        std::vector<unsigned> st(2 * (size_t)n);
+        int rc = be.download(st.data(), d_stats, st.size() * sizeof(unsigned));
+        if (rc) return fail(rc, be.last_error());
+        unsigned mx = 0;
+        for (int i = 0; i < n; ++i) mx = st[2 * i + 1] > mx ? st[2 * i + 1] : mx;
+        memcpy(&gmax, &mx, 4);
+        if (gmax > 0.f) {
+            DmNormalize k{d_energy, h, w, gmax};
+            if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());
+        }
+        weights = d_energy;
+        if (o.smooth_size > 0) {
+            const float gc = (float)(-0.5 / (25.0 * 25.0));
+            DmBilateral k{d_energy, h, w, bil_r, d_sw, gc, 0.5f * gc * gc, d_stats, gmax, d_smooth};
+            if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());
+            weights = d_smooth;
+        }
+        DmFocusMap f{weights, h, w, n, o.map_type, (float)o.temperature};
+        if ((rc = be.launch(f, w, h, 1))) return fail(rc, be.last_error());
+        finished = 1;
+        blended = 0;
+        return DM_OK;
+    }
+
+    template <typename InT>
+    int blend_frame_t(int i)
+    {
+        int rc;
+        DmLevelSrc<InT> s0{d_frames + (size_t)i * frame_bytes, (long long)frame_pitch, nullptr,
+                           weights + (size_t)i * plane, h, w};
+        const int first = blended == 0;
+        if (L > 1) {
+            DmPyrDown<InT> d0{s0, lh[1], lw[1], gp[1]};
+            if ((rc = be.launch(d0, lw[1], lh[1], 4))) return rc;
+        }
+        for (int l = 1; l + 1 < L; ++l) {
+            DmLevelSrc<float> s{nullptr, 0, gp[l], gp[l] + 3 * (size_t)lh[l] * lw[l], lh[l], lw[l]};
+            DmPyrDown<float> d{s, lh[l + 1], lw[l + 1], gp[l + 1]};
+            if ((rc = be.launch(d, lw[l + 1], lh[l + 1], 4))) return rc;
+        }
+        {
+            DmBlendLevel<InT> b{s0, L > 1 ? gp[1] : nullptr, L > 1 ? lh[1] : 0, L > 1 ? lw[1] : 0, acc[0], first};
+            if ((rc = be.launch(b, w, h, 3))) return rc;
+        }
+        for (int l = 1; l < L; ++l) {
+            DmLevelSrc<float> s{nullptr, 0, gp[l], gp[l] + 3 * (size_t)lh[l] * lw[l], lh[l], lw[l]};
+            const bool top = l == L - 1;
+            DmBlendLevel<float> b{s, top ? nullptr : gp[l + 1], top ? 0 : lh[l + 1], top ? 0 : lw[l + 1], acc[l], first};
+            if ((rc = be.launch(b, lw[l], lh[l], 3))) return rc;
+        }
+        return DM_OK;
+    }
+
+    // replaces one iteration of the second loop of focus_stack (depth_map.py:94-115); frames in stack order
+    int blend_frame(int i)
+    {
+        if (!finished) return fail(DM_ERR_STATE, "blend before finish_begin");
+        if (i != blended || i >= n) return fail(DM_ERR_STATE, "frames must be blended once, in stack order");
+        const int rc = bps == 1 ? blend_frame_t<uint8_t>(i) : blend_frame_t<uint16_t>(i);
+        if (rc) return fail(rc, be.last_error());
+        ++blended;
+        return DM_OK;
+    }
+
+    // depth_map.py:116-123: collapse the blended pyramid, clip(|x|), truncate; out_bgr is host memory
+    int finish_end(void *out_bgr, size_t out_pitch)
+    {
+        if (!finished || blended != n) return fail(DM_ERR_STATE, "finish_end before every frame was blended");
+        int rc = 0;
+        if (!collapsed) {   // a second call only downloads the image again
+            for (int l = L - 2; l >= 0; --l) {
+                DmCollapse c{acc[l + 1], lh[l + 1], lw[l + 1], acc[l], lh[l], lw[l]};
+                if ((rc = be.launch(c, lw[l], lh[l], 3))) return fail(rc, be.last_error());
+            }
+            if (bps == 1) {
+                DmStoreOutput<uint8_t> s{acc[0], h, w, 255.f, d_out, (long long)frame_pitch};
+                rc = be.launch(s, w, h, 1);
+            } else {
+                DmStoreOutput<uint16_t> s{acc[0], h, w, 65535.f, d_out, (long long)frame_pitch};
+                rc = be.launch(s, w, h, 1);
+            }
+            if (rc) return fail(rc, be.last_error());
+            collapsed = 1;
+            be.mark_end();
+        }
+        if (out_bgr) {
+            if (out_pitch < frame_pitch) return fail(DM_ERR_INVALID_OPTION, "output row pitch smaller than a row");
+            if ((rc = be.download2d(out_bgr, out_pitch, d_out, frame_pitch, frame_pitch, h))) return fail(rc, be.last_error());
+        } else if ((rc = be.sync())) return fail(rc, be.last_error());
+        return DM_OK;
+    }
+
+    // whole chain again over the frames still resident in HBM (bench: "inputs already in HBM")
+    int rerun_resident()
+    {
+        const int frames = n;
+        if (frames == 0) return fail(DM_ERR_STATE, "no frames");
+        int rc = reset();
+        if (rc) return rc;
+        be.mark_start();
+        for (int i = 0; i < frames; ++i) {
+            rc = bps == 1 ? energy_of_frame<uint8_t>(i) : energy_of_frame<uint16_t>(i);
+            if (rc) return fail(rc, be.last_error());
+            ++n;
+        }
+        if ((rc = finish_begin())) return rc;
+        for (int i = 0; i < frames; ++i) if ((rc = blend_frame(i))) return rc;
+        return finish_end(nullptr, 0);
+    }
+
+    // test hook: what = 0 normalised energy, 1 focus map (after finish_begin), 2 raw energy (before it)
+    int get_plane(int what, int frame, float *out)
+    {
+        if (frame < 0 || frame >= n) return fail(DM_ERR_INVALID_OPTION, "frame out of range");
+        const float *src = nullptr;
+        if (what == 2 && !finished) src = d_energy;
+        else if (what == 0 && finished && weights != d_energy) src = d_energy;
+        else if (what == 1 && finished) src = weights;
+        if (!src) return fail(DM_ERR_STATE, "plane not available in this state");
+        const int rc = be.download(out, src + (size_t)frame * plane, plane * sizeof(float));
+        return rc ? fail(rc, be.last_error()) : DM_OK;
+    }
+};

@@ -1,0 +1,359 @@
+// ss_dm_kernels.cuh -- device code of the depth-map focus stacker (sm_100a), the second stack algorithm
+// behind the reference's stack-algo boundary (reference src/shinestacker/algorithms/depth_map.py:10-123).
+//
+// One body, two builds, like ss_kernels.cuh: every kernel is a small functor "one call = one output
+// pixel (x, y, z)"; nvcc instantiates dm_px_kernel<Functor> over a 2-D/3-D grid (the product), and
+// tests/emu/ runs the same functors in plain loops under g++ (-DSS_HOST_EMU) so border handling, tap
+// order and the whole launch sequence can be checked on a CPU-only box.  The emulation is test
+// infrastructure; the product never uses it.
+//
+// Arithmetic (what the reference's cv2 / numpy calls evaluate, oracle/depthmap_oracle.py):
+//   * gray        cv2.cvtColor(BGR2GRAY) on uint8/uint16: (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+//   * energy      'laplacian': |Laplacian_k(GaussianBlur_b(gray))|, 'sobel': |Sobel_x| + |Sobel_y|;
+//                 separable float32 filters in cv2's symmetric form k0*x0 + sum_j kj*(x[+j] +- x[-j]),
+//                 rows first, REFLECT101
+//   * normalise   energies / max(energies) (one global maximum over the whole stack)
+//   * smooth      cv2.bilateralFilter(e, d, 25, 25): disc of radius d/2, weight = space * colour
+//   * focus map   'average': e_i / sum_i e_i;  'max': softmax((e_i - max_i e_i) / temperature)
+//   * blend       Laplacian pyramid (cv2.pyrDown / cv2.pyrUp, [1,4,6,4,1]) of every frame, each level
+//                 multiplied by the Gaussian pyramid of its weight map, summed over frames, collapsed,
+//                 clip(|x|) and truncated to the input type.
+// Everything is float32 with explicit, unfused multiplies and adds (the library is built with
+// -fmad=false); all stages are HBM-streaming stencils except the bilateral filter (FP32-issue bound).
+#pragma once
+#include <stdint.h>
+#include "ss_kernels.cuh"
+
+#ifdef SS_HOST_EMU
+#define SS_MDEV inline            /* member functions of the pixel functors */
+#else
+#define SS_MDEV __device__ __forceinline__
+#endif
+
+#define DM_MAX_TAPS 16   /* centre + up to 15 one-sided taps: separable kernels up to 31 wide */
+
+struct DmTaps {          // one-sided view of a symmetric / anti-symmetric 1-D kernel
+    float k[DM_MAX_TAPS]; // k[0] = centre tap, k[j] = tap at distance j
+    int r;               // radius
+    int anti;            // 1: anti-symmetric (pairs are x[+j] - x[-j]), 0: symmetric (x[+j] + x[-j])
+};
+
+#ifdef SS_HOST_EMU
+SS_DEV float ss_div(float a, float b) { return a / b; }
+SS_DEV unsigned __float_as_uint_compat(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+SS_DEV float __uint_as_float_compat(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+#else
+SS_DEV float ss_div(float a, float b) { return __fdiv_rn(a, b); }
+SS_DEV unsigned __float_as_uint_compat(float f) { return __float_as_uint(f); }
+SS_DEV float __uint_as_float_compat(unsigned u) { return __uint_as_float(u); }
+#endif
+
+SS_DEV int dm_reflect101(int p, int n)
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+// cv2's small symmetric-kernel form along one axis of a float plane
+SS_DEV float dm_filter1d(const float *line, long long stride, int pos, int n, const DmTaps &t)
+{
+    float acc = ss_mul(line[(long long)pos * stride], t.k[0]);
+    for (int j = 1; j <= t.r; ++j) {
+        const float a = line[(long long)dm_reflect101(pos + j, n) * stride];
+        const float b = line[(long long)dm_reflect101(pos - j, n) * stride];
+        const float pair = t.anti ? ss_add(a, -b) : ss_add(a, b);
+        acc = ss_add(acc, ss_mul(pair, t.k[j]));
+    }
+    return acc;
+}
+
+template <typename InT>
+SS_DEV float dm_gray_at(const void *frame, long long pitch, int x, int y)
+{
+    const InT *s = (const InT *)((const char *)frame + (long long)y * pitch) + 3 * x;
+    const uint32_t v = (uint32_t)s[0] * 3735u + (uint32_t)s[1] * 19235u + (uint32_t)s[2] * 9798u + 16384u;
+    return (float)(v >> 15);
+}
+
+// ---- pass 1, per frame: gray -> (blur) -> derivative filters -> |.| energy + statistics -----------------
+// A: row pass of the Gaussian blur straight from the integer BGR frame (gray computed per tap); with
+//    r == 0 taps {1} it just writes the gray plane (Sobel energy needs no blur).
+template <typename InT>
+struct DmGrayRowFilter {
+    const void *frame; long long pitch; int h, w; DmTaps t; float *out;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        float acc = ss_mul(dm_gray_at<InT>(frame, pitch, x, y), t.k[0]);
+        for (int j = 1; j <= t.r; ++j) {
+            const float a = dm_gray_at<InT>(frame, pitch, dm_reflect101(x + j, w), y);
+            const float b = dm_gray_at<InT>(frame, pitch, dm_reflect101(x - j, w), y);
+            acc = ss_add(acc, ss_mul(ss_add(a, b), t.k[j]));
+        }
+        out[(long long)y * w + x] = acc;
+    }
+};
+
+// B: column pass of a separable filter
+struct DmColFilter {
+    const float *in; int h, w; DmTaps t; float *out;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        out[(long long)y * w + x] = dm_filter1d(in + x, w, y, h, t);
+    }
+};
+
+// C: the two row passes of the derivative pair (Laplacian: kd | ks, Sobel: [-1,0,1] | [1,2,1])
+struct DmRowPair {
+    const float *in; int h, w; DmTaps ta, tb; float *out_a, *out_b;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        const float *line = in + (long long)y * w;
+        out_a[(long long)y * w + x] = dm_filter1d(line, 1, x, w, ta);
+        out_b[(long long)y * w + x] = dm_filter1d(line, 1, x, w, tb);
+    }
+};
+
+// per-frame minimum / maximum of the (non-negative) energies as IEEE bit patterns: stats[0] = min, [1] = max
+SS_DEV void dm_stats_update(unsigned *stats, float e)
+{
+    const unsigned bits = __float_as_uint_compat(e);
+#ifdef SS_HOST_EMU
+    if (bits < stats[0]) stats[0] = bits;
+    if (bits > stats[1]) stats[1] = bits;
+#else
+    const unsigned m = __activemask();
+    const unsigned lo = __reduce_min_sync(m, bits), hi = __reduce_max_sync(m, bits);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+        atomicMin(stats, lo);
+        atomicMax(stats + 1, hi);
+    }
+#endif
+}
+
+// D: column passes + combination.  Laplacian: |col_b(a) + col_a(b)| (cv2.Laplacian = d2/dx2 + d2/dy2,
+//    depth_map.py:40); Sobel: |col_b(a)| + |col_a(b)| (depth_map.py:32-33).  Energy of -0 is +0.
+struct DmColCombine {
+    const float *in_a, *in_b; int h, w; DmTaps ta, tb; int sobel; float *out; unsigned *stats;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        const float da = dm_filter1d(in_a + x, w, y, h, tb);   // rows filtered with ta, columns with tb
+        const float db = dm_filter1d(in_b + x, w, y, h, ta);
+        const float e = sobel ? ss_add(fabsf(da), fabsf(db)) : fabsf(ss_add(da, db));
+        out[(long long)y * w + x] = e;
+        dm_stats_update(stats, e);
+    }
+};
+
+// ---- after the last frame ---------------------------------------------------------------------------------
+// energies / max_energy over the whole stack (depth_map.py:88-90); z = frame
+struct DmNormalize {
+    float *e; int h, w; float gmax;
+    SS_MDEV void operator()(int x, int y, int z) const
+    {
+        float *p = e + ((long long)z * h + y) * w + x;
+        *p = ss_div(*p, gmax);
+    }
+};
+
+// cv2.bilateralFilter(e, d, 25, 25) (smooth_energy, depth_map.py:43-51).  sw holds the (2r+1)^2 space
+// weights, 0 outside the disc.  Normalised energies lie in [0, 1], so the colour exponent
+// t = -(v - v0)^2 / (2*25^2) is in [-8e-4, 0] and exp(t) = 1 + t + t^2/2 to 1e-10 -- three full-rate FP32
+// operations instead of cv2's 4096-bin interpolated table or a MUFU.  `flat` frames (max - min < FLT_EPSILON)
+// are copied, as cv2 does.
+struct DmBilateral {
+    const float *in; int h, w; int r; const float *sw; float c1, c2; const unsigned *stats; float gmax;
+    float *out;
+    SS_MDEV void operator()(int x, int y, int z) const
+    {
+        const long long plane = (long long)h * w;
+        const float *src = in + (long long)z * plane;
+        const float v0 = src[(long long)y * w + x];
+        float mn = __uint_as_float_compat(stats[2 * z]), mx = __uint_as_float_compat(stats[2 * z + 1]);
+        if (gmax > 0.f) { mn = ss_div(mn, gmax); mx = ss_div(mx, gmax); }
+        if (fabsf(mn - mx) < 1.1920929e-07f) { out[(long long)z * plane + (long long)y * w + x] = v0; return; }
+        float num = 0.f, den = 0.f;
+        const int d = 2 * r + 1;
+        if (x >= r && x < w - r && y >= r && y < h - r) {
+            const float *row = src + (long long)(y - r) * w + (x - r);
+            for (int i = 0; i < d; ++i, row += w) {
+#pragma unroll 5
+                for (int j = 0; j < d; ++j) {
+                    const float s = sw[i * d + j];
+                    if (s == 0.f) continue;
+                    const float v = row[j];
+                    const float dv = ss_add(v, -v0);
+                    const float q = ss_mul(dv, dv);
+                    const float wgt = ss_mul(s, ss_fma(q, ss_fma(q, c2, c1), 1.f));
+                    num = ss_fma(v, wgt, num);
+                    den = ss_add(den, wgt);
+                }
+            }
+        } else {
+            for (int i = 0; i < d; ++i) {
+                const float *row = src + (long long)dm_reflect101(y - r + i, h) * w;
+                for (int j = 0; j < d; ++j) {
+                    const float s = sw[i * d + j];
+                    if (s == 0.f) continue;
+                    const float v = row[dm_reflect101(x - r + j, w)];
+                    const float dv = ss_add(v, -v0);
+                    const float q = ss_mul(dv, dv);
+                    const float wgt = ss_mul(s, ss_fma(q, ss_fma(q, c2, c1), 1.f));
+                    num = ss_fma(v, wgt, num);
+                    den = ss_add(den, wgt);
+                }
+            }
+        }
+        out[(long long)z * plane + (long long)y * w + x] = ss_div(num, den);
+    }
+};
+
+// get_focus_map (depth_map.py:53-62), in place over the n planes of e; frames summed in stack order.
+struct DmFocusMap {
+    float *e; int h, w; int n; int softmax; float temperature;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        const long long plane = (long long)h * w;
+        float *p = e + (long long)y * w + x;
+        if (!softmax) {
+            float s = p[0];
+            for (int i = 1; i < n; ++i) s = ss_add(s, p[(long long)i * plane]);
+            for (int i = 0; i < n; ++i) {
+                float *q = p + (long long)i * plane;
+                *q = s != 0.f ? ss_div(*q, s) : 0.f;
+            }
+        } else {
+            float m = p[0];
+            for (int i = 1; i < n; ++i) m = fmaxf(m, p[(long long)i * plane]);
+            float s = 0.f;
+            for (int i = 0; i < n; ++i) {
+                float *q = p + (long long)i * plane;
+                const float rel = expf(ss_div(ss_add(*q, -m), temperature));
+                *q = rel;
+                s = i ? ss_add(s, rel) : rel;
+            }
+            for (int i = 0; i < n; ++i) {
+                float *q = p + (long long)i * plane;
+                *q = ss_div(*q, s);
+            }
+        }
+    }
+};
+
+// ---- pass 2, per frame: Gaussian pyramids of the image and of its weight map, Laplacian blend -----------
+// Source of one pyramid level: planes 0..2 = B, G, R (level 0: the interleaved integer frame, converted
+// on the fly = img.astype(float32), depth_map.py:96; deeper levels: float planes), plane 3 = weight map.
+template <typename InT>
+struct DmLevelSrc {
+    const void *frame; long long pitch;       // level 0 image (InT != float)
+    const float *planes; const float *weight; // float planes (3, contiguous) / weight plane
+    int h, w;
+    SS_MDEV float at(int c, int x, int y) const
+    {
+        if (c == 3) return weight[(long long)y * w + x];
+        if (frame) return (float)((const InT *)((const char *)frame + (long long)y * pitch))[3 * x + c];
+        return planes[((long long)c * h + y) * w + x];
+    }
+};
+
+// cv2.pyrDown (depth_map.py:101-102): row = 6*s[2x] + 4*(s[2x-1] + s[2x+1]) + s[2x-2] + s[2x+2] on five
+// source rows (REFLECT101), then the same vertically, * 1/256.  z = plane (0..2 image, 3 weight).
+template <typename InT>
+struct DmPyrDown {
+    DmLevelSrc<InT> src; int h2, w2; float *out /* 4 planes h2 x w2 */;
+    SS_MDEV float row(int c, int x2, int yy) const
+    {
+        const int w = src.w, x = 2 * x2;
+        const float c0 = src.at(c, x, yy);
+        const float s1 = ss_add(src.at(c, dm_reflect101(x - 1, w), yy), src.at(c, dm_reflect101(x + 1, w), yy));
+        float acc = ss_add(ss_mul(c0, 6.f), ss_mul(s1, 4.f));
+        acc = ss_add(acc, src.at(c, dm_reflect101(x - 2, w), yy));
+        return ss_add(acc, src.at(c, dm_reflect101(x + 2, w), yy));
+    }
+    SS_MDEV void operator()(int x2, int y2, int c) const
+    {
+        const int h = src.h, y = 2 * y2;
+        const float r2 = row(c, x2, y);
+        const float r13 = ss_add(row(c, x2, dm_reflect101(y - 1, h)), row(c, x2, dm_reflect101(y + 1, h)));
+        float acc = ss_add(ss_mul(r2, 6.f), ss_mul(r13, 4.f));
+        acc = ss_add(acc, row(c, x2, dm_reflect101(y - 2, h)));
+        acc = ss_add(acc, row(c, x2, dm_reflect101(y + 2, h)));
+        out[((long long)c * h2 + y2) * w2 + x2] = ss_mul(acc, 0.00390625f);
+    }
+};
+
+// cv2.pyrUp(src, dstsize) (depth_map.py:106, :120) at destination pixel (x, y) of one coarse float plane
+// h2 x w2: even columns l + 6c + r, odd columns 4(c + r); coarse index -1 -> 1, n -> n - 1; then the same
+// vertically, * 1/64.
+SS_DEV float dm_pyrup_row(const float *line, int w2, int x)
+{
+    const int xc = x >> 1;
+    const float c = line[xc];
+    const float r = line[xc + 1 < w2 ? xc + 1 : w2 - 1];
+    if (x & 1) return ss_mul(ss_add(c, r), 4.f);
+    const float l = line[xc > 0 ? xc - 1 : (w2 > 1 ? 1 : 0)];
+    return ss_add(ss_add(l, ss_mul(c, 6.f)), r);
+}
+SS_DEV float dm_pyrup_at(const float *coarse, int h2, int w2, int x, int y)
+{
+    const int yc = y >> 1;
+    const float *lc = coarse + (long long)yc * w2;
+    const float *ld = coarse + (long long)(yc + 1 < h2 ? yc + 1 : h2 - 1) * w2;
+    const float c = dm_pyrup_row(lc, w2, x), d = dm_pyrup_row(ld, w2, x);
+    if (y & 1) return ss_mul(ss_mul(ss_add(c, d), 4.f), 0.015625f);
+    const float *lu = coarse + (long long)(yc > 0 ? yc - 1 : (h2 > 1 ? 1 : 0)) * w2;
+    const float u = dm_pyrup_row(lu, w2, x);
+    return ss_mul(ss_add(ss_add(u, ss_mul(c, 6.f)), d), 0.015625f);
+}
+
+// One level of the frame's weighted Laplacian pyramid added to the running blend (depth_map.py:104-111):
+// acc[c] (+)= (g_l[c] - pyrUp(g_{l+1}[c])) * w_l, or g_l[c] * w_l at the coarsest level (coarse == NULL).
+// The first frame stores instead of adding.  z = channel.
+template <typename InT>
+struct DmBlendLevel {
+    DmLevelSrc<InT> fine; const float *coarse /* 4 planes h2 x w2 or NULL */; int h2, w2;
+    float *acc /* 3 planes */; int first;
+    SS_MDEV void operator()(int x, int y, int c) const
+    {
+        float v = fine.at(c, x, y);
+        if (coarse) v = ss_add(v, -dm_pyrup_at(coarse + (long long)c * h2 * w2, h2, w2, x, y));
+        v = ss_mul(v, fine.at(3, x, y));
+        float *a = acc + ((long long)c * fine.h + y) * fine.w + x;
+        *a = first ? v : ss_add(*a, v);
+    }
+};
+
+// One collapse step (depth_map.py:118-120): fine[c] = pyrUp(coarse[c]) + fine[c], in place.  z = channel.
+struct DmCollapse {
+    const float *coarse; int h2, w2; float *fine; int h, w;
+    SS_MDEV void operator()(int x, int y, int c) const
+    {
+        float *a = fine + ((long long)c * h + y) * w + x;
+        *a = ss_add(dm_pyrup_at(coarse + (long long)c * h2 * w2, h2, w2, x, y), *a);
+    }
+};
+
+// np.clip(np.absolute(result), 0, n_values).astype(dtype) (depth_map.py:121-123) into interleaved BGR.
+template <typename OutT>
+struct DmStoreOutput {
+    const float *res /* 3 planes */; int h, w; float maxv; void *out; long long pitch;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        OutT *o = (OutT *)((char *)out + (long long)y * pitch) + 3 * x;
+        for (int c = 0; c < 3; ++c) {
+            float v = fabsf(res[((long long)c * h + y) * w + x]);
+            v = v > maxv ? maxv : v;
+            o[c] = (OutT)(int)v;
+        }
+    }
+};
+
+#ifndef SS_HOST_EMU
+template <class K>
+__global__ void __launch_bounds__(256) dm_px_kernel(const __grid_constant__ K k, int w, int h)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < w && y < h) k(x, y, (int)blockIdx.z);
+}
+#endif

@@ -1,0 +1,192 @@
+// ss_dm_lib.cuh -- CUDA backend of DmEngine + the ssdm_* C ABI (include/shinestack_b200_depthmap.h).
+// Included at the end of ss_lib.cu (shares its error plumbing); sm_100a only, no CPU fallback.
+#pragma once
+#include "../../include/shinestack_b200_depthmap.h"
+#include "ss_dm_engine.h"
+
+struct DmCudaBackend {
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_copied = nullptr, ev_start = nullptr, ev_end = nullptr;
+    bool started = false, ended = false;
+    long long launches = 0;
+    char msg[256] = "";
+
+    int cuda_fail(cudaError_t e, const char *what)
+    {
+        snprintf(msg, sizeof(msg), "%s failed: %s", what, cudaGetErrorString(e));
+        return DM_ERR_CUDA;
+    }
+#define DM_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+    const char *last_error() const { return msg; }
+    int init()
+    {
+        DM_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        DM_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        DM_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
+        DM_CUDA(cudaEventCreate(&ev_start));
+        DM_CUDA(cudaEventCreate(&ev_end));
+        return 0;
+    }
+    void shutdown()
+    {
+        if (s_copy) cudaStreamDestroy(s_copy);
+        if (s_comp) cudaStreamDestroy(s_comp);
+        if (ev_copied) cudaEventDestroy(ev_copied);
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (ev_end) cudaEventDestroy(ev_end);
+    }
+    int alloc(void **p, size_t bytes)
+    {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+        if (e != cudaSuccess) { *p = nullptr; snprintf(msg, sizeof(msg), "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return DM_ERR_NOMEM; }
+        return 0;
+    }
+    void free(void *p) { cudaFree(p); }
+    int sync()
+    {
+        DM_CUDA(cudaStreamSynchronize(s_copy));
+        DM_CUDA(cudaStreamSynchronize(s_comp));
+        return 0;
+    }
+    int sync_copies() { DM_CUDA(cudaStreamSynchronize(s_copy)); return 0; }
+    void reset_counters() { launches = 0; started = ended = false; }
+    void mark_start() { if (!started) { cudaEventRecord(ev_start, s_comp); started = true; ended = false; } }
+    void mark_end() { cudaEventRecord(ev_end, s_comp); ended = true; }
+    int upload_small(void *dst, const void *src, size_t bytes)
+    {
+        DM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s_comp));
+        DM_CUDA(cudaStreamSynchronize(s_comp));
+        return 0;
+    }
+    // frame -> resident store: host frames go through the copy stream (overlaps the kernels of earlier
+    // frames), the compute stream waits for the copy; device frames are copied on the compute stream
+    int upload_frame(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows, int on_device)
+    {
+        if (on_device) {
+            DM_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, cudaMemcpyDeviceToDevice, s_comp));
+            return 0;
+        }
+        DM_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, cudaMemcpyHostToDevice, s_copy));
+        DM_CUDA(cudaEventRecord(ev_copied, s_copy));
+        DM_CUDA(cudaStreamWaitEvent(s_comp, ev_copied, 0));
+        return 0;
+    }
+    int download(void *dst, const void *src, size_t bytes)
+    {
+        DM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s_comp));
+        DM_CUDA(cudaStreamSynchronize(s_comp));
+        return 0;
+    }
+    int download2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows)
+    {
+        DM_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, cudaMemcpyDeviceToHost, s_comp));
+        DM_CUDA(cudaStreamSynchronize(s_comp));
+        return 0;
+    }
+    template <class K>
+    int launch(const K &k, int w, int h, int z)
+    {
+        const dim3 grid((w + 31) / 32, (h + 7) / 8, z);
+        dm_px_kernel<K><<<grid, 256, 0, s_comp>>>(k, w, h);
+        DM_CUDA(cudaGetLastError());
+        ++launches;
+        return 0;
+    }
+    int elapsed_ms(float *ms)
+    {
+        *ms = 0.f;
+        if (!started || !ended) return 0;
+        DM_CUDA(cudaEventSynchronize(ev_end));
+        DM_CUDA(cudaEventElapsedTime(ms, ev_start, ev_end));
+        return 0;
+    }
+};
+
+struct ssdm_handle {
+    DmEngine<DmCudaBackend> eng;
+    int device = 0;
+};
+
+#define SSDM_ENTER(h)                                                       \
+    if (!(h)) return ss_fail(SS_ERR_STATE, "null handle");                  \
+    SS_CUDA(cudaSetDevice((h)->device))
+#define SSDM_RET(h, rc) do { const int rc_ = (rc); return rc_ ? ss_fail(rc_, "%s", (h)->eng.err) : SS_OK; } while (0)
+
+SS_EXPORT int ssdm_create(const ssdm_config *cfg, ssdm_handle **out)
+{
+    if (!cfg || !out) return ss_fail(SS_ERR_INVALID_OPTION, "null argument");
+    *out = nullptr;
+    if (cfg->float_bits != 32)
+        return ss_fail(SS_ERR_INVALID_OPTION, "float_type: the device depth-map path implements float-32 only");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
+        return ss_fail(SS_ERR_NO_DEVICE, "no CUDA device %d (this library has no CPU fallback)", cfg->device);
+    cudaDeviceProp prop;
+    SS_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return ss_fail(SS_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                       prop.major, prop.minor);
+    SS_CUDA(cudaSetDevice(cfg->device));
+    ssdm_handle *h = new (std::nothrow) ssdm_handle();
+    if (!h) return ss_fail(SS_ERR_NOMEM, "out of host memory");
+    h->device = cfg->device;
+    int rc = h->eng.be.init();
+    if (rc) { ss_fail(rc, "%s", h->eng.be.last_error()); h->eng.be.shutdown(); delete h; return rc; }
+    DmOptions o;
+    o.width = cfg->width; o.height = cfg->height; o.bytes_per_sample = cfg->bytes_per_sample;
+    o.map_type = cfg->map_type; o.energy = cfg->energy; o.kernel_size = cfg->kernel_size;
+    o.blur_size = cfg->blur_size; o.smooth_size = cfg->smooth_size; o.temperature = cfg->temperature;
+    o.levels = cfg->levels; o.max_frames = cfg->max_frames;
+    rc = h->eng.create(o);
+    if (rc) {
+        ss_fail(rc, "%s", h->eng.err);
+        h->eng.destroy(); h->eng.be.shutdown(); delete h;
+        return rc;
+    }
+    *out = h;
+    return SS_OK;
+}
+
+SS_EXPORT void ssdm_destroy(ssdm_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->eng.destroy();
+    h->eng.be.shutdown();
+    delete h;
+}
+
+SS_EXPORT int ssdm_reset(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.reset()); }
+SS_EXPORT int ssdm_push_frame(ssdm_handle *h, const void *bgr, size_t pitch) { SSDM_ENTER(h); SSDM_RET(h, h->eng.push_frame(bgr, pitch, 0)); }
+SS_EXPORT int ssdm_push_frame_device(ssdm_handle *h, const void *d_bgr, size_t pitch) { SSDM_ENTER(h); SSDM_RET(h, h->eng.push_frame(d_bgr, pitch, 1)); }
+SS_EXPORT int ssdm_sync_copies(ssdm_handle *h)
+{
+    SSDM_ENTER(h);
+    const int rc = h->eng.be.sync_copies();
+    return rc ? ss_fail(rc, "%s", h->eng.be.last_error()) : SS_OK;
+}
+SS_EXPORT int ssdm_finish_begin(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.finish_begin()); }
+SS_EXPORT int ssdm_blend_frame(ssdm_handle *h, int frame) { SSDM_ENTER(h); SSDM_RET(h, h->eng.blend_frame(frame)); }
+SS_EXPORT int ssdm_finish_end(ssdm_handle *h, void *out_bgr, size_t pitch) { SSDM_ENTER(h); SSDM_RET(h, h->eng.finish_end(out_bgr, pitch)); }
+SS_EXPORT int ssdm_finish(ssdm_handle *h, void *out_bgr, size_t pitch)
+{
+    SSDM_ENTER(h);
+    int rc = h->eng.finish_begin();
+    for (int i = 0; !rc && i < h->eng.n; ++i) rc = h->eng.blend_frame(i);
+    if (!rc) rc = h->eng.finish_end(out_bgr, pitch);
+    SSDM_RET(h, rc);
+}
+SS_EXPORT int ssdm_rerun_resident(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.rerun_resident()); }
+SS_EXPORT int ssdm_get_plane(ssdm_handle *h, int what, int frame, float *out) { SSDM_ENTER(h); SSDM_RET(h, h->eng.get_plane(what, frame, out)); }
+SS_EXPORT int ssdm_kernel_time_ms(ssdm_handle *h, float *ms)
+{
+    SSDM_ENTER(h);
+    const int rc = h->eng.be.elapsed_ms(ms);
+    return rc ? ss_fail(rc, "%s", h->eng.be.last_error()) : SS_OK;
+}
+SS_EXPORT int ssdm_launch_count(ssdm_handle *h, int64_t *launches)
+{
+    if (!h || !launches) return ss_fail(SS_ERR_STATE, "null argument");
+    *launches = h->eng.be.launches;
+    return SS_OK;
+}

@@ -1537,3 +1537,5 @@ SS_EXPORT int ss_test_collapse_step(const float *img_planes, int h2, int w2, con
     cudaFree(d_img); cudaFree(d_lay); cudaFree(d_out);
     return 0;
 }
+
+#include "ss_dm_lib.cuh"

@@ -1,0 +1,63 @@
+// CPU emulation of the depth-map stacker (TEST INFRASTRUCTURE ONLY): compiles the product's pixel functors
+// (shinestacker_b200/csrc/ss_dm_kernels.cuh) and its launch sequence (ss_dm_engine.h) with g++ against a
+// host backend that runs every "kernel" as plain loops, so tap order, border handling, state machine and
+// buffer plumbing can be checked against the oracle and the golden vectors on a CPU-only box.
+// Build: g++ -O1 -ffp-contract=off -DSS_HOST_EMU -shared -fPIC
+#define SS_HOST_EMU 1
+#include <stdlib.h>
+#include "../../shinestacker_b200/csrc/ss_dm_engine.h"
+
+struct DmHostBackend {
+    long long launches = 0;
+    const char *last_error() const { return "host backend"; }
+    int alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); if (*p) memset(*p, 0xff, bytes); return *p ? 0 : DM_ERR_NOMEM; }
+    void free(void *p) { ::free(p); }
+    int sync() { return 0; }
+    void reset_counters() { launches = 0; }
+    void mark_start() {}
+    void mark_end() {}
+    int upload_small(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+    int upload_frame(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows, int)
+    {
+        for (int y = 0; y < rows; ++y) memcpy((char *)dst + y * dpitch, (const char *)src + y * spitch, row_bytes);
+        return 0;
+    }
+    int download(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+    int download2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows)
+    {
+        for (int y = 0; y < rows; ++y) memcpy((char *)dst + y * dpitch, (const char *)src + y * spitch, row_bytes);
+        return 0;
+    }
+    template <class K>
+    int launch(const K &k, int w, int h, int z)
+    {
+        for (int c = 0; c < z; ++c)
+            for (int y = 0; y < h; ++y)
+                for (int x = 0; x < w; ++x) k(x, y, c);
+        ++launches;
+        return 0;
+    }
+};
+
+typedef DmEngine<DmHostBackend> Emu;
+
+extern "C" {
+void *emu_dm_create(int w, int h, int bps, int map_type, int energy, int kernel_size, int blur_size, int smooth_size,
+                    double temperature, int levels, int max_frames)
+{
+    Emu *e = new Emu();
+    DmOptions o = {w, h, bps, map_type, energy, kernel_size, blur_size, smooth_size, temperature, levels, max_frames};
+    if (e->create(o)) { fprintf(stderr, "emu_dm_create: %s\n", e->err); e->destroy(); delete e; return nullptr; }
+    return e;
+}
+void emu_dm_destroy(void *p) { Emu *e = (Emu *)p; e->destroy(); delete e; }
+int emu_dm_reset(void *p) { return ((Emu *)p)->reset(); }
+int emu_dm_push(void *p, const void *bgr, size_t pitch) { return ((Emu *)p)->push_frame(bgr, pitch, 0); }
+int emu_dm_finish_begin(void *p) { return ((Emu *)p)->finish_begin(); }
+int emu_dm_blend(void *p, int i) { return ((Emu *)p)->blend_frame(i); }
+int emu_dm_finish_end(void *p, void *out, size_t pitch) { return ((Emu *)p)->finish_end(out, pitch); }
+int emu_dm_rerun(void *p) { return ((Emu *)p)->rerun_resident(); }
+int emu_dm_get_plane(void *p, int what, int frame, float *out) { return ((Emu *)p)->get_plane(what, frame, out); }
+const char *emu_dm_error(void *p) { return ((Emu *)p)->err; }
+long long emu_dm_launches(void *p) { return ((Emu *)p)->be.launches; }
+}

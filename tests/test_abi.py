@@ -14,10 +14,10 @@ from shinestacker_b200 import PyramidStack, InvalidOptionError, NativeLibraryErr
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "shinestack_b200.h")).read()
+def _declared_symbols(header="shinestack_b200.h", prefix="ss_"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -28,6 +28,22 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     # and the ctypes prototypes cover the header
     assert set(names) == set(_native.SIGNATURES), set(names) ^ set(_native.SIGNATURES)
+
+
+def test_library_exports_every_depthmap_symbol():
+    lib = _native.load()
+    names = _declared_symbols("shinestack_b200_depthmap.h", "ssdm_")
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(_native.SIGNATURES_DEPTHMAP), set(names) ^ set(_native.SIGNATURES_DEPTHMAP)
+    assert ctypes.sizeof(_native.SsdmConfig) == 72
+    # option errors come back as status codes + message, never as a crash
+    cfg = _native.SsdmConfig(width=64, height=64, bytes_per_sample=1, kernel_size=5, blur_size=5, smooth_size=15,
+                             temperature=0.1, levels=3, float_bits=64, device=0, max_frames=2)
+    h = ctypes.c_void_p()
+    assert lib.ssdm_create(ctypes.byref(cfg), ctypes.byref(h)) == _native.SS_ERR_INVALID_OPTION
+    assert b"float" in lib.ss_last_error()
 
 
 def test_version_and_config_layout():

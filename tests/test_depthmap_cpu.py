@@ -1,0 +1,160 @@
+"""CPU tests of the depth-map path: the numpy oracle against the golden
+vectors of the live reference and -- when cv2 / the reference tree are present -- against cv2's primitives
+and the unmodified reference itself; the product's kernels + launch sequence, compiled for the host
+(tests/emu/emu_depthmap.cpp), against the oracle and the golden vectors; the host mirror's constructor /
+option contract.  Nothing here needs a GPU."""
+import numpy as np
+import pytest
+
+import depthmap_util as du
+from oracle import depthmap_oracle as dmo
+from oracle import ref_harness
+from shinestacker_b200 import DepthMapStack, InvalidOptionError, NativeLibraryError, synthetic, _native
+
+needs_reference = pytest.mark.skipif(not ref_harness.reference_available(),
+                                     reason="reference tree not present on this box")
+
+
+@pytest.mark.parametrize("name", du.case_names())
+def test_oracle_matches_golden(name):
+    frames, kwargs, expect = du.load_case(name)
+    out, st = dmo.focus_stack(frames, return_stages=True, **kwargs)
+    du.assert_within_1lsb(out, expect["fused"], name)
+    assert np.abs(st["weights"][0] - expect["weights0"]).max() < 2e-3   # float16 fixture
+
+
+@pytest.mark.parametrize("name", du.case_names())
+def test_kernels_on_host_match_golden_and_oracle(name):
+    frames, kwargs, expect = du.load_case(name)
+    st = {}
+    out = du.emu_focus_stack(frames, stages=st, **kwargs)
+    du.assert_within_1lsb(out, expect["fused"], name + " vs reference")
+    ref, ost = dmo.focus_stack(frames, return_stages=True, **kwargs)
+    du.assert_within_1lsb(out, ref, name + " vs oracle")
+    # the energy stage follows the oracle's operation order exactly; the focus maps agree to float32 rounding
+    assert np.array_equal(st["energy"], ost["energy"])
+    assert np.abs(st["weights"] - ost["weights"]).max() < 2e-6
+
+
+def test_cv2_primitives_match_the_restatement():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for dt, mx in ((np.uint8, 256), (np.uint16, 65536)):
+        img = rng.integers(0, mx, (41, 67, 3)).astype(dt)
+        assert np.array_equal(dmo.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    g = rng.integers(0, 256, (53, 70)).astype(np.float32)
+    for ks in (3, 5, 7, 9):
+        assert np.array_equal(dmo.gaussian_blur(g, ks), cv2.GaussianBlur(g, (ks, ks), 0))
+    assert np.allclose(dmo.gaussian_blur(g, 13), cv2.GaussianBlur(g, (13, 13), 0), rtol=1e-6, atol=1e-4)
+    bl = cv2.GaussianBlur(g, (5, 5), 0)
+    for ks in (5, 7, 9):
+        kd, ksm = cv2.getDerivKernels(2, 0, ks)
+        a, b = dmo.deriv_kernels(ks)
+        assert np.array_equal(kd.ravel(), a) and np.array_equal(ksm.ravel(), b)
+        assert np.array_equal(dmo.laplacian(bl, ks), cv2.Laplacian(bl, cv2.CV_64F, ksize=ks))  # exact for u8 data
+    sob = np.abs(cv2.Sobel(g, cv2.CV_64F, 1, 0, ksize=3)) + np.abs(cv2.Sobel(g, cv2.CV_64F, 0, 1, ksize=3))
+    assert np.array_equal(dmo.sobel_abs_sum(g), sob)
+    e = (rng.random((60, 83)) ** 4).astype(np.float32)
+    for d in (15, 5, 8):
+        assert np.abs(dmo.bilateral(e, d) - cv2.bilateralFilter(e, d, 25, 25)).max() < 3e-7
+    flat = np.full((20, 30), 0.25, np.float32)
+    assert np.array_equal(dmo.bilateral(flat, 15), cv2.bilateralFilter(flat, 15, 25, 25))
+    a = (rng.random((37, 53)) * 65535).astype(np.float32)
+    assert np.allclose(dmo.pyr_down(a), cv2.pyrDown(a), rtol=4e-7, atol=0)
+    small = dmo.pyr_down(a)
+    for dh, dw in ((37, 53), (38, 54), (38, 53)):
+        assert np.allclose(dmo.pyr_up(small, dh, dw), cv2.pyrUp(small, dstsize=(dw, dh)), rtol=4e-7, atol=0)
+
+
+@needs_reference
+@pytest.mark.parametrize("n,h,w,dtype,seed,kwargs", [
+    (3, 96, 130, np.uint8, 51, {}),
+    (2, 75, 101, np.uint16, 52, {"map_type": "max", "levels": 2}),
+    (4, 64, 80, np.uint8, 53, {"energy": "sobel", "smooth_size": 7}),
+    (3, 70, 70, np.uint16, 54, {"smooth_size": 0, "kernel_size": 7, "blur_size": 11}),
+])
+def test_oracle_matches_live_reference(n, h, w, dtype, seed, kwargs):
+    frames = synthetic.make_noise_stack(n, h, w, np.dtype(dtype), seed)
+    ref, rec = ref_harness.reference_depthmap_arrays(frames, **kwargs)
+    out, st = dmo.focus_stack(frames, return_stages=True, **kwargs)
+    du.assert_within_1lsb(out, ref, "oracle vs live reference")
+    # 16-bit stacks: the float32 Laplacian itself carries rounding noise of ~1e-7 of the LARGEST energy, which
+    # shows up in the focus map of low-energy pixels
+    assert np.abs(rec["weights"] - st["weights"]).max() < (2e-6 if dtype == np.uint8 else 1e-4)
+    if "normalized" in rec:
+        # u16 stacks: cv2's SIMD Laplacian rounds in a different order (absolute, not relative, agreement)
+        assert np.abs(rec["normalized"] - st["energy"] / st["energy"].max()).max() < 2e-6
+
+
+def test_reference_rejects_small_laplacian_kernels_and_so_do_we():
+    # cv2.Laplacian(float32 -> CV_64F, ksize <= 3) raises inside the reference; the oracle and the engine refuse it too
+    with pytest.raises(ValueError):
+        dmo.laplacian(np.zeros((8, 8), np.float32), 3)
+    with pytest.raises(ValueError):
+        du.Emu(32, 32, np.uint8, 2, kernel_size=3)
+    for bad in (dict(blur_size=4), dict(levels=0), dict(kernel_size=6), dict(smooth_size=200)):
+        with pytest.raises(ValueError):
+            du.Emu(32, 32, np.uint8, 2, **bad)
+
+
+def test_engine_state_machine_and_reuse():
+    frames = synthetic.make_noise_stack(3, 40, 56, np.uint8, 61)
+    e = du.Emu(40, 56, np.uint8, 3)
+    lib = e.lib_
+    assert lib.emu_dm_finish_begin(e.p) != 0 and "no frames" in e.error()
+    for f in frames:
+        assert e.push(f) == 0
+    assert e.push(frames[0]) != 0 and "max_frames" in e.error()
+    assert lib.emu_dm_blend(e.p, 0) != 0                      # before finish_begin
+    assert lib.emu_dm_finish_begin(e.p) == 0
+    assert e.push(frames[0]) != 0                             # after finish
+    assert lib.emu_dm_blend(e.p, 1) != 0                      # out of order
+    out = np.empty((40, 56, 3), np.uint8)
+    assert lib.emu_dm_finish_end(e.p, out.ctypes.data, out.strides[0]) != 0   # not every frame blended
+    for i in range(3):
+        assert lib.emu_dm_blend(e.p, i) == 0
+    assert lib.emu_dm_finish_end(e.p, out.ctypes.data, out.strides[0]) == 0
+    first = out.copy()
+    # whole chain again over the resident frames (bench path), then a different, shorter stack on the same handle
+    assert lib.emu_dm_rerun(e.p) == 0
+    assert lib.emu_dm_launches(e.p) == 3 * 4 + 3 + 3 * 5 + 3
+    out2 = np.empty_like(out)
+    assert lib.emu_dm_finish_end(e.p, out2.ctypes.data, out2.strides[0]) == 0  # second call: download only
+    assert np.array_equal(out2, first)
+    e.close()
+    e = du.Emu(40, 56, np.uint8, 3)
+    for f in frames[::-1][:2]:
+        assert e.push(f) == 0
+    other = e.finish()
+    assert lib.emu_dm_reset(e.p) == 0
+    e.n = 0
+    for f in frames:
+        assert e.push(f) == 0
+    again = e.finish()
+    assert np.array_equal(again, first) and not np.array_equal(other, first)
+    e.close()
+
+
+def test_identical_frames_reproduce_the_input():
+    # weights sum to one and the Laplacian pyramid telescopes: a stack of identical frames fuses to that frame
+    img = synthetic.make_noise_stack(1, 90, 123, np.uint16, 62)[0]
+    out = du.emu_focus_stack([img] * 4)
+    du.assert_within_1lsb(out, img, "identical frames", max_frac=0.5)
+
+
+def test_host_mirror_contract():
+    a = DepthMapStack()
+    assert a.name() == "depth map" and a.steps_per_frame() == 2 and a.float_type is np.float32
+    assert (a.map_type, a.energy, a.kernel_size, a.blur_size, a.smooth_size, a.temperature, a.levels) == \
+        ("average", "laplacian", 5, 5, 15, 0.1, 3)
+    with pytest.raises(InvalidOptionError):
+        DepthMapStack(float_type="float-16")
+    frames = [np.zeros((32, 32, 3), np.uint8)] * 2
+    # like the reference, bad energy / map_type surface when the stack runs (depth_map.py:83-87, :61-62)
+    with pytest.raises(InvalidOptionError):
+        DepthMapStack(energy="tenengrad").focus_stack_arrays(frames)
+    with pytest.raises(InvalidOptionError):
+        DepthMapStack(map_type="median").focus_stack_arrays(frames)
+    if _native.load().ss_device_count() == 0:
+        with pytest.raises(NativeLibraryError):     # no silent CPU fallback
+            DepthMapStack().focus_stack_arrays(frames)

@@ -1,0 +1,110 @@
+"""GPU parity tests of the depth-map path (through ctypes -> C ABI, include/shinestack_b200_depthmap.h):
+the CUDA kernels against the golden vectors of the live reference and against the numpy oracle.
+DepthMapStack blends with soft weights, so the contract is the fused image within 1 LSB;
+the focus energy of 8-bit stacks is integer-valued in float32 and must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import depthmap_util as du
+from oracle import depthmap_oracle as dmo
+from shinestacker_b200 import DepthMapStack, synthetic, ShapeError, RunStopException
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", du.case_names())
+def test_cuda_matches_golden(name):
+    frames, kwargs, expect = du.load_case(name)
+    algo = DepthMapStack(**kwargs)
+    out = algo.focus_stack_arrays(frames)
+    du.assert_within_1lsb(out, expect["fused"], name)
+    assert np.abs(algo.get_plane("weights", 0) - expect["weights0"]).max() < 2e-3   # float16 fixture
+    assert algo.last_launches > 0 and algo.last_kernel_ms > 0
+
+
+@pytest.mark.parametrize("n,h,w,dtype,seed,kwargs", [
+    (5, 333, 517, np.uint8, 71, {}),
+    (3, 257, 1000, np.uint16, 72, {"map_type": "max"}),
+    (4, 129, 191, np.uint8, 73, {"energy": "sobel", "levels": 5}),
+    (3, 600, 800, np.uint8, 74, {"smooth_size": 0, "levels": 4}),
+    (2, 1025, 1537, np.uint16, 75, {"kernel_size": 7, "blur_size": 7, "smooth_size": 9}),
+    (12, 96, 136, np.uint8, 76, {"map_type": "max", "temperature": 0.03}),
+])
+def test_cuda_matches_oracle(n, h, w, dtype, seed, kwargs):
+    frames = synthetic.make_noise_stack(n, h, w, np.dtype(dtype), seed)
+    algo = DepthMapStack(**kwargs)
+    out = algo.focus_stack_arrays(frames)
+    ref, st = dmo.focus_stack(frames, return_stages=True, **kwargs)
+    du.assert_within_1lsb(out, ref, "oracle")
+    wts = np.array([algo.get_plane("weights", i) for i in range(n)])
+    assert np.abs(wts - st["weights"]).max() < 5e-6
+    assert np.abs(wts.sum(axis=0) - 1).max() < 1e-5
+
+
+def test_energy_stage_is_exact_and_matches_the_host_build_of_the_kernels():
+    frames = synthetic.make_noise_stack(3, 150, 203, np.uint8, 77)
+    algo = DepthMapStack()
+    algo._ensure_handle(frames[0].shape, frames[0].dtype, 3)
+    ring = algo._staging(frames[0].nbytes, 4)
+    for i, f in enumerate(frames):
+        algo._push(i, f, ring)
+    raw = np.array([algo.get_plane("energy", i) for i in range(3)])
+    assert np.array_equal(raw, dmo.energy_maps(frames))
+    out = algo._blend_and_finish(3, frames[0].shape[:2], frames[0].dtype)
+    st = {}
+    emu = du.emu_focus_stack(frames, stages=st)
+    # same functors, same order of operations: the host build and the device must agree bit for bit
+    assert np.array_equal(out, emu)
+    assert np.array_equal(np.array([algo.get_plane("weights", i) for i in range(3)]), st["weights"])
+
+
+def test_handle_reuse_and_rerun():
+    a = synthetic.make_noise_stack(4, 120, 160, np.uint8, 78)
+    b = synthetic.make_noise_stack(3, 120, 160, np.uint8, 79)
+    algo = DepthMapStack()
+    out_a = algo.focus_stack_arrays(a)
+    out_b = algo.focus_stack_arrays(b)          # FocusStackBunch reuses one stack_algo (stack.py:94-97)
+    assert np.array_equal(algo.focus_stack_arrays(a), out_a)
+    assert np.array_equal(DepthMapStack().focus_stack_arrays(b), out_b)
+    import ctypes
+    assert algo._lib.ssdm_rerun_resident(algo._h) == 0
+    again = np.empty_like(out_a)
+    assert algo._lib.ssdm_finish_end(algo._h, again.ctypes.data_as(ctypes.c_void_p), again.strides[0]) == 0
+    assert np.array_equal(again, out_a)
+
+
+def test_file_interface_callbacks_and_errors(tmp_path):
+    import cv2
+    from unittest.mock import MagicMock
+    frames = synthetic.make_noise_stack(4, 100, 140, np.uint16, 80)
+    paths = []
+    for i, f in enumerate(frames):
+        p = str(tmp_path / f"{i:03d}.tif")
+        cv2.imwrite(p, f)
+        paths.append(p)
+    algo = DepthMapStack()
+    algo.process = MagicMock()
+    algo.process.callback.return_value = True
+    out = algo.focus_stack(paths)
+    assert np.array_equal(out, DepthMapStack().focus_stack_arrays(frames))
+    steps = [c.args[3] for c in algo.process.callback.call_args_list if c.args[0] == "after_step"]
+    assert steps == list(range(8))              # depth_map.py:75 and :113: i, then i + n
+    # cancellation between frames
+    algo.process.callback.side_effect = lambda what, *a: False if what == "check_running" else None
+    with pytest.raises(RunStopException):
+        algo.focus_stack(paths)
+    algo.process.callback.side_effect = None
+    cv2.imwrite(paths[2], frames[2][:50])
+    with pytest.raises(ShapeError):
+        algo.focus_stack(paths)
+    cv2.imwrite(paths[2], frames[2])
+    assert np.array_equal(algo.focus_stack(paths), out)   # the handle survives the failures
+
+
+def test_full_size_identity_property():
+    # 4096 x 3072: a stack of identical frames fuses to that frame (weights sum to 1, the pyramid telescopes)
+    img = synthetic.make_noise_stack(1, 3072, 4096, np.uint8, 81)[0]
+    out = DepthMapStack().focus_stack_arrays([img] * 3)
+    du.assert_within_1lsb(out, img, "identical frames", max_frac=0.5)

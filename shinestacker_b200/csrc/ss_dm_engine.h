@@ -83,6 +83,7 @@ struct DmEngine {
     unsigned *d_stats = nullptr;
     std::vector<int> lh, lw;
     std::vector<float *> gp, acc;  // gp[l] (l >= 1): 4 planes; acc[l]: 3 planes
+    std::vector<float> h_sw;       // bilateral space weights, (2r+1)^2, 0 outside the disc
     DmTaps t_blur, t_a, t_b;
     int bil_r = 0;
     float gmax = 0.f;
@@ -143,7 +144,8 @@ struct DmEngine {
             bil_r = o.smooth_size / 2 > 1 ? o.smooth_size / 2 : 1;
             if (bil_r > 32) return fail(DM_ERR_INVALID_OPTION, "smooth_size must be <= 65");
             const int d = 2 * bil_r + 1;
-            std::vector<float> sw((size_t)d * d, 0.f);
+            std::vector<float> &sw = h_sw;
+            sw.assign((size_t)d * d, 0.f);
             const double gs = -0.5 / (25.0 * 25.0);
             for (int i = -bil_r; i <= bil_r; ++i)
                 for (int j = -bil_r; j <= bil_r; ++j) {
@@ -238,9 +240,16 @@ struct DmEngine {
         }
         weights = d_energy;
         if (o.smooth_size > 0) {
-            const float gc = (float)(-0.5 / (25.0 * 25.0));
-            DmBilateral k{d_energy, h, w, bil_r, d_sw, gc, 0.5f * gc * gc, d_stats, gmax, d_smooth};
-            if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());
+            const float gc = (float)(-0.5 / (25.0 * 25.0)), c1 = gc, c2 = 0.5f * gc * gc;
+            if (bil_r == 7) {
+                DmBilateralFixed<7> k;
+                k.in = d_energy; k.h = h; k.w = w; k.stats = d_stats; k.gmax = gmax; k.out = d_smooth;
+                for (int i = 0; i < 225; ++i) { k.s0[i] = h_sw[i]; k.s1[i] = h_sw[i] * c1; k.s2[i] = h_sw[i] * c2; }
+                if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());
+            } else {
+                DmBilateral k{d_energy, h, w, bil_r, d_sw, c1, c2, d_stats, gmax, d_smooth};
+                if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());
+            }
             weights = d_smooth;
         }
         DmFocusMap f{weights, h, w, n, o.map_type, (float)o.temperature};

@@ -208,6 +208,57 @@ struct DmBilateral {
     }
 };
 
+// The default diameter (smooth_size = 15 -> radius 7) with everything a tap needs in the kernel-parameter
+// constant bank: s, s*c1 and s*c2 by value, loops fully unrolled, taps outside the disc removed at compile
+// time, so an interior tap costs one load and six FP32 instructions:
+//   dv = v - v0;  q = dv*dv;  wgt = fma(q, fma(q, s*c2, s*c1), s);  num = fma(v, wgt, num);  den += wgt.
+template <int R>
+struct DmBilateralFixed {
+    enum { D = 2 * R + 1 };
+    const float *in; int h, w; const unsigned *stats; float gmax; float *out;
+    float s0[D * D], s1[D * D], s2[D * D];
+    SS_MDEV void operator()(int x, int y, int z) const
+    {
+        const long long plane = (long long)h * w;
+        const float *src = in + (long long)z * plane;
+        const float v0 = src[(long long)y * w + x];
+        float mn = __uint_as_float_compat(stats[2 * z]), mx = __uint_as_float_compat(stats[2 * z + 1]);
+        if (gmax > 0.f) { mn = ss_div(mn, gmax); mx = ss_div(mx, gmax); }
+        if (fabsf(mn - mx) < 1.1920929e-07f) { out[(long long)z * plane + (long long)y * w + x] = v0; return; }
+        float num = 0.f, den = 0.f;
+        if (x >= R && x < w - R && y >= R && y < h - R) {
+            const float *row = src + (long long)(y - R) * w + (x - R);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    if ((i - R) * (i - R) + (j - R) * (j - R) > R * R) continue;
+                    const float v = row[(long long)i * w + j];
+                    const float dv = ss_add(v, -v0);
+                    const float q = ss_mul(dv, dv);
+                    const float wgt = ss_fma(q, ss_fma(q, s2[i * D + j], s1[i * D + j]), s0[i * D + j]);
+                    num = ss_fma(v, wgt, num);
+                    den = ss_add(den, wgt);
+                }
+            }
+        } else {
+            for (int i = 0; i < D; ++i) {
+                const float *row = src + (long long)dm_reflect101(y - R + i, h) * w;
+                for (int j = 0; j < D; ++j) {
+                    if ((i - R) * (i - R) + (j - R) * (j - R) > R * R) continue;
+                    const float v = row[dm_reflect101(x - R + j, w)];
+                    const float dv = ss_add(v, -v0);
+                    const float q = ss_mul(dv, dv);
+                    const float wgt = ss_fma(q, ss_fma(q, s2[i * D + j], s1[i * D + j]), s0[i * D + j]);
+                    num = ss_fma(v, wgt, num);
+                    den = ss_add(den, wgt);
+                }
+            }
+        }
+        out[(long long)z * plane + (long long)y * w + x] = ss_div(num, den);
+    }
+};
+
 // get_focus_map (depth_map.py:53-62), in place over the n planes of e; frames summed in stack order.
 struct DmFocusMap {
     float *e; int h, w; int n; int softmax; float temperature;

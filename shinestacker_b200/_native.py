@@ -128,6 +128,19 @@ SIGNATURES_DEPTHMAP = {
     "ssdm_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),
 }
 
+# every symbol declared in include/shinestack_b200_align.h
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+SIGNATURES_ALIGN = {
+    "ssal_create": (_i, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_vp)]),
+    "ssal_destroy": (None, [_vp]),
+    "ssal_warp": (_i, [_vp, _vp, _sz, _dp, _i, _i, _dp, _ip, _i, _vp, _sz]),
+    "ssal_warp_device": (_i, [_vp, _vp, _sz, _dp, _i, _i, _dp, _ip, _i, _vp, _sz]),
+    "ssal_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    "ssal_kernel_time_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "ssal_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),
+}
+
 _LIB = None
 
 
@@ -144,7 +157,7 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as e:
         raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
-    for name, (res, args) in list(SIGNATURES.items()) + list(SIGNATURES_DEPTHMAP.items()):
+    for name, (res, args) in list(SIGNATURES.items()) + list(SIGNATURES_DEPTHMAP.items()) + list(SIGNATURES_ALIGN.items()):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

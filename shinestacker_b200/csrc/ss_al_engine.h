@@ -1,0 +1,146 @@
+// ss_al_engine.h -- launch sequence of the AlignFrames warp stage (reference align.py:216-251) against the same
+// tiny backend as ss_dm_engine.h (GPU in the product, plain loops in tests/emu/emu_align.cpp).  The float64
+// matrix inversion and the affine coordinate tables are built here on the host exactly like cv2 does;
+// everything per pixel is in the functors of ss_al_kernels.cuh.
+#pragma once
+#include "ss_al_kernels.cuh"
+#include "ss_dm_engine.h"
+
+enum { AL_RIGID = 0, AL_HOMOGRAPHY = 1 };
+enum { AL_BORDER_CONSTANT = 0, AL_BORDER_REPLICATE = 1, AL_BORDER_REPLICATE_BLUR = 2 };
+
+template <class Backend>
+struct AlEngine {
+    Backend be;
+    int h = 0, w = 0, bps = 0;
+    size_t pitch = 0, frame_bytes = 0;
+    uint8_t *d_src = nullptr, *d_warp = nullptr, *d_out = nullptr, *d_mask = nullptr;
+    int *d_tab = nullptr;
+    const uint8_t *result = nullptr;
+    std::vector<int> tab;
+    char err[256];
+
+    int fail(int code, const char *msg) { snprintf(err, sizeof(err), "%s", msg); return code; }
+
+    int create(int width, int height, int bytes_per_sample)
+    {
+        err[0] = 0;
+        w = width; h = height; bps = bytes_per_sample;
+        if (w < 1 || h < 1 || w > 32767 || h > 32767 || (bps != 1 && bps != 2))
+            return fail(DM_ERR_INVALID_OPTION, "invalid frame geometry");
+        pitch = (size_t)w * 3 * bps;
+        frame_bytes = pitch * h;
+        int rc;
+        if ((rc = be.alloc((void **)&d_src, frame_bytes))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_warp, frame_bytes))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_out, frame_bytes))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_mask, (size_t)w * h))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_tab, sizeof(int) * 2 * ((size_t)w + h)))) return fail(rc, be.last_error());
+        tab.resize(2 * ((size_t)w + h));
+        return DM_OK;
+    }
+
+    void destroy()
+    {
+        be.sync();
+        void *ptrs[] = {d_src, d_warp, d_out, d_mask, d_tab};
+        for (void *p : ptrs) if (p) be.free(p);
+        d_src = d_warp = d_out = d_mask = nullptr; d_tab = nullptr;
+    }
+
+    template <typename T>
+    int run(const double *m, int transform, int border_mode, const double *bval, const int *kernel, int taps)
+    {
+        AlWarp<T> k;
+        memset(&k, 0, sizeof(k));
+        k.src = (const T *)d_src; k.spitch = (long long)pitch; k.h = h; k.w = w;
+        k.dst = (T *)d_warp; k.dpitch = (long long)pitch;
+        k.mask = border_mode == AL_BORDER_REPLICATE_BLUR ? d_mask : nullptr;
+        k.border_const = border_mode == AL_BORDER_CONSTANT;
+        const double maxv = bps == 1 ? 255.0 : 65535.0;
+        for (int c = 0; c < 3; ++c) {       // saturate_cast<T>(borderValue[c])
+            double v = bval ? nearbyint(bval[c]) : 0.0;
+            k.bval[c] = (int)(v < 0 ? 0 : (v > maxv ? maxv : v));
+        }
+        int rc;
+        if (transform == AL_RIGID) {
+            // cv2.warpAffine: invert the 2x3 matrix in float64, then fixed-point tables with AB_BITS = 10
+            double M[6];
+            memcpy(M, m, sizeof(M));
+            double D = M[0] * M[4] - M[1] * M[3];
+            D = D != 0 ? 1. / D : 0;
+            const double A11 = M[4] * D, A22 = M[0] * D;
+            M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+            const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+            M[2] = b1; M[5] = b2;
+            int *ad = tab.data(), *bd = ad + w, *x0 = bd + w, *y0 = x0 + h;
+            for (int x = 0; x < w; ++x) {
+                ad[x] = (int)nearbyint(M[0] * x * 1024);
+                bd[x] = (int)nearbyint(M[3] * x * 1024);
+            }
+            for (int y = 0; y < h; ++y) {
+                x0[y] = (int)nearbyint((M[1] * y + M[2]) * 1024) + 16;
+                y0[y] = (int)nearbyint((M[4] * y + M[5]) * 1024) + 16;
+            }
+            if ((rc = be.upload_small(d_tab, tab.data(), tab.size() * sizeof(int)))) return rc;
+            k.persp = 0;
+            k.adelta = d_tab; k.bdelta = d_tab + w; k.x0 = d_tab + 2 * w; k.y0 = d_tab + 2 * w + h;
+        } else {
+            // cv2.warpPerspective: cv::invert of the 3x3 matrix (adjugate / determinant in float64)
+            const double *S = m;
+            double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) +
+                       S[2] * (S[3] * S[7] - S[4] * S[6]);
+            if (d == 0) return DM_ERR_INVALID_OPTION;
+            d = 1. / d;
+            k.m[0] = (S[4] * S[8] - S[5] * S[7]) * d; k.m[1] = (S[2] * S[7] - S[1] * S[8]) * d;
+            k.m[2] = (S[1] * S[5] - S[2] * S[4]) * d; k.m[3] = (S[5] * S[6] - S[3] * S[8]) * d;
+            k.m[4] = (S[0] * S[8] - S[2] * S[6]) * d; k.m[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+            k.m[6] = (S[3] * S[7] - S[4] * S[6]) * d; k.m[7] = (S[1] * S[6] - S[0] * S[7]) * d;
+            k.m[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+            k.persp = 1;
+            k.float_persp = bps == 2;
+        }
+        if ((rc = be.launch(k, w, h, 1))) return rc;
+        result = d_warp;
+        if (border_mode == AL_BORDER_REPLICATE_BLUR) {
+            AlBlurFill<T> b;
+            memset(&b, 0, sizeof(b));
+            b.warped = (const T *)d_warp; b.wpitch = (long long)pitch; b.h = h; b.w = w; b.mask = d_mask;
+            b.taps = taps;
+            for (int i = 0; i < taps; ++i) b.k[i] = kernel[i];
+            b.out = (T *)d_out; b.opitch = (long long)pitch;
+            if ((rc = be.launch(b, w, h, 1))) return rc;
+            result = d_out;
+        }
+        return DM_OK;
+    }
+
+    // replaces align.py:228-251 for one frame; dst_host may be NULL (result stays on the device)
+    int warp(const void *src, size_t spitch, int src_on_device, const double *m, int transform, int border_mode,
+             const double *bval, const int *kernel, int taps, void *dst_host, size_t dpitch)
+    {
+        if (!src || !m) return fail(DM_ERR_INVALID_OPTION, "null argument");
+        if (transform != AL_RIGID && transform != AL_HOMOGRAPHY) return fail(DM_ERR_INVALID_OPTION, "transform");
+        if (border_mode < 0 || border_mode > 2) return fail(DM_ERR_INVALID_OPTION, "border_mode");
+        if (border_mode == AL_BORDER_REPLICATE_BLUR) {
+            if (!kernel || taps < 1 || taps > AL_MAX_BLUR_TAPS || !(taps & 1))
+                return fail(DM_ERR_INVALID_OPTION, "blur kernel: odd number of taps, at most 63");
+            long long sum = 0;
+            for (int i = 0; i < taps; ++i) sum += kernel[i];
+            if (sum != (bps == 1 ? 256 : 65536)) return fail(DM_ERR_INVALID_OPTION, "blur kernel must sum to 1.0 in fixed point");
+        }
+        if (spitch < pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
+        be.mark_start();
+        int rc = be.upload_frame(d_src, pitch, src, spitch, pitch, h, src_on_device);
+        if (rc) return fail(rc, be.last_error());
+        rc = bps == 1 ? run<uint8_t>(m, transform, border_mode, bval, kernel, taps)
+                      : run<uint16_t>(m, transform, border_mode, bval, kernel, taps);
+        if (rc) return fail(rc, rc == DM_ERR_INVALID_OPTION ? "singular transform" : be.last_error());
+        be.mark_end();
+        if (dst_host) {
+            if (dpitch < pitch) return fail(DM_ERR_INVALID_OPTION, "output row pitch smaller than a row");
+            rc = be.download2d(dst_host, dpitch, result, pitch, pitch, h);
+        } else rc = be.sync();
+        return rc ? fail(rc, be.last_error()) : DM_OK;
+    }
+};

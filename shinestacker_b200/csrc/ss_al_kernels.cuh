@@ -1,0 +1,137 @@
+// ss_al_kernels.cuh -- device code of the warp stage of AlignFrames (sm_100a): what the reference's
+// align_images does once the transform is known (reference src/shinestacker/algorithms/align.py:216-251):
+// cv2.warpAffine / cv2.warpPerspective (INTER_LINEAR; constant or replicated border), the validity mask of
+// BORDER_REPLICATE_BLUR, cv2.GaussianBlur(21x21) and the paste of the blurred pixels where the mask is 0.
+// Pixel functors like ss_dm_kernels.cuh: nvcc instantiates dm_px_kernel<Functor>, tests/emu/ runs the same
+// functors in loops under g++.
+//
+// All of it is integer / fixed-point work and bit-exact against cv2 4.13 (oracle/align_oracle.py):
+//   * source coordinates in 1/32 pixel: affine from the host-built tables rint(M*x*1024) (+16, >> 5) --
+//     float64 only on the host --, perspective rint(32 * X/W) in float64 per pixel;
+//   * uint8: (sum_i w_i p_i * 32 + 2^14) >> 15 with w = (32-fx)(32-fy), ...; uint16: float32
+//     v0*w0 + v1*w1 + v2*w2 + v3*w3 (unfused, left to right), round-half-even;
+//   * mask != 0 <=> the taps inside the image carry >= 512/1024 of the weight;
+//   * blur: (sum_ij k_i k_j p_ij + half) >> shift with cv2's integer kernel (8 / 16 fractional bits),
+//     evaluated only where the mask is 0 (thin border strips), REFLECT101.
+// uint16 + homography follows cv2 4.13's float kernels instead (not bit-pinned, see the oracle's header).
+#pragma once
+#include "ss_dm_kernels.cuh"
+
+#define AL_MAX_BLUR_TAPS 64
+
+#ifdef SS_HOST_EMU
+#include <math.h>
+SS_DEV long long al_rint_ll(double v) { return (long long)nearbyint(v); }
+SS_DEV float al_rintf(float v) { return nearbyintf(v); }
+#else
+SS_DEV long long al_rint_ll(double v) { return __double2ll_rn(v); }
+SS_DEV float al_rintf(float v) { return rintf(v); }
+#endif
+
+template <typename T>
+struct AlWarp {
+    const T *src; long long spitch; int h, w;
+    int persp;                                   // 0: affine tables, 1: perspective (inverted matrix in m)
+    const int *adelta, *bdelta, *x0, *y0;        // affine: rint(M0*x*1024), rint(M3*x*1024), row offsets + 16
+    double m[9];
+    int border_const; int bval[3];               // BORDER_CONSTANT and its value (already saturated to T)
+    int float_persp;                             // uint16 + homography: cv2's float path
+    T *dst; long long dpitch; uint8_t *mask;     // mask (h x w, nullable): 1 where the warp of ones is non-zero
+
+    SS_MDEV const T *row(int y) const { return (const T *)((const char *)src + (long long)y * spitch); }
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        long long X, Y;
+        float ffx = 0.f, ffy = 0.f;
+        if (!persp) {
+            X = ((long long)x0[y] + adelta[x]) >> 5;
+            Y = ((long long)y0[y] + bdelta[x]) >> 5;
+        } else {
+            const double dx = (double)x, dy = (double)y;
+            const double X0 = m[0] * dx + (m[1] * dy + m[2]);
+            const double Y0 = m[3] * dx + (m[4] * dy + m[5]);
+            double W = m[6] * dx + (m[7] * dy + m[8]);
+            if (float_persp) {
+                const float fX = (float)(X0 / W), fY = (float)(Y0 / W);
+                const float flx = floorf(fX), fly = floorf(fY);
+                ffx = fX - flx; ffy = fY - fly;
+                X = (long long)flx * 32; Y = (long long)fly * 32;
+            } else {
+                W = W != 0.0 ? 32.0 / W : 0.0;
+                double fX = X0 * W, fY = Y0 * W;
+                fX = fX < -2147483648.0 ? -2147483648.0 : (fX > 2147483647.0 ? 2147483647.0 : fX);
+                fY = fY < -2147483648.0 ? -2147483648.0 : (fY > 2147483647.0 ? 2147483647.0 : fY);
+                X = al_rint_ll(fX); Y = al_rint_ll(fY);
+            }
+        }
+        long long sxl = X >> 5, syl = Y >> 5;
+        sxl = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);
+        syl = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
+        const int sx = (int)sxl, sy = (int)syl, fx = (int)(X & 31), fy = (int)(Y & 31);
+        const int wt[4] = {(32 - fx) * (32 - fy), fx * (32 - fy), (32 - fx) * fy, fx * fy};
+        const int in_x0 = sx >= 0 && sx < w, in_x1 = sx + 1 >= 0 && sx + 1 < w;
+        const int in_y0 = sy >= 0 && sy < h, in_y1 = sy + 1 >= 0 && sy + 1 < h;
+        const int inside[4] = {in_x0 && in_y0, in_x1 && in_y0, in_x0 && in_y1, in_x1 && in_y1};
+        const int cx0 = sx < 0 ? 0 : (sx > w - 1 ? w - 1 : sx), cx1 = sx + 1 < 0 ? 0 : (sx + 1 > w - 1 ? w - 1 : sx + 1);
+        const int cy0 = sy < 0 ? 0 : (sy > h - 1 ? h - 1 : sy), cy1 = sy + 1 < 0 ? 0 : (sy + 1 > h - 1 ? h - 1 : sy + 1);
+        const T *r0 = row(cy0), *r1 = row(cy1);
+        T *o = (T *)((char *)dst + (long long)y * dpitch) + 3 * x;
+        if (mask) {
+            int s = 0;
+            for (int i = 0; i < 4; ++i) s += inside[i] ? wt[i] : 0;
+            mask[(long long)y * w + x] = s >= 512 ? 1 : 0;
+        }
+        for (int c = 0; c < 3; ++c) {
+            int v[4] = {(int)r0[3 * cx0 + c], (int)r0[3 * cx1 + c], (int)r1[3 * cx0 + c], (int)r1[3 * cx1 + c]};
+            if (border_const)
+                for (int i = 0; i < 4; ++i) if (!inside[i]) v[i] = bval[c];
+            if (sizeof(T) == 1) {
+                const int t = ((v[0] * wt[0] + v[1] * wt[1] + v[2] * wt[2] + v[3] * wt[3]) * 32 + 16384) >> 15;
+                o[c] = (T)(t > 255 ? 255 : t);
+            } else if (float_persp) {
+                const float top = ss_add((float)v[0], ss_mul(ffx, ss_add((float)v[1], -(float)v[0])));
+                const float bot = ss_add((float)v[2], ss_mul(ffx, ss_add((float)v[3], -(float)v[2])));
+                float t = al_rintf(ss_add(top, ss_mul(ffy, ss_add(bot, -top))));
+                t = t < 0.f ? 0.f : (t > 65535.f ? 65535.f : t);
+                o[c] = (T)(int)t;
+            } else {
+                float t = ss_mul((float)v[0], ss_mul((float)wt[0], 0.0009765625f));
+                t = ss_add(t, ss_mul((float)v[1], ss_mul((float)wt[1], 0.0009765625f)));
+                t = ss_add(t, ss_mul((float)v[2], ss_mul((float)wt[2], 0.0009765625f)));
+                t = ss_add(t, ss_mul((float)v[3], ss_mul((float)wt[3], 0.0009765625f)));
+                t = al_rintf(t);
+                o[c] = (T)(int)(t > 65535.f ? 65535.f : t);
+            }
+        }
+    }
+};
+
+// img_warp[mask == 0] = GaussianBlur(img_warp)[mask == 0] (align.py:249-251): copy where the mask is set,
+// the full 2-D fixed-point sum elsewhere (no intermediate rounding in cv2's separable passes either).
+template <typename T>
+struct AlBlurFill {
+    const T *warped; long long wpitch; int h, w; const uint8_t *mask;
+    int taps; int k[AL_MAX_BLUR_TAPS];
+    T *out; long long opitch;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        T *o = (T *)((char *)out + (long long)y * opitch) + 3 * x;
+        const T *s = (const T *)((const char *)warped + (long long)y * wpitch) + 3 * x;
+        if (mask[(long long)y * w + x]) { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; return; }
+        const int r = taps / 2;
+        unsigned long long acc[3] = {0, 0, 0};
+        for (int i = 0; i < taps; ++i) {
+            const T *line = (const T *)((const char *)warped + (long long)dm_reflect101(y - r + i, h) * wpitch);
+            unsigned long long ra[3] = {0, 0, 0};
+            for (int j = 0; j < taps; ++j) {
+                const T *p = line + 3 * dm_reflect101(x - r + j, w);
+                ra[0] += (unsigned long long)k[j] * p[0];
+                ra[1] += (unsigned long long)k[j] * p[1];
+                ra[2] += (unsigned long long)k[j] * p[2];
+            }
+            for (int c = 0; c < 3; ++c) acc[c] += (unsigned long long)k[i] * ra[c];
+        }
+        const int shift = sizeof(T) == 1 ? 16 : 32;
+        for (int c = 0; c < 3; ++c) o[c] = (T)((acc[c] + (1ull << (shift - 1))) >> shift);
+    }
+};

@@ -268,22 +268,22 @@ struct DmEngine {
         const int first = blended == 0;
         if (L > 1) {
             DmPyrDown<InT> d0{s0, lh[1], lw[1], gp[1]};
-            if ((rc = be.launch(d0, lw[1], lh[1], 4))) return rc;
+            if ((rc = be.launch(d0, lw[1], lh[1], 1))) return rc;
         }
         for (int l = 1; l + 1 < L; ++l) {
             DmLevelSrc<float> s{nullptr, 0, gp[l], gp[l] + 3 * (size_t)lh[l] * lw[l], lh[l], lw[l]};
             DmPyrDown<float> d{s, lh[l + 1], lw[l + 1], gp[l + 1]};
-            if ((rc = be.launch(d, lw[l + 1], lh[l + 1], 4))) return rc;
+            if ((rc = be.launch(d, lw[l + 1], lh[l + 1], 1))) return rc;
         }
         {
             DmBlendLevel<InT> b{s0, L > 1 ? gp[1] : nullptr, L > 1 ? lh[1] : 0, L > 1 ? lw[1] : 0, acc[0], first};
-            if ((rc = be.launch(b, w, h, 3))) return rc;
+            if ((rc = be.launch(b, w, h, 1))) return rc;
         }
         for (int l = 1; l < L; ++l) {
             DmLevelSrc<float> s{nullptr, 0, gp[l], gp[l] + 3 * (size_t)lh[l] * lw[l], lh[l], lw[l]};
             const bool top = l == L - 1;
             DmBlendLevel<float> b{s, top ? nullptr : gp[l + 1], top ? 0 : lh[l + 1], top ? 0 : lw[l + 1], acc[l], first};
-            if ((rc = be.launch(b, lw[l], lh[l], 3))) return rc;
+            if ((rc = be.launch(b, lw[l], lh[l], 1))) return rc;
         }
         return DM_OK;
     }
@@ -307,7 +307,7 @@ struct DmEngine {
         if (!collapsed) {   // a second call only downloads the image again
             for (int l = L - 2; l >= 0; --l) {
                 DmCollapse c{acc[l + 1], lh[l + 1], lw[l + 1], acc[l], lh[l], lw[l]};
-                if ((rc = be.launch(c, lw[l], lh[l], 3))) return fail(rc, be.last_error());
+                if ((rc = be.launch(c, lw[l], lh[l], 1))) return fail(rc, be.last_error());
             }
             if (bps == 1) {
                 DmStoreOutput<uint8_t> s{acc[0], h, w, 255.f, d_out, (long long)frame_pitch};

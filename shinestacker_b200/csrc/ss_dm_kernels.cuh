@@ -124,9 +124,10 @@ SS_DEV void dm_stats_update(unsigned *stats, float e)
 #else
     const unsigned m = __activemask();
     const unsigned lo = __reduce_min_sync(m, bits), hi = __reduce_max_sync(m, bits);
+    // one lane per warp; the values are monotone, so a plain (L2) read first skips almost every atomic
     if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
-        atomicMin(stats, lo);
-        atomicMax(stats + 1, hi);
+        if (lo < __ldcg(stats)) atomicMin(stats, lo);
+        if (hi > __ldcg(stats + 1)) atomicMax(stats + 1, hi);
     }
 #endif
 }
@@ -308,79 +309,107 @@ struct DmLevelSrc {
 };
 
 // cv2.pyrDown (depth_map.py:101-102): row = 6*s[2x] + 4*(s[2x-1] + s[2x+1]) + s[2x-2] + s[2x+2] on five
-// source rows (REFLECT101), then the same vertically, * 1/256.  z = plane (0..2 image, 3 weight).
+// source rows (REFLECT101), then the same vertically, * 1/256.  One call computes all four planes (B, G, R,
+// weight) of one output pixel: the ten reflected source indices are shared by the planes.
 template <typename InT>
 struct DmPyrDown {
     DmLevelSrc<InT> src; int h2, w2; float *out /* 4 planes h2 x w2 */;
-    SS_MDEV float row(int c, int x2, int yy) const
+    SS_MDEV void operator()(int x2, int y2, int) const
     {
-        const int w = src.w, x = 2 * x2;
-        const float c0 = src.at(c, x, yy);
-        const float s1 = ss_add(src.at(c, dm_reflect101(x - 1, w), yy), src.at(c, dm_reflect101(x + 1, w), yy));
-        float acc = ss_add(ss_mul(c0, 6.f), ss_mul(s1, 4.f));
-        acc = ss_add(acc, src.at(c, dm_reflect101(x - 2, w), yy));
-        return ss_add(acc, src.at(c, dm_reflect101(x + 2, w), yy));
-    }
-    SS_MDEV void operator()(int x2, int y2, int c) const
-    {
-        const int h = src.h, y = 2 * y2;
-        const float r2 = row(c, x2, y);
-        const float r13 = ss_add(row(c, x2, dm_reflect101(y - 1, h)), row(c, x2, dm_reflect101(y + 1, h)));
-        float acc = ss_add(ss_mul(r2, 6.f), ss_mul(r13, 4.f));
-        acc = ss_add(acc, row(c, x2, dm_reflect101(y - 2, h)));
-        acc = ss_add(acc, row(c, x2, dm_reflect101(y + 2, h)));
-        out[((long long)c * h2 + y2) * w2 + x2] = ss_mul(acc, 0.00390625f);
+        const int h = src.h, w = src.w, x = 2 * x2, y = 2 * y2;
+        int xs[5], ys[5];   // order of use: centre, -1, +1, -2, +2
+        if (x >= 2 && x + 2 < w) { xs[0] = x; xs[1] = x - 1; xs[2] = x + 1; xs[3] = x - 2; xs[4] = x + 2; }
+        else { xs[0] = x; xs[1] = dm_reflect101(x - 1, w); xs[2] = dm_reflect101(x + 1, w);
+               xs[3] = dm_reflect101(x - 2, w); xs[4] = dm_reflect101(x + 2, w); }
+        if (y >= 2 && y + 2 < h) { ys[0] = y; ys[1] = y - 1; ys[2] = y + 1; ys[3] = y - 2; ys[4] = y + 2; }
+        else { ys[0] = y; ys[1] = dm_reflect101(y - 1, h); ys[2] = dm_reflect101(y + 1, h);
+               ys[3] = dm_reflect101(y - 2, h); ys[4] = dm_reflect101(y + 2, h); }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float r[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int yy = ys[i];
+                const float s1 = ss_add(src.at(c, xs[1], yy), src.at(c, xs[2], yy));
+                float acc = ss_add(ss_mul(src.at(c, xs[0], yy), 6.f), ss_mul(s1, 4.f));
+                acc = ss_add(acc, src.at(c, xs[3], yy));
+                r[i] = ss_add(acc, src.at(c, xs[4], yy));
+            }
+            float acc = ss_add(ss_mul(r[0], 6.f), ss_mul(ss_add(r[1], r[2]), 4.f));
+            acc = ss_add(acc, r[3]);
+            acc = ss_add(acc, r[4]);
+            out[((long long)c * h2 + y2) * w2 + x2] = ss_mul(acc, 0.00390625f);
+        }
     }
 };
 
-// cv2.pyrUp(src, dstsize) (depth_map.py:106, :120) at destination pixel (x, y) of one coarse float plane
+// cv2.pyrUp(src, dstsize) (depth_map.py:106, :120) at destination pixel (x, y) of a coarse float plane
 // h2 x w2: even columns l + 6c + r, odd columns 4(c + r); coarse index -1 -> 1, n -> n - 1; then the same
-// vertically, * 1/64.
-SS_DEV float dm_pyrup_row(const float *line, int w2, int x)
+// vertically, * 1/64.  DmUpIdx holds the coarse indices of one destination pixel (shared by the channels).
+struct DmUpIdx {
+    int xl, xc, xr, odd_x; long long yu, yc, yd; int odd_y;
+};
+SS_DEV DmUpIdx dm_pyrup_idx(int h2, int w2, int x, int y)
 {
-    const int xc = x >> 1;
-    const float c = line[xc];
-    const float r = line[xc + 1 < w2 ? xc + 1 : w2 - 1];
-    if (x & 1) return ss_mul(ss_add(c, r), 4.f);
-    const float l = line[xc > 0 ? xc - 1 : (w2 > 1 ? 1 : 0)];
-    return ss_add(ss_add(l, ss_mul(c, 6.f)), r);
-}
-SS_DEV float dm_pyrup_at(const float *coarse, int h2, int w2, int x, int y)
-{
+    DmUpIdx i;
+    i.xc = x >> 1; i.odd_x = x & 1;
+    i.xr = i.xc + 1 < w2 ? i.xc + 1 : w2 - 1;
+    i.xl = i.xc > 0 ? i.xc - 1 : (w2 > 1 ? 1 : 0);
     const int yc = y >> 1;
-    const float *lc = coarse + (long long)yc * w2;
-    const float *ld = coarse + (long long)(yc + 1 < h2 ? yc + 1 : h2 - 1) * w2;
-    const float c = dm_pyrup_row(lc, w2, x), d = dm_pyrup_row(ld, w2, x);
-    if (y & 1) return ss_mul(ss_mul(ss_add(c, d), 4.f), 0.015625f);
-    const float *lu = coarse + (long long)(yc > 0 ? yc - 1 : (h2 > 1 ? 1 : 0)) * w2;
-    const float u = dm_pyrup_row(lu, w2, x);
+    i.odd_y = y & 1;
+    i.yc = (long long)yc * w2;
+    i.yd = (long long)(yc + 1 < h2 ? yc + 1 : h2 - 1) * w2;
+    i.yu = (long long)(yc > 0 ? yc - 1 : (h2 > 1 ? 1 : 0)) * w2;
+    return i;
+}
+SS_DEV float dm_pyrup_row(const float *line, const DmUpIdx &i)
+{
+    const float c = line[i.xc], r = line[i.xr];
+    if (i.odd_x) return ss_mul(ss_add(c, r), 4.f);
+    return ss_add(ss_add(line[i.xl], ss_mul(c, 6.f)), r);
+}
+SS_DEV float dm_pyrup_at(const float *coarse, const DmUpIdx &i)
+{
+    const float c = dm_pyrup_row(coarse + i.yc, i), d = dm_pyrup_row(coarse + i.yd, i);
+    if (i.odd_y) return ss_mul(ss_mul(ss_add(c, d), 4.f), 0.015625f);
+    const float u = dm_pyrup_row(coarse + i.yu, i);
     return ss_mul(ss_add(ss_add(u, ss_mul(c, 6.f)), d), 0.015625f);
 }
 
 // One level of the frame's weighted Laplacian pyramid added to the running blend (depth_map.py:104-111):
 // acc[c] (+)= (g_l[c] - pyrUp(g_{l+1}[c])) * w_l, or g_l[c] * w_l at the coarsest level (coarse == NULL).
-// The first frame stores instead of adding.  z = channel.
+// The first frame stores instead of adding.  One call handles the three channels of one pixel.
 template <typename InT>
 struct DmBlendLevel {
     DmLevelSrc<InT> fine; const float *coarse /* 4 planes h2 x w2 or NULL */; int h2, w2;
     float *acc /* 3 planes */; int first;
-    SS_MDEV void operator()(int x, int y, int c) const
+    SS_MDEV void operator()(int x, int y, int) const
     {
-        float v = fine.at(c, x, y);
-        if (coarse) v = ss_add(v, -dm_pyrup_at(coarse + (long long)c * h2 * w2, h2, w2, x, y));
-        v = ss_mul(v, fine.at(3, x, y));
-        float *a = acc + ((long long)c * fine.h + y) * fine.w + x;
-        *a = first ? v : ss_add(*a, v);
+        const float wgt = fine.at(3, x, y);
+        DmUpIdx ix;
+        if (coarse) ix = dm_pyrup_idx(h2, w2, x, y);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = fine.at(c, x, y);
+            if (coarse) v = ss_add(v, -dm_pyrup_at(coarse + (long long)c * h2 * w2, ix));
+            v = ss_mul(v, wgt);
+            float *a = acc + ((long long)c * fine.h + y) * fine.w + x;
+            *a = first ? v : ss_add(*a, v);
+        }
     }
 };
 
-// One collapse step (depth_map.py:118-120): fine[c] = pyrUp(coarse[c]) + fine[c], in place.  z = channel.
+// One collapse step (depth_map.py:118-120): fine[c] = pyrUp(coarse[c]) + fine[c], in place.
 struct DmCollapse {
     const float *coarse; int h2, w2; float *fine; int h, w;
-    SS_MDEV void operator()(int x, int y, int c) const
+    SS_MDEV void operator()(int x, int y, int) const
     {
-        float *a = fine + ((long long)c * h + y) * w + x;
-        *a = ss_add(dm_pyrup_at(coarse + (long long)c * h2 * w2, h2, w2, x, y), *a);
+        const DmUpIdx ix = dm_pyrup_idx(h2, w2, x, y);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float *a = fine + ((long long)c * h + y) * w + x;
+            *a = ss_add(dm_pyrup_at(coarse + (long long)c * h2 * w2, ix), *a);
+        }
     }
 };
 

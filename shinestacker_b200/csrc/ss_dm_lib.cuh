@@ -50,6 +50,7 @@ struct DmCudaBackend {
     }
     int sync_copies() { DM_CUDA(cudaStreamSynchronize(s_copy)); return 0; }
     void reset_counters() { launches = 0; started = ended = false; }
+    void reset_timing() { started = ended = false; }
     void mark_start() { if (!started) { cudaEventRecord(ev_start, s_comp); started = true; ended = false; } }
     void mark_end() { cudaEventRecord(ev_end, s_comp); ended = true; }
     int upload_small(void *dst, const void *src, size_t bytes)

@@ -1,0 +1,37 @@
+// Host backend of the engine templates (TEST INFRASTRUCTURE ONLY): every "kernel" launch is a plain loop.
+#pragma once
+#include <stdlib.h>
+#include <string.h>
+
+struct DmHostBackend {
+    long long launches = 0;
+    const char *last_error() const { return "host backend"; }
+    int alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); if (*p) memset(*p, 0xff, bytes); return *p ? 0 : DM_ERR_NOMEM; }
+    void free(void *p) { ::free(p); }
+    int sync() { return 0; }
+    void reset_counters() { launches = 0; }
+    void mark_start() {}
+    void mark_end() {}
+    int upload_small(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+    int upload_frame(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows, int)
+    {
+        for (int y = 0; y < rows; ++y) memcpy((char *)dst + y * dpitch, (const char *)src + y * spitch, row_bytes);
+        return 0;
+    }
+    int download(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+    int download2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows)
+    {
+        for (int y = 0; y < rows; ++y) memcpy((char *)dst + y * dpitch, (const char *)src + y * spitch, row_bytes);
+        return 0;
+    }
+    template <class K>
+    int launch(const K &k, int w, int h, int z)
+    {
+        for (int c = 0; c < z; ++c)
+            for (int y = 0; y < h; ++y)
+                for (int x = 0; x < w; ++x) k(x, y, c);
+        ++launches;
+        return 0;
+    }
+};
+

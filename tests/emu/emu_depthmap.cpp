@@ -7,37 +7,7 @@
 #include <stdlib.h>
 #include "../../shinestacker_b200/csrc/ss_dm_engine.h"
 
-struct DmHostBackend {
-    long long launches = 0;
-    const char *last_error() const { return "host backend"; }
-    int alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); if (*p) memset(*p, 0xff, bytes); return *p ? 0 : DM_ERR_NOMEM; }
-    void free(void *p) { ::free(p); }
-    int sync() { return 0; }
-    void reset_counters() { launches = 0; }
-    void mark_start() {}
-    void mark_end() {}
-    int upload_small(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
-    int upload_frame(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows, int)
-    {
-        for (int y = 0; y < rows; ++y) memcpy((char *)dst + y * dpitch, (const char *)src + y * spitch, row_bytes);
-        return 0;
-    }
-    int download(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
-    int download2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows)
-    {
-        for (int y = 0; y < rows; ++y) memcpy((char *)dst + y * dpitch, (const char *)src + y * spitch, row_bytes);
-        return 0;
-    }
-    template <class K>
-    int launch(const K &k, int w, int h, int z)
-    {
-        for (int c = 0; c < z; ++c)
-            for (int y = 0; y < h; ++y)
-                for (int x = 0; x < w; ++x) k(x, y, c);
-        ++launches;
-        return 0;
-    }
-};
+#include "emu_backend.h"
 
 typedef DmEngine<DmHostBackend> Emu;
 

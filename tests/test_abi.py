@@ -46,6 +46,18 @@ def test_library_exports_every_depthmap_symbol():
     assert b"float" in lib.ss_last_error()
 
 
+def test_library_exports_every_align_symbol():
+    lib = _native.load()
+    names = _declared_symbols("shinestack_b200_align.h", "ssal_")
+    assert len(names) >= 7
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(_native.SIGNATURES_ALIGN), set(names) ^ set(_native.SIGNATURES_ALIGN)
+    h = ctypes.c_void_p()
+    if lib.ss_device_count() == 0:      # no silent CPU fallback for the warp either
+        assert lib.ssal_create(64, 64, 1, 0, ctypes.byref(h)) == _native.SS_ERR_NO_DEVICE
+
+
 def test_version_and_config_layout():
     lib = _native.load()
     assert b"sm_100a" in lib.ss_version()

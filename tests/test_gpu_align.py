@@ -1,0 +1,96 @@
+"""GPU parity tests of the AlignFrames warp stage (through ctypes -> C ABI, include/shinestack_b200_align.h)
+against cv2 itself -- the library the reference calls at align.py:228-251 -- bit-exact for uint8 and for
+uint16 + rigid transforms, in all three border modes."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import align_util as au
+from oracle import align_oracle as ao
+from shinestacker_b200 import align as al
+from shinestacker_b200 import PyramidStack, synthetic
+from shinestacker_b200.pyramid import _check
+
+cv2 = pytest.importorskip("cv2")
+pytestmark = pytest.mark.gpu
+
+PINNED = [(dt, name) for dt in (np.uint8, np.uint16) for name, _ in au.TRANSFORMS
+          if not (dt == np.uint16 and name == "homography")]
+
+
+def _img(dtype, h, w, seed):
+    return np.random.default_rng(seed).integers(0, np.iinfo(dtype).max + 1, (h, w, 3)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype,name", PINNED)
+@pytest.mark.parametrize("mode", list(au.MODES))
+def test_cuda_warp_matches_cv2(dtype, name, mode):
+    m = dict(au.TRANSFORMS)[name]
+    img = _img(dtype, 333, 517, seed=len(name) + 7)
+    bval = (17, 99, 250, 0) if mode == "BORDER_CONSTANT" else (0, 0, 0, 0)
+    ref = au.cv2_warp_stage(img, m, mode, bval)
+    wp = al.Warper(img.shape[:2], dtype)
+    tr = al.ALIGN_HOMOGRAPHY if np.asarray(m).size == 9 else al.ALIGN_RIGID
+    out = wp.warp(img, m, tr, mode, bval)
+    assert np.array_equal(out, ref), f"{(out != ref).mean():.5f} of the samples differ"
+    assert wp.last_kernel_ms > 0
+    wp.close()
+
+
+def test_uint16_homography_matches_the_float_model():
+    yy, xx = np.mgrid[0:300, 0:420]
+    img = np.stack([xx * 150 + yy * 17, xx * 5 + yy * 200, xx * 61 + yy * 122], -1).astype(np.uint16)
+    m = au.homography(0.7, 1.01, 5.5, -8.25)
+    wp = al.Warper(img.shape[:2], np.uint16)
+    out = wp.warp(img, m, al.ALIGN_HOMOGRAPHY, "BORDER_REPLICATE")
+    assert np.array_equal(out, ao.warp(img, m, ao.BORDER_REPLICATE))
+    ref = cv2.warpPerspective(img, m, (420, 300), borderMode=cv2.BORDER_REPLICATE)
+    inner = (slice(30, 270), slice(30, 390))
+    assert np.abs(out[inner].astype(int) - ref[inner].astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_full_size_frame_and_other_blur_sigma(dtype):
+    img = _img(dtype, 3072, 4096, seed=11)
+    m = au.rigid(0.35, 1.002, 18.4, -11.7)
+    wp = al.Warper(img.shape[:2], dtype)
+    for sigma in (50, 4.0):
+        out = wp.warp(img, m, al.ALIGN_RIGID, "BORDER_REPLICATE_BLUR", border_blur=sigma)
+        assert np.array_equal(out, au.cv2_warp_stage(img, m, "BORDER_REPLICATE_BLUR", border_blur=sigma))
+    wp.close()
+
+
+def test_align_images_end_to_end_matches_the_reference_pipeline():
+    # same estimator calls (cv2, host) + warp on the GPU == the reference's align_images, image for image
+    from test_align_cpu import _scene
+    img = _scene(768, 1024, seed=9)
+    m_true = cv2.getRotationMatrix2D((512, 384), 1.2, 1.004)
+    m_true[:, 2] += (9.0, -6.5)
+    moved = cv2.warpAffine(img, m_true, (1024, 768), borderMode=cv2.BORDER_REPLICATE)
+    n, m, out = al.align_images(img, moved)
+    assert n > 100 and m is not None and m.dtype == np.float32      # estimated on the 2x sub-sampled frames
+    assert np.array_equal(out, au.cv2_warp_stage(moved, m, "BORDER_REPLICATE_BLUR"))
+    # the aligned frame is close to the reference frame again
+    inner = (slice(40, -40), slice(40, -40))
+    assert np.abs(out[inner].astype(int) - img[inner].astype(int)).mean() < 6.0
+
+
+def test_aligned_frames_feed_the_stacker_without_leaving_hbm():
+    # config 5 of BASELINE.json in miniature: warp on the device, ss_push_frame_device, same fused image as
+    # stacking the cv2-aligned frames
+    frames = synthetic.make_stack(5, 300, 408, np.uint8, 13)
+    mats = [au.rigid(0.1 * i, 1 + 0.001 * i, 1.5 * i, -0.75 * i) for i in range(5)]
+    aligned = [au.cv2_warp_stage(f, m, "BORDER_REPLICATE_BLUR") for f, m in zip(frames, mats)]
+    expect = PyramidStack().focus_stack_arrays(aligned)
+    algo = PyramidStack(batch_frames=2)
+    algo._set_metadata(frames[0])
+    algo._ensure_handle(frames[0].shape, frames[0].dtype, 5)
+    wp = al.Warper(frames[0].shape[:2], np.uint8)
+    for f, m in zip(frames, mats):
+        assert wp.warp(f, m, al.ALIGN_RIGID, "BORDER_REPLICATE_BLUR", download=False) is None
+        ptr, pitch = wp.result_device()
+        _check(algo._lib.ss_push_frame_device(algo._h, ptr, pitch))
+        _check(algo._lib.ss_sync(algo._h))      # the warper's output buffer is reused by the next frame
+    out = algo._finish(5, frames[0].shape[:2])
+    assert np.array_equal(out, expect)

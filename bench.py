@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=64,
                     help="frames of the stack the CPU baseline fuses (64 = the whole workload, ~10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true",
+                    help="skip the short DepthMapStack / AlignFrames measurements appended as 'next_rows' (N=1 only)")
     return ap.parse_args()
 
 
@@ -126,6 +128,21 @@ def cpu_baseline(a, n_sample, threads=None, frames=None):
     return {"value": mp / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {n_sample} of the {a.frames} frames ({workload_name(a)}), oracle/pyramid_oracle "
                       f"(C + OpenMP, {cores} threads), {dt:.2f} s"}, frames
+
+
+def next_rows(a, host):
+    """SURVEY.md section 8f rows built beyond the headline path, measured on the same frames (not part of
+    `value`): DepthMapStack (device-resident chain + end to end from host frames) and the AlignFrames warp
+    stage (one frame: warp + mask + 21x21 blur fill) with cv2 on the host cores beside it."""
+    out = {}
+    try:
+        from tools import time_depthmap, time_align
+        out["depth_map"] = time_depthmap.measure(a.frames, a.height, a.width, a.dtype, steps=3, warmup=1,
+                                                 host=list(host))
+        out["align_warp"] = time_align.measure(a.height, a.width, a.dtype, steps=5)
+    except Exception as e:  # pylint: disable=broad-except
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
 
 
 def run_reference(a):
@@ -343,6 +360,8 @@ def main():
                                  "peak_source": "tools/microbench.cu on B200 (scalar FFMA, 124.5 of 128 lanes/clk/SM)"}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline(a, max(1, min(a.cpu_sample_frames, N)), frames=list(host))
+        if world == 1 and not a.no_next_rows:
+            line["next_rows"] = next_rows(a, host)
         print(json.dumps(line))
     lib.ss_host_free(pin)
     lib.ss_host_free(out_pin)

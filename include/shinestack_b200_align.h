@@ -45,6 +45,24 @@ int ssal_warp(ssal_handle *h, const void *src_bgr, size_t src_pitch_bytes, const
 int ssal_warp_device(ssal_handle *h, const void *d_src_bgr, size_t src_pitch_bytes, const double *m, int transform,
                      int border_mode, const double *border_value, const int32_t *blur_kernel, int blur_taps,
                      void *dst_bgr, size_t dst_pitch_bytes);
+/* ---- gradient-based estimator (BASELINE.json north-star: "the ECC/feature alignment pre-pass becomes a CUDA
+ * warp-reduction over image gradients").  Optional replacement of the host-side feature pipeline
+ * detect_and_compute + find_transform (align.py:89-148) for constants.ALIGN_RIGID: enhanced-correlation-
+ * coefficient iterations on 8-bit gray pyramids, one reduction pass over the image gradients per iteration.
+ * The reference has no such estimator; its accuracy contract is the reference's own precision test
+ * (tests/test_0031_align_precision.py:62-65). */
+/* The frame the following frames are aligned to (AlignFrames.run_frame: process.img_ref(ref_idx)). */
+int ssal_ecc_set_reference(ssal_handle *h, const void *ref_bgr, size_t pitch_bytes);
+/* Estimates the forward 2x3 similarity m_out (6 doubles; moving frame -> reference frame, what
+ * cv2.estimateAffinePartial2D returns in the reference) of mov_bgr.  finest_level: pyramid level at which the
+ * refinement stops (0 = full resolution, 1 = half, like the reference's default subsample = 2; < 0 = default 1);
+ * max_iters per level (<= 0: 30); eps_px: stop when a step moves no pixel by more than this (<= 0: 1e-3);
+ * init_m: optional initial forward transform.  info (4 doubles, may be NULL): correlation coefficient, total
+ * iterations, overlap fraction, last step in pixels.  The uploaded frame stays on the device: a following
+ * ssal_warp with src_bgr == NULL warps it without a second upload. */
+int ssal_ecc_estimate(ssal_handle *h, const void *mov_bgr, size_t pitch_bytes, int finest_level, int max_iters,
+                      double eps_px, const double *init_m, double *m_out, double *info);
+
 /* Device address and row pitch of the last aligned frame (valid until the next ssal_warp on this handle). */
 int ssal_result_device(ssal_handle *h, const void **d_bgr, size_t *pitch_bytes);
 /* Device time of the last warp (CUDA events around its kernels) and kernels launched so far. */

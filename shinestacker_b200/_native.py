@@ -136,6 +136,8 @@ SIGNATURES_ALIGN = {
     "ssal_destroy": (None, [_vp]),
     "ssal_warp": (_i, [_vp, _vp, _sz, _dp, _i, _i, _dp, _ip, _i, _vp, _sz]),
     "ssal_warp_device": (_i, [_vp, _vp, _sz, _dp, _i, _i, _dp, _ip, _i, _vp, _sz]),
+    "ssal_ecc_set_reference": (_i, [_vp, _vp, _sz]),
+    "ssal_ecc_estimate": (_i, [_vp, _vp, _sz, _i, _i, ctypes.c_double, _dp, _dp, _dp]),
     "ssal_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ssal_kernel_time_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "ssal_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),

@@ -54,6 +54,12 @@ DEFAULT_ALIGNMENT_CONFIG = {'transform': ALIGN_RIGID, 'align_method': ALIGN_RANS
                             'border_mode': BORDER_REPLICATE_BLUR, 'border_value': [0] * 4, 'border_blur': 50,
                             'subsample': 2, 'fast_subsampling': False, 'min_good_matches': 100}
 
+# extra keys of alignment_config in this mirror (not reference options): which estimator fits the transform
+# ('features' = the reference's cv2 pipeline on the host, 'ecc' = gradient-based fit on the GPU) and its knobs
+ESTIMATOR_FEATURES, ESTIMATOR_ECC = "features", "ecc"
+DEFAULT_ALIGNMENT_CONFIG.update({'estimator': ESTIMATOR_FEATURES, 'ecc_finest_level': 0, 'ecc_max_iters': 30,
+                                 'ecc_eps': 1e-3})
+
 _BORDER_CODE = {BORDER_CONSTANT: 0, BORDER_REPLICATE: 1, BORDER_REPLICATE_BLUR: 2}
 _BLUR_KSIZE = 21      # align.py:249: cv2.GaussianBlur(img_warp, (21, 21), sigmaX=border_blur)
 
@@ -226,10 +232,8 @@ class Warper:
              border_blur=50, download=True):
         """align.py:228-251 for one frame; returns the aligned image (or None with download=False: the frame
         then stays in HBM, see ``result_device``)."""
-        if img.shape[:2] != self.shape or img.ndim != 3 or img.shape[2] != 3:
-            raise ShapeError(self.shape, img.shape[:2])
-        if img.dtype != self.dtype:
-            raise BitDepthError(self.dtype, img.dtype)
+        if img is not None:     # None: warp the frame the last ecc_estimate uploaded
+            self._check_frame(img)
         try:
             mode = _BORDER_CODE[border_mode]
         except KeyError as e:
@@ -250,10 +254,12 @@ class Warper:
         bval = np.zeros(4, np.float64)
         bv = np.asarray(border_value, np.float64).ravel()
         bval[:min(4, bv.size)] = bv[:4]
-        img = np.ascontiguousarray(img)
-        out = np.empty_like(img) if download else None
+        if img is not None:
+            img = np.ascontiguousarray(img)
+        out = np.empty(self.shape + (3,), self.dtype) if download else None
         _check(self._lib.ssal_warp(
-            self._h, img.ctypes.data_as(ctypes.c_void_p), img.strides[0],
+            self._h, img.ctypes.data_as(ctypes.c_void_p) if img is not None else None,
+            img.strides[0] if img is not None else 0,
             mat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), code, mode,
             bval.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             ktab.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if ktab is not None else None, taps,
@@ -262,6 +268,38 @@ class Warper:
         _check(self._lib.ssal_kernel_time_ms(self._h, ctypes.byref(ms)))
         self.last_kernel_ms = ms.value
         return out
+
+    # ---- gradient-based estimator (ssal_ecc_*) -----------------------------------------------------------------
+    def ecc_set_reference(self, img):
+        """The frame the following frames are aligned to (uploaded once; its gray pyramid stays in HBM)."""
+        self._check_frame(img)
+        img = np.ascontiguousarray(img)
+        _check(self._lib.ssal_ecc_set_reference(self._h, img.ctypes.data_as(ctypes.c_void_p), img.strides[0]))
+
+    def ecc_estimate(self, img, finest_level=0, max_iters=30, eps_px=1e-3, init_m=None):
+        """Forward 2x3 similarity (moving -> reference frame, like cv2.estimateAffinePartial2D) of ``img`` by
+        ECC iterations on the GPU; returns ``(m, info)`` with info = dict(rho, iterations, overlap, last_step).
+        The frame stays on the device: ``warp(None, m, ...)`` then warps it without a second upload."""
+        self._check_frame(img)
+        img = np.ascontiguousarray(img)
+        m = np.zeros(6, np.float64)
+        info = np.zeros(4, np.float64)
+        init = None if init_m is None else np.ascontiguousarray(np.asarray(init_m, np.float64).reshape(6))
+        dp = ctypes.POINTER(ctypes.c_double)
+        _check(self._lib.ssal_ecc_estimate(self._h, img.ctypes.data_as(ctypes.c_void_p), img.strides[0],
+                                           int(finest_level), int(max_iters), float(eps_px),
+                                           init.ctypes.data_as(dp) if init is not None else None,
+                                           m.ctypes.data_as(dp), info.ctypes.data_as(dp)))
+        ms = ctypes.c_float()
+        _check(self._lib.ssal_kernel_time_ms(self._h, ctypes.byref(ms)))
+        self.last_kernel_ms = ms.value
+        return m.reshape(2, 3), dict(rho=info[0], iterations=int(info[1]), overlap=info[2], last_step=info[3])
+
+    def _check_frame(self, img):
+        if img.shape[:2] != self.shape or img.ndim != 3 or img.shape[2] != 3:
+            raise ShapeError(self.shape, img.shape[:2])
+        if img.dtype != self.dtype:
+            raise BitDepthError(self.dtype, img.dtype)
 
     def result_device(self):
         """(device pointer, row pitch) of the last aligned frame, for ss_push_frame_device."""
@@ -287,7 +325,10 @@ def align_images(img_1, img_0, feature_config=None, matching_config=None, alignm
     """reference align.py:170-252: align ``img_0`` onto the reference frame ``img_1``.
 
     Returns ``(n_good_matches, m, img_warp)`` like the reference (``m``/``img_warp`` are None when there are too
-    few matches).  ``plot_path`` (a matches plot, matplotlib) is not produced by this mirror."""
+    few matches).  ``plot_path`` (a matches plot, matplotlib) is not produced by this mirror.
+    ``alignment_config['estimator'] = 'ecc'`` (not a reference option) replaces the feature pipeline by the
+    gradient-based estimator on the GPU (ALIGN_RIGID only); the first return value is then the number of
+    overlapping pixels."""
     fcfg = _merged(DEFAULT_FEATURE_CONFIG, feature_config)
     mcfg = _merged(DEFAULT_MATCHING_CONFIG, matching_config)
     acfg = _merged(DEFAULT_ALIGNMENT_CONFIG, alignment_config)
@@ -304,6 +345,11 @@ def align_images(img_1, img_0, feature_config=None, matching_config=None, alignm
         raise BitDepthError(img_1.dtype, img_0.dtype)
     if 'message' in callbacks:
         callbacks['message']()
+    if acfg.get('estimator', ESTIMATOR_FEATURES) == ESTIMATOR_ECC:
+        return _align_images_ecc(img_1, img_0, acfg, callbacks, device)
+    if acfg.get('estimator', ESTIMATOR_FEATURES) != ESTIMATOR_FEATURES:
+        raise InvalidOptionError("estimator", acfg['estimator'],
+                                 f". Valid options are: {ESTIMATOR_FEATURES}, {ESTIMATOR_ECC}")
     subsample = acfg['subsample']
     while True:
         if subsample > 1:
@@ -337,6 +383,38 @@ def align_images(img_1, img_0, feature_config=None, matching_config=None, alignm
     return n_good, m, img_warp
 
 
+ECC_MIN_RHO = 0.2     # below this correlation the ECC fit is reported as a failed alignment
+
+
+def _align_images_ecc(img_1, img_0, acfg, callbacks, device, reference_is_set=False):
+    """align_images with the gradient-based estimator: both the fit and the warp run on the GPU, the moving
+    frame is uploaded once.  Returns (overlapping pixels, m, img_warp) or (0, None, None) when the fit fails."""
+    if acfg['transform'] != ALIGN_RIGID:
+        raise InvalidOptionError("transform", acfg['transform'],
+                                 details=" the ecc estimator fits the ALIGN_RIGID similarity only")
+    wp = _warper_for(img_0, device)
+    if not reference_is_set:
+        wp.ecc_set_reference(img_1)
+    try:
+        m, info = wp.ecc_estimate(img_0, finest_level=acfg.get('ecc_finest_level', 0),
+                                  max_iters=acfg.get('ecc_max_iters', 30), eps_px=acfg.get('ecc_eps', 1e-3))
+    except FocusStackError as e:
+        if 'warning' in callbacks:
+            callbacks['warning'](f"ecc estimator failed: {e}")
+        return 0, None, None
+    n_px = int(info['overlap'] * img_0.shape[0] * img_0.shape[1])
+    if 'matches_message' in callbacks:
+        callbacks['matches_message'](n_px)
+    if not info['rho'] >= ECC_MIN_RHO:
+        return 0, None, None
+    if 'align_message' in callbacks:
+        callbacks['align_message']()
+    if acfg['border_mode'] == BORDER_REPLICATE_BLUR and 'blur_message' in callbacks:
+        callbacks['blur_message']()
+    out = wp.warp(None, m, ALIGN_RIGID, acfg['border_mode'], acfg['border_value'], acfg['border_blur'])
+    return n_px, m, out
+
+
 class AlignFrames:
     """Sub-action with the interface of the reference ``AlignFrames`` (align.py:254-353; ``SubAction``,
     stack_framework.py:235-243).  ``plot_summary`` / ``plot_matches`` are accepted and ignored."""
@@ -357,10 +435,12 @@ class AlignFrames:
                 if key in kwargs:
                     cfg[key] = kwargs[key]
         self.min_matches = 4 if self.alignment_config['transform'] == ALIGN_HOMOGRAPHY else 3
+        self._ecc_ref = None
 
     def begin(self, process):
         self.process = process
         self.n_matches = np.zeros(process.counts)
+        self._ecc_ref = None
 
     def end(self):
         pass
@@ -371,9 +451,11 @@ class AlignFrames:
     def run_frame(self, idx, ref_idx, img_0):
         if idx == self.process.ref_idx:
             return img_0
-        return self.align_images(idx, self.process.img_ref(ref_idx), img_0)
+        if self.alignment_config['estimator'] == ESTIMATOR_ECC and self._ecc_ref == (ref_idx, img_0.shape, img_0.dtype):
+            return self.align_images(idx, None, img_0)      # the reference pyramid is already in HBM
+        return self.align_images(idx, self.process.img_ref(ref_idx), img_0, ref_idx)
 
-    def align_images(self, idx, img_1, img_0):
+    def align_images(self, idx, img_1, img_0, ref_idx=None):
         callbacks = {
             'message': lambda: self.sub_msg(': find matches'),
             'matches_message': lambda n: self.sub_msg(f": good matches: {n}"),
@@ -381,10 +463,17 @@ class AlignFrames:
             'blur_message': lambda: self.sub_msg(': blur borders'),
             'warning': lambda msg: self.sub_msg(f': {msg}'),
         }
-        n_good, _m, img = align_images(img_1, img_0, feature_config=self.feature_config,
-                                       matching_config=self.matching_config,
-                                       alignment_config=self.alignment_config, callbacks=callbacks,
-                                       device=self.device)
+        if self.alignment_config['estimator'] == ESTIMATOR_ECC:
+            callbacks['message']()
+            n_good, _m, img = _align_images_ecc(img_1, img_0, self.alignment_config, callbacks, self.device,
+                                                reference_is_set=img_1 is None)
+            if img_1 is not None and ref_idx is not None:
+                self._ecc_ref = (ref_idx, img_0.shape, img_0.dtype)
+        else:
+            n_good, _m, img = align_images(img_1, img_0, feature_config=self.feature_config,
+                                           matching_config=self.matching_config,
+                                           alignment_config=self.alignment_config, callbacks=callbacks,
+                                           device=self.device)
         self.n_matches[idx] = n_good
         if n_good < self.min_matches:
             self.process.sub_message(f": image not aligned, too few matches found: {n_good}",

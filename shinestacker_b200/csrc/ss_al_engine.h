@@ -5,6 +5,7 @@
 #pragma once
 #include "ss_al_kernels.cuh"
 #include "ss_dm_engine.h"
+#include "ss_ecc_engine.h"
 
 enum { AL_RIGID = 0, AL_HOMOGRAPHY = 1 };
 enum { AL_BORDER_CONSTANT = 0, AL_BORDER_REPLICATE = 1, AL_BORDER_REPLICATE_BLUR = 2 };
@@ -19,6 +20,8 @@ struct AlEngine {
     const uint8_t *result = nullptr;
     std::vector<int> tab;
     char err[256];
+    EccEstimator<Backend> ecc;          // allocated on first use
+    bool ecc_ready = false, src_valid = false;
 
     int fail(int code, const char *msg) { snprintf(err, sizeof(err), "%s", msg); return code; }
 
@@ -43,6 +46,7 @@ struct AlEngine {
     void destroy()
     {
         be.sync();
+        if (ecc_ready) { ecc.destroy(); ecc_ready = false; }
         void *ptrs[] = {d_src, d_warp, d_out, d_mask, d_tab};
         for (void *p : ptrs) if (p) be.free(p);
         d_src = d_warp = d_out = d_mask = nullptr; d_tab = nullptr;
@@ -115,11 +119,51 @@ struct AlEngine {
         return DM_OK;
     }
 
+    int ecc_prepare()
+    {
+        if (ecc_ready) return DM_OK;
+        const int rc = ecc.init(&be, h, w, bps);
+        if (rc) { snprintf(err, sizeof(err), "%s", ecc.err); ecc.destroy(); return rc; }
+        ecc_ready = true;
+        return DM_OK;
+    }
+
+    // the frame every later frame is aligned to (AlignFrames.run_frame: process.img_ref(ref_idx), align.py:283-287)
+    int ecc_set_reference(const void *src, size_t spitch, int on_device)
+    {
+        if (!src) return fail(DM_ERR_INVALID_OPTION, "null argument");
+        if (spitch < pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
+        int rc = ecc_prepare();
+        if (rc) return rc;
+        if ((rc = be.upload_frame(d_src, pitch, src, spitch, pitch, h, on_device))) return fail(rc, be.last_error());
+        src_valid = false;
+        if ((rc = ecc.set_reference(d_src, pitch))) return fail(rc, ecc.err);
+        rc = be.sync();
+        return rc ? fail(rc, be.last_error()) : DM_OK;
+    }
+
+    // gradient-based replacement of detect_and_compute + find_transform (align.py:89-148) for ALIGN_RIGID; the
+    // uploaded frame stays in d_src so that warp(src = NULL, ...) can warp it without a second upload
+    int ecc_estimate(const void *src, size_t spitch, int on_device, int finest_level, int max_iters, double eps_px,
+                     const double *init_m, double *m_out, double *info)
+    {
+        if (!src || !m_out) return fail(DM_ERR_INVALID_OPTION, "null argument");
+        if (spitch < pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
+        int rc = ecc_prepare();
+        if (rc) return rc;
+        be.mark_start();
+        if ((rc = be.upload_frame(d_src, pitch, src, spitch, pitch, h, on_device))) return fail(rc, be.last_error());
+        src_valid = true;
+        if ((rc = ecc.estimate(d_src, pitch, finest_level, max_iters, eps_px, init_m, m_out, info))) return fail(rc, ecc.err);
+        be.mark_end();
+        return DM_OK;
+    }
+
     // replaces align.py:228-251 for one frame; dst_host may be NULL (result stays on the device)
     int warp(const void *src, size_t spitch, int src_on_device, const double *m, int transform, int border_mode,
              const double *bval, const int *kernel, int taps, void *dst_host, size_t dpitch)
     {
-        if (!src || !m) return fail(DM_ERR_INVALID_OPTION, "null argument");
+        if (!m || (!src && !src_valid)) return fail(DM_ERR_INVALID_OPTION, "null argument");
         if (transform != AL_RIGID && transform != AL_HOMOGRAPHY) return fail(DM_ERR_INVALID_OPTION, "transform");
         if (border_mode < 0 || border_mode > 2) return fail(DM_ERR_INVALID_OPTION, "border_mode");
         if (border_mode == AL_BORDER_REPLICATE_BLUR) {
@@ -129,10 +173,14 @@ struct AlEngine {
             for (int i = 0; i < taps; ++i) sum += kernel[i];
             if (sum != (bps == 1 ? 256 : 65536)) return fail(DM_ERR_INVALID_OPTION, "blur kernel must sum to 1.0 in fixed point");
         }
-        if (spitch < pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
+        if (src && spitch < pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
         be.mark_start();
-        int rc = be.upload_frame(d_src, pitch, src, spitch, pitch, h, src_on_device);
-        if (rc) return fail(rc, be.last_error());
+        int rc = 0;
+        if (src) {      // src == NULL: warp the frame the last ecc_estimate uploaded
+            rc = be.upload_frame(d_src, pitch, src, spitch, pitch, h, src_on_device);
+            if (rc) return fail(rc, be.last_error());
+            src_valid = true;
+        }
         rc = bps == 1 ? run<uint8_t>(m, transform, border_mode, bval, kernel, taps)
                       : run<uint16_t>(m, transform, border_mode, bval, kernel, taps);
         if (rc) return fail(rc, rc == DM_ERR_INVALID_OPTION ? "singular transform" : be.last_error());

@@ -69,6 +69,20 @@ SS_EXPORT int ssal_warp_device(ssal_handle *h, const void *src, size_t spitch, c
 {
     return ssal_warp_any(h, src, spitch, 1, m, transform, border_mode, bval, kernel, taps, dst, dpitch);
 }
+SS_EXPORT int ssal_ecc_set_reference(ssal_handle *h, const void *ref_bgr, size_t pitch)
+{
+    SSAL_ENTER(h);
+    const int rc = h->eng.ecc_set_reference(ref_bgr, pitch, 0);
+    return rc ? ss_fail(rc, "%s", h->eng.err) : SS_OK;
+}
+SS_EXPORT int ssal_ecc_estimate(ssal_handle *h, const void *mov_bgr, size_t pitch, int finest_level, int max_iters,
+                                double eps_px, const double *init_m, double *m_out, double *info)
+{
+    SSAL_ENTER(h);
+    h->eng.be.reset_timing();
+    const int rc = h->eng.ecc_estimate(mov_bgr, pitch, 0, finest_level, max_iters, eps_px, init_m, m_out, info);
+    return rc ? ss_fail(rc, "%s", h->eng.err) : SS_OK;
+}
 SS_EXPORT int ssal_result_device(ssal_handle *h, const void **d_bgr, size_t *pitch)
 {
     if (!h || !d_bgr || !pitch) return ss_fail(SS_ERR_STATE, "null argument");

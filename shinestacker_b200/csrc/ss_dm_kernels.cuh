@@ -311,6 +311,24 @@ struct DmLevelSrc {
 // cv2.pyrDown (depth_map.py:101-102): row = 6*s[2x] + 4*(s[2x-1] + s[2x+1]) + s[2x-2] + s[2x+2] on five
 // source rows (REFLECT101), then the same vertically, * 1/256.  One call computes all four planes (B, G, R,
 // weight) of one output pixel: the ten reflected source indices are shared by the planes.
+template <typename P>
+SS_DEV float dm_pyrdown_px(const P *const *rows, const int *xo)
+{
+    float r[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const P *p = rows[i];
+        const float s1 = ss_add((float)p[xo[1]], (float)p[xo[2]]);
+        float acc = ss_add(ss_mul((float)p[xo[0]], 6.f), ss_mul(s1, 4.f));
+        acc = ss_add(acc, (float)p[xo[3]]);
+        r[i] = ss_add(acc, (float)p[xo[4]]);
+    }
+    float acc = ss_add(ss_mul(r[0], 6.f), ss_mul(ss_add(r[1], r[2]), 4.f));
+    acc = ss_add(acc, r[3]);
+    acc = ss_add(acc, r[4]);
+    return ss_mul(acc, 0.00390625f);
+}
+
 template <typename InT>
 struct DmPyrDown {
     DmLevelSrc<InT> src; int h2, w2; float *out /* 4 planes h2 x w2 */;
@@ -324,22 +342,35 @@ struct DmPyrDown {
         if (y >= 2 && y + 2 < h) { ys[0] = y; ys[1] = y - 1; ys[2] = y + 1; ys[3] = y - 2; ys[4] = y + 2; }
         else { ys[0] = y; ys[1] = dm_reflect101(y - 1, h); ys[2] = dm_reflect101(y + 1, h);
                ys[3] = dm_reflect101(y - 2, h); ys[4] = dm_reflect101(y + 2, h); }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float r[5];
+        const long long o = (long long)y2 * w2 + x2, plane2 = (long long)h2 * w2;
+        if (src.frame) {    // level 0: interleaved integer frame, the three channels share row pointers
+            const InT *rows[5];
+            int xo[5];
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                const int yy = ys[i];
-                const float s1 = ss_add(src.at(c, xs[1], yy), src.at(c, xs[2], yy));
-                float acc = ss_add(ss_mul(src.at(c, xs[0], yy), 6.f), ss_mul(s1, 4.f));
-                acc = ss_add(acc, src.at(c, xs[3], yy));
-                r[i] = ss_add(acc, src.at(c, xs[4], yy));
+                rows[i] = (const InT *)((const char *)src.frame + (long long)ys[i] * src.pitch);
+                xo[i] = 3 * xs[i];
             }
-            float acc = ss_add(ss_mul(r[0], 6.f), ss_mul(ss_add(r[1], r[2]), 4.f));
-            acc = ss_add(acc, r[3]);
-            acc = ss_add(acc, r[4]);
-            out[((long long)c * h2 + y2) * w2 + x2] = ss_mul(acc, 0.00390625f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                out[c * plane2 + o] = dm_pyrdown_px<InT>(rows, xo);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) ++rows[i];
+            }
+        } else {
+            const long long plane = (long long)h * w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float *rows[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) rows[i] = src.planes + c * plane + (long long)ys[i] * w;
+                out[c * plane2 + o] = dm_pyrdown_px<float>(rows, xs);
+            }
         }
+        const float *rows[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) rows[i] = src.weight + (long long)ys[i] * w;
+        out[3 * plane2 + o] = dm_pyrdown_px<float>(rows, xs);
     }
 };
 

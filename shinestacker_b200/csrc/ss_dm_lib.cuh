@@ -3,6 +3,7 @@
 #pragma once
 #include "../../include/shinestack_b200_depthmap.h"
 #include "ss_dm_engine.h"
+#include "ss_ecc_kernels.cuh"
 
 struct DmCudaBackend {
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -92,6 +93,24 @@ struct DmCudaBackend {
         DM_CUDA(cudaGetLastError());
         ++launches;
         return 0;
+    }
+    // one ECC iteration: zero the 28 device sums, one persistent-grid pass, bring the sums back
+    int ecc_accumulate(const EccParams &p, double *d_sums, double *host_sums)
+    {
+        static int n_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            DM_CUDA(cudaGetDevice(&dev));
+            DM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        DM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * ECC_NSUMS, s_comp));
+        const long long n = (long long)p.h * p.w;
+        long long blocks = (n + 255) / 256;
+        if (blocks > 4LL * n_sm) blocks = 4LL * n_sm;     // 4 resident CTAs of 256 threads per SM
+        ecc_accumulate_kernel<<<(int)blocks, 256, 0, s_comp>>>(p, d_sums);
+        DM_CUDA(cudaGetLastError());
+        ++launches;
+        return download(host_sums, d_sums, sizeof(double) * ECC_NSUMS);
     }
     int elapsed_ms(float *ms)
     {

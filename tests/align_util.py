@@ -43,6 +43,41 @@ TRANSFORMS = [
 ]
 
 
+def transform_error(m, m_true, shape):
+    """(angle difference in degrees, scale difference, displacement difference at the image centre in pixels):
+    the three quantities the reference's precision test bounds (tests/test_0031_align_precision.py:50-65)."""
+    ang = np.degrees(np.arctan2(m[1, 0], m[0, 0]) - np.arctan2(m_true[1, 0], m_true[0, 0]))
+    scale = np.hypot(m[0, 0], m[1, 0]) - np.hypot(m_true[0, 0], m_true[1, 0])
+    c = np.array([shape[1] / 2.0, shape[0] / 2.0, 1.0])
+    return abs(ang), abs(scale), float(np.abs(m @ c - m_true @ c).max())
+
+
+def textured_scene(h, w, seed=9, blur=1.0):
+    """Shapes + noise, slightly blurred (a photographic frame is band-limited too)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w, 3), np.uint8)
+    for _ in range(max(40, h * w // 6000)):
+        c = tuple(int(v) for v in rng.integers(60, 255, 3))
+        p = (int(rng.integers(0, w)), int(rng.integers(0, h)))
+        if rng.random() < 0.5:
+            cv2.circle(img, p, int(rng.integers(5, 40)), c, int(rng.integers(1, 4)))
+        else:
+            q = (int(rng.integers(0, w)), int(rng.integers(0, h)))
+            cv2.rectangle(img, p, q, c, int(rng.integers(1, 3)))
+    img = cv2.add(img, rng.integers(0, 12, img.shape).astype(np.uint8))
+    return cv2.GaussianBlur(img, (0, 0), blur) if blur > 0 else img
+
+
+def moved_frame(img, angle_deg, scale, tx, ty):
+    """Returns (moving frame, forward transform that aligns it back onto img)."""
+    import cv2
+    h, w = img.shape[:2]
+    t = cv2.getRotationMatrix2D((w / 2.0, h / 2.0), angle_deg, scale)
+    t[:, 2] += (tx, ty)
+    return cv2.warpAffine(img, t, (w, h), borderMode=cv2.BORDER_REPLICATE), cv2.invertAffineTransform(t)
+
+
 class EmuWarper:
     _lib = None
 
@@ -66,6 +101,8 @@ class EmuWarper:
             lib.emu_al_error.restype = ctypes.c_char_p
             lib.emu_al_error.argtypes = [vp]
             lib.emu_al_warp.argtypes = [vp, vp, sz, vp, i, i, vp, vp, i, vp, sz]
+            lib.emu_al_ecc_set_reference.argtypes = [vp, vp, sz]
+            lib.emu_al_ecc_estimate.argtypes = [vp, vp, sz, i, i, ctypes.c_double, vp, vp, vp]
             cls._lib = lib
         return cls._lib
 
@@ -86,6 +123,21 @@ class EmuWarper:
         if rc:
             raise ValueError(self.lib_.emu_al_error(self.p).decode())
         return out
+
+    def ecc_set_reference(self, img):
+        img = np.ascontiguousarray(img)
+        if self.lib_.emu_al_ecc_set_reference(self.p, img.ctypes.data, img.strides[0]):
+            raise ValueError(self.lib_.emu_al_error(self.p).decode())
+
+    def ecc_estimate(self, img, finest_level=0, max_iters=30, eps_px=1e-3, init_m=None):
+        img = np.ascontiguousarray(img)
+        m, info = np.zeros(6), np.zeros(4)
+        init = None if init_m is None else np.ascontiguousarray(np.asarray(init_m, np.float64).reshape(6))
+        rc = self.lib_.emu_al_ecc_estimate(self.p, img.ctypes.data, img.strides[0], finest_level, max_iters, eps_px,
+                                           init.ctypes.data if init is not None else None, m.ctypes.data, info.ctypes.data)
+        if rc:
+            raise ValueError(self.lib_.emu_al_error(self.p).decode())
+        return m.reshape(2, 3), dict(rho=info[0], iterations=int(info[1]), overlap=info[2], last_step=info[3])
 
     def close(self):
         if self.p:

@@ -22,5 +22,11 @@ int emu_al_warp(void *p, const void *src, size_t spitch, const double *m, int tr
 {
     return ((Emu *)p)->warp(src, spitch, 0, m, transform, border_mode, bval, kernel, taps, dst, dpitch);
 }
+int emu_al_ecc_set_reference(void *p, const void *ref, size_t pitch) { return ((Emu *)p)->ecc_set_reference(ref, pitch, 0); }
+int emu_al_ecc_estimate(void *p, const void *mov, size_t pitch, int finest, int max_iters, double eps, const double *init_m,
+                        double *m_out, double *info)
+{
+    return ((Emu *)p)->ecc_estimate(mov, pitch, 0, finest, max_iters, eps, init_m, m_out, info);
+}
 const char *emu_al_error(void *p) { return ((Emu *)p)->err; }
 }

@@ -24,6 +24,19 @@ struct DmHostBackend {
         for (int y = 0; y < rows; ++y) memcpy((char *)dst + y * dpitch, (const char *)src + y * spitch, row_bytes);
         return 0;
     }
+#ifdef ECC_NSUMS
+    int ecc_accumulate(const EccParams &p, double *, double *host_sums)
+    {
+        for (int i = 0; i < ECC_NSUMS; ++i) host_sums[i] = 0;
+        float s[ECC_NSUMS];
+        for (int y = 0; y < p.h; ++y)
+            for (int x = 0; x < p.w; ++x)
+                if (ecc_pixel(p, x, y, s))
+                    for (int i = 0; i < ECC_NSUMS; ++i) host_sums[i] += s[i];
+        ++launches;
+        return 0;
+    }
+#endif
     template <class K>
     int launch(const K &k, int w, int h, int z)
     {

@@ -136,10 +136,13 @@ def next_rows(a, host):
     stage (one frame: warp + mask + 21x21 blur fill) with cv2 on the host cores beside it."""
     out = {}
     try:
-        from tools import time_depthmap, time_align
+        from tools import time_depthmap, time_align, time_ecc, time_pipeline
         out["depth_map"] = time_depthmap.measure(a.frames, a.height, a.width, a.dtype, steps=3, warmup=1,
                                                  host=list(host))
         out["align_warp"] = time_align.measure(a.height, a.width, a.dtype, steps=5)
+        if a.dtype == "uint8":
+            out["align_ecc_estimator"] = time_ecc.measure(a.height, a.width, steps=3, with_features=True)
+            out["align_ecc_plus_stack_config5"] = time_pipeline.measure(list(host), steps=2)
     except Exception as e:  # pylint: disable=broad-except
         out["error"] = f"{type(e).__name__}: {e}"
     return out

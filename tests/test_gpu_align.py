@@ -138,3 +138,20 @@ def test_align_frames_sub_action_with_both_estimators():
         if estimator == "ecc":
             assert process.img_ref.call_count == 1      # the reference pyramid stayed in HBM
         action.end()
+
+
+def test_fused_align_and_stack_pipeline_recovers_the_undisplaced_result():
+    from shinestacker_b200.pipeline import align_and_stack_arrays
+    from tools.time_pipeline import displaced_stack
+    frames = synthetic.make_stack(7, 600, 800, np.uint8, 23)
+    moved, truth, _ = displaced_stack(frames)
+    out, ms = align_and_stack_arrays(list(moved), return_transforms=True)
+    c = np.array([400.0, 300.0, 1.0])
+    assert max(np.abs(m @ c - t @ c).max() for m, t in zip(ms, truth)) < 0.1
+    # identical to aligning with cv2 (same matrices) and stacking the aligned files, which is what the reference job does
+    aligned = [f if i == 3 else au.cv2_warp_stage(f, m, "BORDER_REPLICATE_BLUR") for i, (f, m) in enumerate(zip(moved, ms))]
+    assert np.array_equal(out, PyramidStack().focus_stack_arrays(aligned))
+    # and close to the fusion of the undisplaced stack away from the borders
+    plain = PyramidStack().focus_stack_arrays(frames)
+    inner = (slice(60, -60), slice(60, -60))
+    assert np.abs(out[inner].astype(int) - plain[inner].astype(int)).mean() < 4.0

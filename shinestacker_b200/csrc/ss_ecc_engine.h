@@ -51,7 +51,7 @@ struct EccEstimator {
         err[0] = 0;
         L = 1;
         lh[0] = h; lw[0] = w;
-        while (L < ECC_MAX_LEVELS && (lh[L - 1] + 1) / 2 >= 48 && (lw[L - 1] + 1) / 2 >= 48) {
+        while (L < ECC_MAX_LEVELS && (lh[L - 1] + 1) / 2 >= 32 && (lw[L - 1] + 1) / 2 >= 32) {
             lh[L] = (lh[L - 1] + 1) / 2; lw[L] = (lw[L - 1] + 1) / 2; ++L;
         }
         int rc;
@@ -131,34 +131,72 @@ struct EccEstimator {
             double tx = dx + a * cx - b * cy - cx, ty = dy + b * cx + a * cy - cy;
             const double radius = 0.5 * sqrt((double)ww * ww + (double)hh * hh);
             double mean_r = 0, mean_w = 0;
-            for (int it = 0; it < max_iters; ++it) {
+            double S[ECC_NSUMS];
+            auto pass = [&](double pa, double pb, double ptx, double pty) -> int {
                 EccParams p;
                 p.ref = ref[l]; p.mov = mov[l]; p.gx = gx; p.gy = gy; p.h = hh; p.w = ww;
-                p.a = (float)a; p.b = (float)b; p.tx = (float)tx; p.ty = (float)ty; p.cx = (float)cx; p.cy = (float)cy;
+                p.a = (float)pa; p.b = (float)pb; p.tx = (float)ptx; p.ty = (float)pty; p.cx = (float)cx; p.cy = (float)cy;
                 p.mean_r = (float)mean_r; p.mean_w = (float)mean_w;
-                double S[ECC_NSUMS];
-                if ((rc = be->ecc_accumulate(p, d_sums, S))) return fail(rc, be->last_error());
                 ++total;
+                return be->ecc_accumulate(p, d_sums, S);
+            };
+            auto correlation = [&]() -> double {    // of the zero-mean samples over the overlap; -2 = unusable
                 const double n = S[27];
+                if (n < 64) return -2.0;
+                const double mw = S[25] / n, mr = S[26] / n;
+                const double sww = S[22] - n * mw * mw, srw = S[23] - n * mw * mr, srr = S[24] - n * mr * mr;
+                return sww > 0 && srr > 0 ? srw / sqrt(sww * srr) : -2.0;
+            };
+            if (l == L - 1 && !init_m) {
+                // coarsest level: exhaustive search over whole-pixel shifts (+-4 px here = +-4 * 2^(L-1) px at full
+                // resolution) so that the iterations start inside the basin of the right optimum even on
+                // content without low frequencies
+                double best = -3, btx = tx, bty = ty;
+                for (int sy = -4; sy <= 4; ++sy)
+                    for (int sx = -4; sx <= 4; ++sx) {
+                        if ((rc = pass(a, b, tx + sx, ty + sy))) return fail(rc, be->last_error());
+                        const double r = correlation();
+                        if (r > best) { best = r; btx = tx + sx; bty = ty + sy; }
+                    }
+                tx = btx; ty = bty;
+            }
+            double prev_rho = -3, pa = a, pb = b, ptx = tx, pty = ty, step[4] = {0, 0, 0, 0};
+            int halvings = 0;
+            for (int it = 0; it < max_iters; ++it) {
+                if ((rc = pass(a, b, tx, ty))) return fail(rc, be->last_error());
+                const double n = S[27];
+                double r_now = correlation();
+                if (it > 0 && r_now < prev_rho - 1e-4 && halvings < 5) {
+                    // the last step lowered the correlation (or left the frame): retreat to half of it
+                    ++halvings;
+                    for (int i = 0; i < 4; ++i) step[i] *= 0.5;
+                    a = pa + step[0]; b = pb + step[1]; tx = ptx + step[2]; ty = pty + step[3];
+                    continue;
+                }
                 if (n < 64) return fail(DM_ERR_STATE, "ecc: the frames do not overlap");
+                halvings = 0;
                 overlap = n / ((double)hh * ww);
                 const double mw = S[25] / n, mr = S[26] / n;   // means of the offset values over the overlap
                 double Gw[4], Gr[4];
                 for (int i = 0; i < 4; ++i) { Gw[i] = S[10 + i] - mw * S[18 + i]; Gr[i] = S[14 + i] - mr * S[18 + i]; }
                 const double sww = S[22] - n * mw * mw, srw = S[23] - n * mw * mr, srr = S[24] - n * mr * mr;
-                mean_r += mr; mean_w += mw;                    // offsets used by the next pass (less cancellation)
                 if (sww <= 0 || srr <= 0) return fail(DM_ERR_STATE, "ecc: flat image, nothing to align");
                 rho = srw / sqrt(sww * srr);
+                prev_rho = rho; pa = a; pb = b; ptx = tx; pty = ty;
                 double HiGw[4];
                 if (!ecc_solve4(S, Gw, HiGw)) return fail(DM_ERR_STATE, "ecc: singular normal equations");
                 double num = sww, den = srw;
                 for (int i = 0; i < 4; ++i) { num -= Gw[i] * HiGw[i]; den -= Gr[i] * HiGw[i]; }
-                double lambda = den > 0 ? num / den : (srw > 0 ? sww / srw : 1.0);
+                const double lambda = den > 0 ? num / den : (srw > 0 ? sww / srw : 1.0);
                 double rhs[4], dp[4];
                 for (int i = 0; i < 4; ++i) rhs[i] = lambda * Gr[i] - Gw[i];
                 if (!ecc_solve4(S, rhs, dp)) return fail(DM_ERR_STATE, "ecc: singular normal equations");
-                a += dp[0]; b += dp[1]; tx += dp[2]; ty += dp[3];
                 last = sqrt(dp[2] * dp[2] + dp[3] * dp[3]) + radius * sqrt(dp[0] * dp[0] + dp[1] * dp[1]);
+                const double cap = last > 2.0 ? 2.0 / last : 1.0;   // no pixel moves by more than ~2 px per step
+                for (int i = 0; i < 4; ++i) step[i] = dp[i] * cap;
+                a += step[0]; b += step[1]; tx += step[2]; ty += step[3];
+                // the offsets only condition the float sums; keep them fixed after the first pass of a level
+                if (it == 0) { mean_r += mr; mean_w += mw; }
                 if (last < eps_px) break;
             }
             dx = tx - a * cx + b * cy + cx; dy = ty - b * cx - a * cy + cy;

@@ -60,6 +60,7 @@ struct AlEngine {
         k.src = (const T *)d_src; k.spitch = (long long)pitch; k.h = h; k.w = w;
         k.dst = (T *)d_warp; k.dpitch = (long long)pitch;
         k.mask = border_mode == AL_BORDER_REPLICATE_BLUR ? d_mask : nullptr;
+        k.dst2 = border_mode == AL_BORDER_REPLICATE_BLUR ? (T *)d_out : nullptr;
         k.border_const = border_mode == AL_BORDER_CONSTANT;
         const double maxv = bps == 1 ? 255.0 : 65535.0;
         for (int c = 0; c < 3; ++c) {       // saturate_cast<T>(borderValue[c])

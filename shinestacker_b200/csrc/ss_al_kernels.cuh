@@ -37,6 +37,7 @@ struct AlWarp {
     int border_const; int bval[3];               // BORDER_CONSTANT and its value (already saturated to T)
     int float_persp;                             // uint16 + homography: cv2's float path
     T *dst; long long dpitch; uint8_t *mask;     // mask (h x w, nullable): 1 where the warp of ones is non-zero
+    T *dst2;                                     // second copy of the result (nullable): the buffer AlBlurFill patches
 
     SS_MDEV const T *row(int y) const { return (const T *)((const char *)src + (long long)y * spitch); }
     SS_MDEV void operator()(int x, int y, int) const
@@ -62,6 +63,39 @@ struct AlWarp {
                 fX = fX < -2147483648.0 ? -2147483648.0 : (fX > 2147483647.0 ? 2147483647.0 : fX);
                 fY = fY < -2147483648.0 ? -2147483648.0 : (fY > 2147483647.0 ? 2147483647.0 : fY);
                 X = al_rint_ll(fX); Y = al_rint_ll(fY);
+            }
+        }
+        if (!float_persp) {
+            // interior fast path: all four taps inside the image (the overwhelming majority of the pixels)
+            const long long sxi = X >> 5, syi = Y >> 5;
+            if (sxi >= 0 && sxi < w - 1 && syi >= 0 && syi < h - 1) {
+                const int fx = (int)(X & 31), fy = (int)(Y & 31);
+                const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
+                const T *p0 = row((int)syi) + 3 * (int)sxi;
+                const T *p1 = (const T *)((const char *)p0 + spitch);
+                T *o = (T *)((char *)dst + (long long)y * dpitch) + 3 * x;
+                T res[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int v00 = p0[c], v01 = p0[3 + c], v10 = p1[c], v11 = p1[3 + c];
+                    if (sizeof(T) == 1) {
+                        res[c] = (T)(((v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11) * 32 + 16384) >> 15);
+                    } else {
+                        float t = ss_mul((float)v00, ss_mul((float)w00, 0.0009765625f));
+                        t = ss_add(t, ss_mul((float)v01, ss_mul((float)w01, 0.0009765625f)));
+                        t = ss_add(t, ss_mul((float)v10, ss_mul((float)w10, 0.0009765625f)));
+                        t = ss_add(t, ss_mul((float)v11, ss_mul((float)w11, 0.0009765625f)));
+                        t = al_rintf(t);
+                        res[c] = (T)(int)(t > 65535.f ? 65535.f : t);
+                    }
+                }
+                o[0] = res[0]; o[1] = res[1]; o[2] = res[2];
+                if (dst2) {
+                    T *o2 = (T *)((char *)dst2 + (long long)y * dpitch) + 3 * x;
+                    o2[0] = res[0]; o2[1] = res[1]; o2[2] = res[2];
+                }
+                if (mask) mask[(long long)y * w + x] = 1;
+                return;
             }
         }
         long long sxl = X >> 5, syl = Y >> 5;
@@ -103,11 +137,17 @@ struct AlWarp {
                 o[c] = (T)(int)(t > 65535.f ? 65535.f : t);
             }
         }
+        if (dst2) {
+            T *o2 = (T *)((char *)dst2 + (long long)y * dpitch) + 3 * x;
+            o2[0] = o[0]; o2[1] = o[1]; o2[2] = o[2];
+        }
     }
 };
 
-// img_warp[mask == 0] = GaussianBlur(img_warp)[mask == 0] (align.py:249-251): copy where the mask is set,
-// the full 2-D fixed-point sum elsewhere (no intermediate rounding in cv2's separable passes either).
+// img_warp[mask == 0] = GaussianBlur(img_warp)[mask == 0] (align.py:249-251).  `out` already holds a copy of
+// the warped frame (AlWarp's second destination); only the pixels whose mask is 0 are replaced by the full
+// 2-D fixed-point sum (no intermediate rounding in cv2's separable passes either).  A row sum fits 32 bits
+// (uint8: 2^16, uint16: 2^32 - 2^16), the column sum needs 64 bits for uint16 only.
 template <typename T>
 struct AlBlurFill {
     const T *warped; long long wpitch; int h, w; const uint8_t *mask;
@@ -115,21 +155,28 @@ struct AlBlurFill {
     T *out; long long opitch;
     SS_MDEV void operator()(int x, int y, int) const
     {
+        if (mask[(long long)y * w + x]) return;
         T *o = (T *)((char *)out + (long long)y * opitch) + 3 * x;
-        const T *s = (const T *)((const char *)warped + (long long)y * wpitch) + 3 * x;
-        if (mask[(long long)y * w + x]) { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; return; }
         const int r = taps / 2;
         unsigned long long acc[3] = {0, 0, 0};
+        const bool inner_x = x >= r && x + r < w;
         for (int i = 0; i < taps; ++i) {
             const T *line = (const T *)((const char *)warped + (long long)dm_reflect101(y - r + i, h) * wpitch);
-            unsigned long long ra[3] = {0, 0, 0};
-            for (int j = 0; j < taps; ++j) {
-                const T *p = line + 3 * dm_reflect101(x - r + j, w);
-                ra[0] += (unsigned long long)k[j] * p[0];
-                ra[1] += (unsigned long long)k[j] * p[1];
-                ra[2] += (unsigned long long)k[j] * p[2];
+            unsigned ra[3] = {0, 0, 0};
+            if (inner_x) {
+                const T *p = line + 3 * (x - r);
+                for (int j = 0; j < taps; ++j, p += 3) {
+                    const unsigned kj = (unsigned)k[j];
+                    ra[0] += kj * p[0]; ra[1] += kj * p[1]; ra[2] += kj * p[2];
+                }
+            } else {
+                for (int j = 0; j < taps; ++j) {
+                    const T *p = line + 3 * dm_reflect101(x - r + j, w);
+                    const unsigned kj = (unsigned)k[j];
+                    ra[0] += kj * p[0]; ra[1] += kj * p[1]; ra[2] += kj * p[2];
+                }
             }
-            for (int c = 0; c < 3; ++c) acc[c] += (unsigned long long)k[i] * ra[c];
+            for (int c = 0; c < 3; ++c) acc[c] += (unsigned long long)(unsigned)k[i] * ra[c];
         }
         const int shift = sizeof(T) == 1 ? 16 : 32;
         for (int c = 0; c < 3; ++c) o[c] = (T)((acc[c] + (1ull << (shift - 1))) >> shift);

@@ -15,8 +15,8 @@ struct AlEngine {
     Backend be;
     int h = 0, w = 0, bps = 0;
     size_t pitch = 0, frame_bytes = 0;
-    uint8_t *d_src = nullptr, *d_warp = nullptr, *d_out = nullptr, *d_mask = nullptr;
-    int *d_tab = nullptr;
+    uint8_t *d_src = nullptr, *d_warp = nullptr, *d_out = nullptr;
+    int *d_tab = nullptr, *d_fill = nullptr;      // d_fill[0] = number of pixels to fill, d_fill[1..] = their indices
     const uint8_t *result = nullptr;
     std::vector<int> tab;
     char err[256];
@@ -37,7 +37,7 @@ struct AlEngine {
         if ((rc = be.alloc((void **)&d_src, frame_bytes))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_warp, frame_bytes))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_out, frame_bytes))) return fail(rc, be.last_error());
-        if ((rc = be.alloc((void **)&d_mask, (size_t)w * h))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_fill, sizeof(int) * ((size_t)w * h + 1)))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_tab, sizeof(int) * 2 * ((size_t)w + h)))) return fail(rc, be.last_error());
         tab.resize(2 * ((size_t)w + h));
         return DM_OK;
@@ -47,9 +47,9 @@ struct AlEngine {
     {
         be.sync();
         if (ecc_ready) { ecc.destroy(); ecc_ready = false; }
-        void *ptrs[] = {d_src, d_warp, d_out, d_mask, d_tab};
+        void *ptrs[] = {d_src, d_warp, d_out, d_fill, d_tab};
         for (void *p : ptrs) if (p) be.free(p);
-        d_src = d_warp = d_out = d_mask = nullptr; d_tab = nullptr;
+        d_src = d_warp = d_out = nullptr; d_tab = d_fill = nullptr;
     }
 
     template <typename T>
@@ -59,15 +59,18 @@ struct AlEngine {
         memset(&k, 0, sizeof(k));
         k.src = (const T *)d_src; k.spitch = (long long)pitch; k.h = h; k.w = w;
         k.dst = (T *)d_warp; k.dpitch = (long long)pitch;
-        k.mask = border_mode == AL_BORDER_REPLICATE_BLUR ? d_mask : nullptr;
-        k.dst2 = border_mode == AL_BORDER_REPLICATE_BLUR ? (T *)d_out : nullptr;
+        const bool fill = border_mode == AL_BORDER_REPLICATE_BLUR;
+        k.dst2 = fill ? (T *)d_out : nullptr;
+        k.fill_count = fill ? d_fill : nullptr;
+        k.fill_list = fill ? d_fill + 1 : nullptr;
+        int rc;
+        if (fill && (rc = be.zero(d_fill, sizeof(int)))) return rc;
         k.border_const = border_mode == AL_BORDER_CONSTANT;
         const double maxv = bps == 1 ? 255.0 : 65535.0;
         for (int c = 0; c < 3; ++c) {       // saturate_cast<T>(borderValue[c])
             double v = bval ? nearbyint(bval[c]) : 0.0;
             k.bval[c] = (int)(v < 0 ? 0 : (v > maxv ? maxv : v));
         }
-        int rc;
         if (transform == AL_RIGID) {
             // cv2.warpAffine: invert the 2x3 matrix in float64, then fixed-point tables with AB_BITS = 10
             double M[6];
@@ -107,14 +110,14 @@ struct AlEngine {
         }
         if ((rc = be.launch(k, w, h, 1))) return rc;
         result = d_warp;
-        if (border_mode == AL_BORDER_REPLICATE_BLUR) {
-            AlBlurFill<T> b;
+        if (fill) {
+            AlBlurFillList<T> b;
             memset(&b, 0, sizeof(b));
-            b.warped = (const T *)d_warp; b.wpitch = (long long)pitch; b.h = h; b.w = w; b.mask = d_mask;
+            b.warped = (const T *)d_warp; b.wpitch = (long long)pitch; b.h = h; b.w = w; b.list = d_fill + 1;
             b.taps = taps;
             for (int i = 0; i < taps; ++i) b.k[i] = kernel[i];
             b.out = (T *)d_out; b.opitch = (long long)pitch;
-            if ((rc = be.launch(b, w, h, 1))) return rc;
+            if ((rc = be.launch_items(b, d_fill))) return rc;
             result = d_out;
         }
         return DM_OK;

@@ -28,6 +28,24 @@ SS_DEV long long al_rint_ll(double v) { return __double2ll_rn(v); }
 SS_DEV float al_rintf(float v) { return rintf(v); }
 #endif
 
+// list of the pixels the blur has to fill (mask == 0): appended by AlWarp, consumed one warp per pixel
+SS_DEV void al_append(int *counter, int *list, int idx)
+{
+#ifdef SS_HOST_EMU
+    list[(*counter)++] = idx;
+#else
+    list[atomicAdd(counter, 1)] = idx;
+#endif
+}
+SS_DEV unsigned long long al_lane_sum(unsigned long long v)
+{
+#ifndef SS_HOST_EMU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+    return v;
+}
+
 template <typename T>
 struct AlWarp {
     const T *src; long long spitch; int h, w;
@@ -36,8 +54,9 @@ struct AlWarp {
     double m[9];
     int border_const; int bval[3];               // BORDER_CONSTANT and its value (already saturated to T)
     int float_persp;                             // uint16 + homography: cv2's float path
-    T *dst; long long dpitch; uint8_t *mask;     // mask (h x w, nullable): 1 where the warp of ones is non-zero
-    T *dst2;                                     // second copy of the result (nullable): the buffer AlBlurFill patches
+    T *dst; long long dpitch;
+    T *dst2;                                     // second copy of the result (nullable): the buffer the blur fill patches
+    int *fill_count, *fill_list;                 // nullable: pixels whose mask (warp of ones, constant 0 border) is 0
 
     SS_MDEV const T *row(int y) const { return (const T *)((const char *)src + (long long)y * spitch); }
     SS_MDEV void operator()(int x, int y, int) const
@@ -94,7 +113,6 @@ struct AlWarp {
                     T *o2 = (T *)((char *)dst2 + (long long)y * dpitch) + 3 * x;
                     o2[0] = res[0]; o2[1] = res[1]; o2[2] = res[2];
                 }
-                if (mask) mask[(long long)y * w + x] = 1;
                 return;
             }
         }
@@ -110,10 +128,10 @@ struct AlWarp {
         const int cy0 = sy < 0 ? 0 : (sy > h - 1 ? h - 1 : sy), cy1 = sy + 1 < 0 ? 0 : (sy + 1 > h - 1 ? h - 1 : sy + 1);
         const T *r0 = row(cy0), *r1 = row(cy1);
         T *o = (T *)((char *)dst + (long long)y * dpitch) + 3 * x;
-        if (mask) {
+        if (fill_list) {
             int s = 0;
             for (int i = 0; i < 4; ++i) s += inside[i] ? wt[i] : 0;
-            mask[(long long)y * w + x] = s >= 512 ? 1 : 0;
+            if (s < 512) al_append(fill_count, fill_list, y * w + x);
         }
         for (int c = 0; c < 3; ++c) {
             int v[4] = {(int)r0[3 * cx0 + c], (int)r0[3 * cx1 + c], (int)r1[3 * cx0 + c], (int)r1[3 * cx1 + c]};
@@ -145,40 +163,35 @@ struct AlWarp {
 };
 
 // img_warp[mask == 0] = GaussianBlur(img_warp)[mask == 0] (align.py:249-251).  `out` already holds a copy of
-// the warped frame (AlWarp's second destination); only the pixels whose mask is 0 are replaced by the full
-// 2-D fixed-point sum (no intermediate rounding in cv2's separable passes either).  A row sum fits 32 bits
-// (uint8: 2^16, uint16: 2^32 - 2^16), the column sum needs 64 bits for uint16 only.
+// the warped frame (AlWarp's second destination); the listed pixels (thin border strips) are replaced by the
+// full 2-D fixed-point sum (sum_ij k_i k_j p_ij + half) >> shift -- exact integers, so the order of the taps
+// is free: one WARP per pixel, the 441 taps split over its lanes, shuffle reduction.  (One thread per pixel
+// left a long tail: all the heavy pixels sit in a few border CTAs.)  The host build runs item(i, 0, 1).
 template <typename T>
-struct AlBlurFill {
-    const T *warped; long long wpitch; int h, w; const uint8_t *mask;
+struct AlBlurFillList {
+    const T *warped; long long wpitch; int h, w; const int *list;
     int taps; int k[AL_MAX_BLUR_TAPS];
     T *out; long long opitch;
-    SS_MDEV void operator()(int x, int y, int) const
+    SS_MDEV void item(int i, int lane, int nlanes) const
     {
-        if (mask[(long long)y * w + x]) return;
-        T *o = (T *)((char *)out + (long long)y * opitch) + 3 * x;
-        const int r = taps / 2;
-        unsigned long long acc[3] = {0, 0, 0};
-        const bool inner_x = x >= r && x + r < w;
-        for (int i = 0; i < taps; ++i) {
-            const T *line = (const T *)((const char *)warped + (long long)dm_reflect101(y - r + i, h) * wpitch);
-            unsigned ra[3] = {0, 0, 0};
-            if (inner_x) {
-                const T *p = line + 3 * (x - r);
-                for (int j = 0; j < taps; ++j, p += 3) {
-                    const unsigned kj = (unsigned)k[j];
-                    ra[0] += kj * p[0]; ra[1] += kj * p[1]; ra[2] += kj * p[2];
-                }
-            } else {
-                for (int j = 0; j < taps; ++j) {
-                    const T *p = line + 3 * dm_reflect101(x - r + j, w);
-                    const unsigned kj = (unsigned)k[j];
-                    ra[0] += kj * p[0]; ra[1] += kj * p[1]; ra[2] += kj * p[2];
-                }
-            }
-            for (int c = 0; c < 3; ++c) acc[c] += (unsigned long long)(unsigned)k[i] * ra[c];
+        const int idx = list[i];
+        const int y = idx / w, x = idx - y * w, r = taps / 2;
+        unsigned long long acc0 = 0, acc1 = 0, acc2 = 0;
+        for (int t = lane; t < taps * taps; t += nlanes) {
+            const int ti = t / taps, tj = t - ti * taps;
+            const T *p = (const T *)((const char *)warped + (long long)dm_reflect101(y - r + ti, h) * wpitch) +
+                         3 * dm_reflect101(x - r + tj, w);
+            const unsigned long long kk = (unsigned long long)(unsigned)k[ti] * (unsigned)k[tj];
+            acc0 += kk * p[0]; acc1 += kk * p[1]; acc2 += kk * p[2];
         }
-        const int shift = sizeof(T) == 1 ? 16 : 32;
-        for (int c = 0; c < 3; ++c) o[c] = (T)((acc[c] + (1ull << (shift - 1))) >> shift);
+        acc0 = al_lane_sum(acc0); acc1 = al_lane_sum(acc1); acc2 = al_lane_sum(acc2);
+        if (lane == 0) {
+            const int shift = sizeof(T) == 1 ? 16 : 32;
+            T *o = (T *)((char *)out + (long long)y * opitch) + 3 * x;
+            o[0] = (T)((acc0 + (1ull << (shift - 1))) >> shift);
+            o[1] = (T)((acc1 + (1ull << (shift - 1))) >> shift);
+            o[2] = (T)((acc2 + (1ull << (shift - 1))) >> shift);
+        }
     }
 };
+

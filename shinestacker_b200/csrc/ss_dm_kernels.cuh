@@ -468,3 +468,14 @@ __global__ void __launch_bounds__(256) dm_px_kernel(const __grid_constant__ K k,
     if (x < w && y < h) k(x, y, (int)blockIdx.z);
 }
 #endif
+
+#ifndef SS_HOST_EMU
+// persistent grid, one warp per list entry; the entry count is read from device memory (no host round trip)
+template <class K>
+__global__ void __launch_bounds__(256) dm_item_kernel(const __grid_constant__ K k, const int *count)
+{
+    const int n = *count, lane = threadIdx.x & 31;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) k.item(i, lane, 32);
+}
+#endif

@@ -35,6 +35,8 @@ struct DmCudaBackend {
         if (ev_copied) cudaEventDestroy(ev_copied);
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_end) cudaEventDestroy(ev_end);
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr; h_pinned_n = 0;
     }
     int alloc(void **p, size_t bytes)
     {
@@ -94,8 +96,10 @@ struct DmCudaBackend {
         ++launches;
         return 0;
     }
-    // one ECC iteration: zero the 28 device sums, one persistent-grid pass, bring the sums back
-    int ecc_accumulate(const EccParams &p, double *d_sums, double *host_sums)
+    int zero(void *p, size_t bytes) { DM_CUDA(cudaMemsetAsync(p, 0, bytes, s_comp)); return 0; }
+    // one warp per item of a device-side list whose length sits in device memory (persistent grid)
+    template <class K>
+    int launch_items(const K &k, const int *d_count)
     {
         static int n_sm = 0;
         if (!n_sm) {
@@ -103,14 +107,44 @@ struct DmCudaBackend {
             DM_CUDA(cudaGetDevice(&dev));
             DM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         }
-        DM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * ECC_NSUMS, s_comp));
-        const long long n = (long long)p.h * p.w;
-        long long blocks = (n + 255) / 256;
-        if (blocks > 4LL * n_sm) blocks = 4LL * n_sm;     // 4 resident CTAs of 256 threads per SM
-        ecc_accumulate_kernel<<<(int)blocks, 256, 0, s_comp>>>(p, d_sums);
+        dm_item_kernel<K><<<8 * n_sm, 256, 0, s_comp>>>(k, d_count);
         DM_CUDA(cudaGetLastError());
         ++launches;
-        return download(host_sums, d_sums, sizeof(double) * ECC_NSUMS);
+        return 0;
+    }
+    // ECC passes: `count` parameter sets (one ECC iteration, or all candidates of the coarse search) are
+    // evaluated back to back -- zero the count x 28 device sums, one persistent-grid launch per set, ONE
+    // download through pinned memory and ONE synchronisation for all of them
+    double *h_pinned = nullptr;
+    size_t h_pinned_n = 0;
+    int ecc_accumulate_batch(const EccParams *p, int count, double *d_sums, double *host_sums)
+    {
+        static int n_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            DM_CUDA(cudaGetDevice(&dev));
+            DM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const size_t n_d = (size_t)count * ECC_NSUMS;
+        if (h_pinned_n < n_d) {
+            if (h_pinned) cudaFreeHost(h_pinned);
+            h_pinned = nullptr; h_pinned_n = 0;
+            DM_CUDA(cudaHostAlloc((void **)&h_pinned, sizeof(double) * n_d, cudaHostAllocDefault));
+            h_pinned_n = n_d;
+        }
+        DM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * n_d, s_comp));
+        for (int i = 0; i < count; ++i) {
+            const long long n = (long long)p[i].h * p[i].w;
+            long long blocks = (n + 255) / 256;
+            if (blocks > 4LL * n_sm) blocks = 4LL * n_sm;     // 4 resident CTAs of 256 threads per SM
+            ecc_accumulate_kernel<<<(int)blocks, 256, 0, s_comp>>>(p[i], d_sums + (size_t)i * ECC_NSUMS);
+            ++launches;
+        }
+        DM_CUDA(cudaGetLastError());
+        DM_CUDA(cudaMemcpyAsync(h_pinned, d_sums, sizeof(double) * n_d, cudaMemcpyDeviceToHost, s_comp));
+        DM_CUDA(cudaStreamSynchronize(s_comp));
+        memcpy(host_sums, h_pinned, sizeof(double) * n_d);
+        return 0;
     }
     int elapsed_ms(float *ms)
     {

@@ -3,9 +3,12 @@
 // the device pass returns (zero-mean correction, 4x4 solve, ECC lambda, parameter update).
 #pragma once
 #include <math.h>
+#include <vector>
 #include "ss_ecc_kernels.cuh"
 
 #define ECC_MAX_LEVELS 12
+#define ECC_SEARCH 4            /* coarse search: whole-pixel shifts in [-4, 4]^2 at the coarsest level */
+#define ECC_SEARCH_N ((2 * ECC_SEARCH + 1) * (2 * ECC_SEARCH + 1))
 
 static inline bool ecc_solve4(const double *Hs /*10 upper-triangular*/, const double *b, double *x)
 {
@@ -63,7 +66,7 @@ struct EccEstimator {
         const size_t bytes0 = sizeof(float) * (size_t)h * w;
         if ((rc = be->alloc((void **)&gx, bytes0))) return fail(rc, be->last_error());
         if ((rc = be->alloc((void **)&gy, bytes0))) return fail(rc, be->last_error());
-        if ((rc = be->alloc((void **)&d_sums, sizeof(double) * ECC_NSUMS))) return fail(rc, be->last_error());
+        if ((rc = be->alloc((void **)&d_sums, sizeof(double) * ECC_NSUMS * ECC_SEARCH_N))) return fail(rc, be->last_error());
         return DM_OK;
     }
 
@@ -132,32 +135,42 @@ struct EccEstimator {
             const double radius = 0.5 * sqrt((double)ww * ww + (double)hh * hh);
             double mean_r = 0, mean_w = 0;
             double S[ECC_NSUMS];
-            auto pass = [&](double pa, double pb, double ptx, double pty) -> int {
+            auto params = [&](double pa, double pb, double ptx, double pty) -> EccParams {
                 EccParams p;
                 p.ref = ref[l]; p.mov = mov[l]; p.gx = gx; p.gy = gy; p.h = hh; p.w = ww;
                 p.a = (float)pa; p.b = (float)pb; p.tx = (float)ptx; p.ty = (float)pty; p.cx = (float)cx; p.cy = (float)cy;
                 p.mean_r = (float)mean_r; p.mean_w = (float)mean_w;
-                ++total;
-                return be->ecc_accumulate(p, d_sums, S);
+                return p;
             };
-            auto correlation = [&]() -> double {    // of the zero-mean samples over the overlap; -2 = unusable
-                const double n = S[27];
+            auto pass = [&](double pa, double pb, double ptx, double pty) -> int {
+                const EccParams p = params(pa, pb, ptx, pty);
+                ++total;
+                return be->ecc_accumulate_batch(&p, 1, d_sums, S);
+            };
+            auto correlation_of = [](const double *Q) -> double {   // zero-mean samples over the overlap; -2 = unusable
+                const double n = Q[27];
                 if (n < 64) return -2.0;
-                const double mw = S[25] / n, mr = S[26] / n;
-                const double sww = S[22] - n * mw * mw, srw = S[23] - n * mw * mr, srr = S[24] - n * mr * mr;
+                const double mw = Q[25] / n, mr = Q[26] / n;
+                const double sww = Q[22] - n * mw * mw, srw = Q[23] - n * mw * mr, srr = Q[24] - n * mr * mr;
                 return sww > 0 && srr > 0 ? srw / sqrt(sww * srr) : -2.0;
             };
+            auto correlation = [&]() -> double { return correlation_of(S); };
             if (l == L - 1 && !init_m) {
                 // coarsest level: exhaustive search over whole-pixel shifts (+-4 px here = +-4 * 2^(L-1) px at full
                 // resolution) so that the iterations start inside the basin of the right optimum even on
-                // content without low frequencies
+                // content without low frequencies; all candidates are evaluated with one synchronisation
+                std::vector<EccParams> cand;
+                std::vector<double> sums((size_t)ECC_SEARCH_N * ECC_NSUMS);
+                for (int sy = -ECC_SEARCH; sy <= ECC_SEARCH; ++sy)
+                    for (int sx = -ECC_SEARCH; sx <= ECC_SEARCH; ++sx) cand.push_back(params(a, b, tx + sx, ty + sy));
+                total += (int)cand.size();
+                if ((rc = be->ecc_accumulate_batch(cand.data(), (int)cand.size(), d_sums, sums.data())))
+                    return fail(rc, be->last_error());
                 double best = -3, btx = tx, bty = ty;
-                for (int sy = -4; sy <= 4; ++sy)
-                    for (int sx = -4; sx <= 4; ++sx) {
-                        if ((rc = pass(a, b, tx + sx, ty + sy))) return fail(rc, be->last_error());
-                        const double r = correlation();
-                        if (r > best) { best = r; btx = tx + sx; bty = ty + sy; }
-                    }
+                for (size_t c = 0; c < cand.size(); ++c) {
+                    const double r = correlation_of(sums.data() + c * ECC_NSUMS);
+                    if (r > best) { best = r; btx = cand[c].tx; bty = cand[c].ty; }
+                }
                 tx = btx; ty = bty;
             }
             double prev_rho = -3, pa = a, pb = b, ptx = tx, pty = ty, step[4] = {0, 0, 0, 0};
@@ -197,7 +210,8 @@ struct EccEstimator {
                 a += step[0]; b += step[1]; tx += step[2]; ty += step[3];
                 // the offsets only condition the float sums; keep them fixed after the first pass of a level
                 if (it == 0) { mean_r += mr; mean_w += mw; }
-                if (last < eps_px) break;
+                // coarse levels only have to bring the next level into its basin
+                if (last < (l > finest_level ? (eps_px > 0.02 ? eps_px : 0.02) : eps_px)) break;
             }
             dx = tx - a * cx + b * cy + cx; dy = ty - b * cx - a * cy + cy;
             if (l > finest_level) { dx *= 2; dy *= 2; }

@@ -25,18 +25,30 @@ struct DmHostBackend {
         return 0;
     }
 #ifdef ECC_NSUMS
-    int ecc_accumulate(const EccParams &p, double *, double *host_sums)
+    int ecc_accumulate_batch(const EccParams *pp, int count, double *, double *host_sums)
     {
-        for (int i = 0; i < ECC_NSUMS; ++i) host_sums[i] = 0;
-        float s[ECC_NSUMS];
-        for (int y = 0; y < p.h; ++y)
-            for (int x = 0; x < p.w; ++x)
-                if (ecc_pixel(p, x, y, s))
-                    for (int i = 0; i < ECC_NSUMS; ++i) host_sums[i] += s[i];
-        ++launches;
+        for (int c = 0; c < count; ++c) {
+            const EccParams &p = pp[c];
+            double *out = host_sums + (size_t)c * ECC_NSUMS;
+            for (int i = 0; i < ECC_NSUMS; ++i) out[i] = 0;
+            float s[ECC_NSUMS];
+            for (int y = 0; y < p.h; ++y)
+                for (int x = 0; x < p.w; ++x)
+                    if (ecc_pixel(p, x, y, s))
+                        for (int i = 0; i < ECC_NSUMS; ++i) out[i] += s[i];
+            ++launches;
+        }
         return 0;
     }
 #endif
+    int zero(void *p, size_t bytes) { memset(p, 0, bytes); return 0; }
+    template <class K>
+    int launch_items(const K &k, const int *count)
+    {
+        for (int i = 0; i < *count; ++i) k.item(i, 0, 1);
+        ++launches;
+        return 0;
+    }
     template <class K>
     int launch(const K &k, int w, int h, int z)
     {

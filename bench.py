@@ -138,7 +138,7 @@ def next_rows(a, host):
     try:
         from tools import time_depthmap, time_align, time_ecc, time_pipeline
         out["depth_map"] = time_depthmap.measure(a.frames, a.height, a.width, a.dtype, steps=3, warmup=1,
-                                                 host=list(host))
+                                                 host=list(host), pinned=True)
         out["align_warp"] = time_align.measure(a.height, a.width, a.dtype, steps=5)
         if a.dtype == "uint8":
             out["align_ecc_estimator"] = time_ecc.measure(a.height, a.width, steps=3, with_features=True)

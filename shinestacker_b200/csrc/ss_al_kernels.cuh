@@ -165,7 +165,7 @@ struct AlWarp {
 // img_warp[mask == 0] = GaussianBlur(img_warp)[mask == 0] (align.py:249-251).  `out` already holds a copy of
 // the warped frame (AlWarp's second destination); the listed pixels (thin border strips) are replaced by the
 // full 2-D fixed-point sum (sum_ij k_i k_j p_ij + half) >> shift -- exact integers, so the order of the taps
-// is free: one WARP per pixel, the 441 taps split over its lanes, shuffle reduction.  (One thread per pixel
+// is free: one WARP per pixel, the kernel columns split over its lanes, shuffle reduction.  (One thread per pixel
 // left a long tail: all the heavy pixels sit in a few border CTAs.)  The host build runs item(i, 0, 1).
 template <typename T>
 struct AlBlurFillList {
@@ -176,13 +176,21 @@ struct AlBlurFillList {
     {
         const int idx = list[i];
         const int y = idx / w, x = idx - y * w, r = taps / 2;
+        // a lane owns whole kernel columns: 32-bit column sums sum_i k_i p_ij (< 2^32 even for uint16), one
+        // 64-bit multiply by k_j per column
         unsigned long long acc0 = 0, acc1 = 0, acc2 = 0;
-        for (int t = lane; t < taps * taps; t += nlanes) {
-            const int ti = t / taps, tj = t - ti * taps;
-            const T *p = (const T *)((const char *)warped + (long long)dm_reflect101(y - r + ti, h) * wpitch) +
-                         3 * dm_reflect101(x - r + tj, w);
-            const unsigned long long kk = (unsigned long long)(unsigned)k[ti] * (unsigned)k[tj];
-            acc0 += kk * p[0]; acc1 += kk * p[1]; acc2 += kk * p[2];
+        const bool inner_y = y >= r && y + r < h;
+        for (int tj = lane; tj < taps; tj += nlanes) {
+            const int xo = 3 * dm_reflect101(x - r + tj, w);
+            unsigned c0 = 0, c1 = 0, c2 = 0;
+            for (int ti = 0; ti < taps; ++ti) {
+                const int yy = inner_y ? y - r + ti : dm_reflect101(y - r + ti, h);
+                const T *p = (const T *)((const char *)warped + (long long)yy * wpitch) + xo;
+                const unsigned ki = (unsigned)k[ti];
+                c0 += ki * p[0]; c1 += ki * p[1]; c2 += ki * p[2];
+            }
+            const unsigned long long kj = (unsigned)k[tj];
+            acc0 += kj * c0; acc1 += kj * c1; acc2 += kj * c2;
         }
         acc0 = al_lane_sum(acc0); acc1 = al_lane_sum(acc1); acc2 = al_lane_sum(acc2);
         if (lane == 0) {

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -80,7 +81,8 @@ struct DmEngine {
     uint8_t *d_frames = nullptr, *d_out = nullptr;
     float *d_energy = nullptr, *d_smooth = nullptr, *d_t1 = nullptr, *d_t2 = nullptr, *d_t3 = nullptr, *d_sw = nullptr;
     float *weights = nullptr;      // the buffer that holds the focus maps after finish_begin
-    unsigned *d_stats = nullptr;
+    unsigned *d_stats = nullptr;        // per frame (min, max) bits of the raw energy, folded by finish_begin
+    unsigned *d_slots = nullptr;        // per frame DM_STAT_SLOTS (min, max) pairs the energy kernel updates
     std::vector<int> lh, lw;
     std::vector<float *> gp, acc;  // gp[l] (l >= 1): 4 planes; acc[l]: 3 planes
     std::vector<float> h_sw;       // bilateral space weights, (2r+1)^2, 0 outside the disc
@@ -133,6 +135,7 @@ struct DmEngine {
         if ((rc = be.alloc((void **)&d_t2, plane * sizeof(float)))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_t3, plane * sizeof(float)))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_stats, nf * 2 * sizeof(unsigned)))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_slots, nf * 2 * DM_STAT_SLOTS * sizeof(unsigned)))) return fail(rc, be.last_error());
         gp.assign(L, nullptr); acc.assign(L, nullptr);
         for (int l = 0; l < L; ++l) {
             const size_t px = (size_t)lh[l] * lw[l];
@@ -162,11 +165,11 @@ struct DmEngine {
     void destroy()
     {
         be.sync();
-        void *ptrs[] = {d_frames, d_out, d_energy, d_smooth, d_t1, d_t2, d_t3, d_stats, d_sw};
+        void *ptrs[] = {d_frames, d_out, d_energy, d_smooth, d_t1, d_t2, d_t3, d_stats, d_slots, d_sw};
         for (void *p : ptrs) if (p) be.free(p);
         for (float *p : gp) if (p) be.free(p);
         for (float *p : acc) if (p) be.free(p);
-        d_frames = d_out = nullptr; d_energy = d_smooth = d_t1 = d_t2 = d_t3 = d_sw = nullptr; d_stats = nullptr;
+        d_frames = d_out = nullptr; d_energy = d_smooth = d_t1 = d_t2 = d_t3 = d_sw = nullptr; d_stats = d_slots = nullptr;
         gp.clear(); acc.clear();
     }
 
@@ -176,9 +179,9 @@ struct DmEngine {
         if (rc) return fail(rc, be.last_error());
         n = 0; finished = 0; blended = 0; collapsed = 0; weights = nullptr; gmax = 0.f;
         be.reset_counters();
-        std::vector<unsigned> init(2 * (size_t)o.max_frames);
+        std::vector<unsigned> init(2 * (size_t)o.max_frames * DM_STAT_SLOTS);
         for (size_t i = 0; i < init.size(); i += 2) { init[i] = 0x7f800000u; init[i + 1] = 0u; }  // min = +inf, max = 0
-        if ((rc = be.upload_small(d_stats, init.data(), init.size() * sizeof(unsigned)))) return fail(rc, be.last_error());
+        if ((rc = be.upload_small(d_slots, init.data(), init.size() * sizeof(unsigned)))) return fail(rc, be.last_error());
         return DM_OK;
     }
 
@@ -189,7 +192,7 @@ struct DmEngine {
         int rc;
         const void *frame = d_frames + (size_t)i * frame_bytes;
         float *e = d_energy + (size_t)i * plane;
-        unsigned *st = d_stats + 2 * (size_t)i;
+        unsigned *st = d_slots + 2 * DM_STAT_SLOTS * (size_t)i;
         if (o.energy == 0) {
             DmGrayRowFilter<InT> a{frame, (long long)frame_pitch, h, w, t_blur, d_t1};
             if ((rc = be.launch(a, w, h, 1))) return rc;
@@ -228,11 +231,20 @@ struct DmEngine {
     {
         if (n == 0) return fail(DM_ERR_STATE, "no frames");
         if (finished) return fail(DM_ERR_STATE, "already finished");
-        std::vector<unsigned> st(2 * (size_t)n);
-        int rc = be.download(st.data(), d_stats, st.size() * sizeof(unsigned));
+        std::vector<unsigned> slots(2 * (size_t)n * DM_STAT_SLOTS), st(2 * (size_t)n);
+        int rc = be.download(slots.data(), d_slots, slots.size() * sizeof(unsigned));
         if (rc) return fail(rc, be.last_error());
         unsigned mx = 0;
-        for (int i = 0; i < n; ++i) mx = st[2 * i + 1] > mx ? st[2 * i + 1] : mx;
+        for (int i = 0; i < n; ++i) {       // fold the slots of every frame; non-negative floats order like their bits
+            unsigned lo = 0x7f800000u, hi = 0u;
+            for (int s = 0; s < DM_STAT_SLOTS; ++s) {
+                const unsigned a = slots[2 * ((size_t)i * DM_STAT_SLOTS + s)], b = slots[2 * ((size_t)i * DM_STAT_SLOTS + s) + 1];
+                lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+            }
+            st[2 * i] = lo; st[2 * i + 1] = hi;
+            mx = hi > mx ? hi : mx;
+        }
+        if ((rc = be.upload_small(d_stats, st.data(), st.size() * sizeof(unsigned)))) return fail(rc, be.last_error());
         memcpy(&gmax, &mx, 4);
         if (gmax > 0.f) {
             DmNormalize k{d_energy, h, w, gmax};
@@ -241,11 +253,17 @@ struct DmEngine {
         weights = d_energy;
         if (o.smooth_size > 0) {
             const float gc = (float)(-0.5 / (25.0 * 25.0)), c1 = gc, c2 = 0.5f * gc * gc;
-            if (bil_r == 7) {
-                DmBilateralFixed<7> k;
+            const char *pair_env = getenv("SSDM_BILATERAL_PAIR");     // A/B knob (default: two pixels per thread)
+            if (bil_r == 7 && pair_env && pair_env[0] == '0') {
+                DmBilateralSingle<7> k;
                 k.in = d_energy; k.h = h; k.w = w; k.stats = d_stats; k.gmax = gmax; k.out = d_smooth;
                 for (int i = 0; i < 225; ++i) { k.s0[i] = h_sw[i]; k.s1[i] = h_sw[i] * c1; k.s2[i] = h_sw[i] * c2; }
                 if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());
+            } else if (bil_r == 7) {
+                DmBilateralFixed<7> k;
+                k.in = d_energy; k.h = h; k.w = w; k.stats = d_stats; k.gmax = gmax; k.out = d_smooth;
+                for (int i = 0; i < 225; ++i) { k.s0[i] = h_sw[i]; k.s1[i] = h_sw[i] * c1; k.s2[i] = h_sw[i] * c2; }
+                if ((rc = be.launch(k, (w + 1) / 2, h, n))) return fail(rc, be.last_error());   // two pixels per call
             } else {
                 DmBilateral k{d_energy, h, w, bil_r, d_sw, c1, c2, d_stats, gmax, d_smooth};
                 if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());

@@ -114,7 +114,10 @@ struct DmRowPair {
     }
 };
 
-// per-frame minimum / maximum of the (non-negative) energies as IEEE bit patterns: stats[0] = min, [1] = max
+// per-frame minimum / maximum of the (non-negative) energies as IEEE bit patterns, kept in DM_STAT_SLOTS
+// (min, max) pairs per frame: every CTA updates the slot picked by its block index, so the atomics of a launch
+// spread over 64 L2 lines instead of hammering one; the host folds the slots (ss_dm_engine.h, finish_begin)
+#define DM_STAT_SLOTS 64
 SS_DEV void dm_stats_update(unsigned *stats, float e)
 {
     const unsigned bits = __float_as_uint_compat(e);
@@ -122,12 +125,13 @@ SS_DEV void dm_stats_update(unsigned *stats, float e)
     if (bits < stats[0]) stats[0] = bits;
     if (bits > stats[1]) stats[1] = bits;
 #else
+    unsigned *slot = stats + 2 * ((blockIdx.x + 7 * blockIdx.y) & (DM_STAT_SLOTS - 1));
     const unsigned m = __activemask();
     const unsigned lo = __reduce_min_sync(m, bits), hi = __reduce_max_sync(m, bits);
     // one lane per warp; the values are monotone, so a plain (L2) read first skips almost every atomic
     if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
-        if (lo < __ldcg(stats)) atomicMin(stats, lo);
-        if (hi > __ldcg(stats + 1)) atomicMax(stats + 1, hi);
+        if (lo < __ldcg(slot)) atomicMin(slot, lo);
+        if (hi > __ldcg(slot + 1)) atomicMax(slot + 1, hi);
     }
 #endif
 }
@@ -215,6 +219,76 @@ struct DmBilateral {
 //   dv = v - v0;  q = dv*dv;  wgt = fma(q, fma(q, s*c2, s*c1), s);  num = fma(v, wgt, num);  den += wgt.
 template <int R>
 struct DmBilateralFixed {
+    enum { D = 2 * R + 1 };
+    const float *in; int h, w; const unsigned *stats; float gmax; float *out;
+    float s0[D * D], s1[D * D], s2[D * D];
+    SS_MDEV void tap(float v, float v0, int t, float &num, float &den) const
+    {
+        const float dv = ss_add(v, -v0);
+        const float q = ss_mul(dv, dv);
+        const float wgt = ss_fma(q, ss_fma(q, s2[t], s1[t]), s0[t]);
+        num = ss_fma(v, wgt, num);
+        den = ss_add(den, wgt);
+    }
+    // any pixel (image borders: REFLECT101)
+    SS_MDEV void one(const float *src, int x, int y, float *dst) const
+    {
+        const float v0 = src[(long long)y * w + x];
+        float num = 0.f, den = 0.f;
+        for (int i = 0; i < D; ++i) {
+            const float *row = src + (long long)dm_reflect101(y - R + i, h) * w;
+            for (int j = 0; j < D; ++j) {
+                if ((i - R) * (i - R) + (j - R) * (j - R) > R * R) continue;
+                tap(row[dm_reflect101(x - R + j, w)], v0, i * D + j, num, den);
+            }
+        }
+        dst[(long long)y * w + x] = ss_div(num, den);
+    }
+    // One call = the two horizontally adjacent pixels (2 xi, y) and (2 xi + 1, y): away from the borders every
+    // loaded sample feeds the windows of both (16 columns x 15 rows loaded for 2 x 149 taps), and the
+    // tap constants are fetched once for the pair.  The order of the taps of each pixel is unchanged.
+    SS_MDEV void operator()(int xi, int y, int z) const
+    {
+        const long long plane = (long long)h * w;
+        const float *src = in + (long long)z * plane;
+        float *dst = out + (long long)z * plane;
+        const int x = 2 * xi;
+        float mn = __uint_as_float_compat(stats[2 * z]), mx = __uint_as_float_compat(stats[2 * z + 1]);
+        if (gmax > 0.f) { mn = ss_div(mn, gmax); mx = ss_div(mx, gmax); }
+        if (fabsf(mn - mx) < 1.1920929e-07f) {      // cv2 copies a flat plane
+            dst[(long long)y * w + x] = src[(long long)y * w + x];
+            if (x + 1 < w) dst[(long long)y * w + x + 1] = src[(long long)y * w + x + 1];
+            return;
+        }
+        if (!(x >= R && x + 1 < w - R && y >= R && y < h - R)) {
+            one(src, x, y, dst);
+            if (x + 1 < w) one(src, x + 1, y, dst);
+            return;
+        }
+        const float *row = src + (long long)(y - R) * w + (x - R);
+        const float va = row[(long long)R * w + R], vb = row[(long long)R * w + R + 1];
+        float na = 0.f, da = 0.f, nb = 0.f, db = 0.f;
+        const float *rp = row;
+#pragma unroll
+        for (int i = 0; i < D; ++i, rp += w) {
+#pragma unroll
+            for (int j = 0; j <= D; ++j) {
+                const bool in_a = j < D && (i - R) * (i - R) + (j - R) * (j - R) <= R * R;
+                const bool in_b = j >= 1 && (i - R) * (i - R) + (j - 1 - R) * (j - 1 - R) <= R * R;
+                if (!in_a && !in_b) continue;
+                const float v = rp[j];
+                if (in_a) tap(v, va, i * D + j, na, da);
+                if (in_b) tap(v, vb, i * D + j - 1, nb, db);
+            }
+        }
+        dst[(long long)y * w + x] = ss_div(na, da);
+        dst[(long long)y * w + x + 1] = ss_div(nb, db);
+    }
+};
+
+// One pixel per call (the variant the pair version is measured against: SSDM_BILATERAL_PAIR=0).
+template <int R>
+struct DmBilateralSingle {
     enum { D = 2 * R + 1 };
     const float *in; int h, w; const unsigned *stats; float gmax; float *out;
     float s0[D * D], s1[D * D], s2[D * D];

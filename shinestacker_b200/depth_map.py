@@ -230,8 +230,10 @@ class DepthMapStack:
                     fut.cancel()
                 pool.shutdown(wait=True)
 
-    def focus_stack_arrays(self, frames, keep_handle_state=False):
-        """In-memory entry point: iterable of H x W x 3 BGR uint8/uint16 arrays -> fused image."""
+    def focus_stack_arrays(self, frames, stage=True):
+        """In-memory entry point: iterable of H x W x 3 BGR uint8/uint16 arrays -> fused image.
+        ``stage=False`` uploads straight from the arrays' own memory (C-contiguous, ideally pinned, e.g.
+        allocated with ss_host_alloc) instead of copying each frame into the pinned staging ring first."""
         frames = list(frames)
         if not frames:
             raise ImageLoadError("", "empty frame list")
@@ -239,11 +241,16 @@ class DepthMapStack:
         if img0.ndim != 3 or img0.shape[2] != 3 or img0.dtype not in (np.uint8, np.uint16):
             raise ImageLoadError("<array>", "expected a 3-channel 8 or 16 bit image")
         self._ensure_handle(img0.shape, img0.dtype, len(frames))
-        ring = self._staging(img0.nbytes, 4)
+        ring = self._staging(img0.nbytes, 4) if stage else None
         try:
             for i, img in enumerate(frames):
                 self._validate(img, img0.shape[:2], img0.dtype)
-                self._push(i, img, ring)
+                if stage:
+                    self._push(i, img, ring)
+                else:
+                    if not img.flags.c_contiguous:
+                        raise ValueError("stage=False needs C-contiguous frames")
+                    _check(self._lib.ssdm_push_frame(self._h, img.ctypes.data_as(ctypes.c_void_p), img.strides[0]))
             return self._blend_and_finish(len(frames), img0.shape[:2], img0.dtype)
         except BaseException:
             if self._h is not None:

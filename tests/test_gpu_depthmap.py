@@ -68,6 +68,7 @@ def test_handle_reuse_and_rerun():
     out_b = algo.focus_stack_arrays(b)          # FocusStackBunch reuses one stack_algo (stack.py:94-97)
     assert np.array_equal(algo.focus_stack_arrays(a), out_a)
     assert np.array_equal(DepthMapStack().focus_stack_arrays(b), out_b)
+    assert np.array_equal(DepthMapStack().focus_stack_arrays(b, stage=False), out_b)    # upload without staging
     import ctypes
     assert algo._lib.ssdm_rerun_resident(algo._h) == 0
     again = np.empty_like(out_a)

@@ -16,7 +16,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def measure(frames_n=64, height=3072, width=4096, dtype="uint8", steps=5, warmup=2, host=None, **kwargs):
+def measure(frames_n=64, height=3072, width=4096, dtype="uint8", steps=5, warmup=2, host=None, pinned=False, **kwargs):
     from shinestacker_b200 import DepthMapStack, synthetic, _native
     from shinestacker_b200.pyramid import _check
     lib = _native.load()
@@ -49,14 +49,14 @@ def measure(frames_n=64, height=3072, width=4096, dtype="uint8", steps=5, warmup
     e2e = []
     for _ in range(max(2, steps // 2)):
         t0 = time.perf_counter()
-        algo.focus_stack_arrays(host)
+        algo.focus_stack_arrays(host, stage=not pinned)   # pinned frames are uploaded from where they are
         e2e.append(time.perf_counter() - t0)
     mp = frames_n * height * width / 1e6
     return {"workload": f"DepthMapStack {frames_n} x {width}x{height} {dtype} {kwargs}",
             "device_ms_per_stack": float(np.median(dev)), "wall_ms_per_stack": float(np.median(wall) * 1e3),
             "resident_mp_per_s": mp / (float(np.median(wall))), "launches_per_stack": int(nl.value),
             "e2e_ms_per_stack": float(np.median(e2e) * 1e3), "e2e_mp_per_s": mp / float(np.median(e2e)),
-            "first_call_ms": first * 1e3, "rerun_matches_first_result": bool(np.array_equal(out, again))}
+            "e2e_frames_pinned": bool(pinned), "first_call_ms": first * 1e3, "rerun_matches_first_result": bool(np.array_equal(out, again))}
 
 
 if __name__ == "__main__":

@@ -136,10 +136,11 @@ def next_rows(a, host):
     stage (one frame: warp + mask + 21x21 blur fill) with cv2 on the host cores beside it."""
     out = {}
     try:
-        from tools import time_depthmap, time_align, time_ecc, time_pipeline
+        from tools import time_depthmap, time_align, time_ecc, time_pipeline, time_files
         out["depth_map"] = time_depthmap.measure(a.frames, a.height, a.width, a.dtype, steps=3, warmup=1,
                                                  host=list(host), pinned=True)
         out["align_warp"] = time_align.measure(a.height, a.width, a.dtype, steps=5)
+        out["files_e2e"] = time_files.measure(list(host), steps=2)
         if a.dtype == "uint8":
             out["align_ecc_estimator"] = time_ecc.measure(a.height, a.width, steps=3, with_features=True)
             out["align_ecc_plus_stack_config5"] = time_pipeline.measure(list(host), steps=2)

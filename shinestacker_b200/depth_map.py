@@ -19,7 +19,8 @@ import numpy as np
 
 from . import _native
 from .exceptions import InvalidOptionError, ImageLoadError, RunStopException
-from .pyramid import read_img, _check, PyramidStack, FLOAT_32, FLOAT_64
+from . import fastio
+from .pyramid import read_img, _check, stage_frame, PyramidStack, FLOAT_32, FLOAT_64
 
 # reference src/shinestacker/config/constants.py:144-157
 DM_ENERGY_LAPLACIAN = "laplacian"
@@ -150,12 +151,11 @@ class DepthMapStack:
             raise RunStopException(self.name())
 
     def _push(self, i, img, ring):
-        img = np.ascontiguousarray(img)
         slot = i % len(ring)
         if i >= len(ring) and slot == 0:
             _check(self._lib.ssdm_sync_copies(self._h))
         ptr, view = ring[slot]
-        view[:img.nbytes] = img.reshape(-1).view(np.uint8)
+        stage_frame(img, view)
         _check(self._lib.ssdm_push_frame(self._h, ptr, img.shape[1] * 3 * img.dtype.itemsize))
 
     def _blend_and_finish(self, n, shape, dtype, names=None):
@@ -195,10 +195,10 @@ class DepthMapStack:
 
         def fetch(i):
             if pool is None:
-                return read_img(filenames[i])
+                return fastio.read_frame(filenames[i], read_img)
             for j in range(i, min(n, i + self.decode_threads + 1)):
                 if j not in pending:
-                    pending[j] = pool.submit(read_img, filenames[j])
+                    pending[j] = pool.submit(fastio.read_frame, filenames[j], read_img)
             return pending.pop(i).result()
 
         try:

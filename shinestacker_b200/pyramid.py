@@ -19,7 +19,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from . import _native
+from . import _native, fastio
 from .exceptions import (InvalidOptionError, ImageLoadError, BitDepthError, ShapeError,
                          RunStopException, NativeLibraryError)
 
@@ -101,6 +101,17 @@ def select_base(lib, h, n_frames, num_values, float_type=np.float32):
             _check(lib.ss_finish_select_base_f64(h, table.ctypes.data_as(ctypes.c_void_p), 1))
         else:
             _check(lib.ss_finish_select_base_px(h, table.ctypes.data_as(ctypes.c_void_p)))
+
+
+def stage_frame(img, view):
+    """Copy one decoded frame -- an ndarray from cv2.imread or a mapped plain TIFF (fastio) -- into a pinned
+    staging buffer (flat uint8 view)."""
+    if isinstance(img, fastio.PlainTiff):
+        img.into_bgr(view[:img.nbytes].view(img.dtype).reshape(img.shape))
+        img.close()
+    else:
+        img = np.ascontiguousarray(img)
+        view[:img.nbytes] = img.reshape(-1).view(np.uint8)
 
 
 def _check(rc):
@@ -266,12 +277,11 @@ class PyramidStack(PyramidBase):
             raise RunStopException(self.name())
 
     def _push(self, i, img, ring):
-        img = np.ascontiguousarray(img)
         slot = i % len(ring)
         if i >= len(ring) and slot == 0:
             _check(self._lib.ss_sync_copies(self._h))
         ptr, view = ring[slot]
-        view[:img.nbytes] = img.reshape(-1).view(np.uint8)
+        stage_frame(img, view)
         _check(self._lib.ss_push_frame(self._h, ptr, img.shape[1] * 3 * img.dtype.itemsize))
 
     def _finish(self, n, shape):
@@ -328,11 +338,12 @@ class PyramidStack(PyramidBase):
         pending = {}
 
         def fetch(i):
+            # uncompressed TIFFs (what the reference's write_img produces) are mapped instead of decoded
             if pool is None:
-                return read_img(filenames[i])
+                return fastio.read_frame(filenames[i], read_img)
             for j in range(i, min(n, i + self.decode_threads + 1)):
                 if j not in pending:
-                    pending[j] = pool.submit(read_img, filenames[j])
+                    pending[j] = pool.submit(fastio.read_frame, filenames[j], read_img)
             return pending.pop(i).result()
 
         try:

@@ -126,3 +126,14 @@ def test_option_contract():
     a = al.AlignFrames(transform=al.ALIGN_HOMOGRAPHY, detector=al.DETECTOR_ORB, subsample=1, plot_summary=True)
     assert a.enabled and a.min_matches == 4 and a.feature_config["detector"] == "ORB"
     assert a.alignment_config["subsample"] == 1 and a.alignment_config["border_mode"] == "BORDER_REPLICATE_BLUR"
+
+
+@pytest.mark.parametrize("h,w,dtype", [(10, 13, np.uint8), (25, 21, np.uint16), (64, 3, np.uint8), (1, 50, np.uint8)])
+def test_frames_smaller_than_the_blur_kernel(h, w, dtype):
+    img = _img(dtype, h, w, seed=h)
+    k = ao.fixed_point_kernel(dtype, 21, 50)
+    emu = au.EmuWarper(h, w, dtype)
+    for _, m in au.TRANSFORMS[:2]:
+        for mode in au.MODES:
+            assert np.array_equal(emu.warp(img, m, mode, kernel=k), au.cv2_warp_stage(img, m, mode))
+    emu.close()

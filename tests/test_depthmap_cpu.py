@@ -158,3 +158,24 @@ def test_host_mirror_contract():
     if _native.load().ss_device_count() == 0:
         with pytest.raises(NativeLibraryError):     # no silent CPU fallback
             DepthMapStack().focus_stack_arrays(frames)
+
+
+@pytest.mark.parametrize("n,h,w,dtype,kwargs", [
+    (1, 40, 40, np.uint8, {}),                                   # a one-frame stack: weights are 1 where defined
+    (2, 9, 11, np.uint8, {}),                                    # image smaller than the bilateral window
+    (2, 16, 300, np.uint16, {"levels": 4}),
+    (3, 31, 17, np.uint8, {"smooth_size": 31, "blur_size": 15, "kernel_size": 9}),
+    (2, 20, 20, np.uint8, {"levels": 6}),                        # pyramid runs down to 1 x 1
+    (2, 5, 5, np.uint8, {"smooth_size": 3, "levels": 2}),
+])
+def test_kernels_on_host_edge_geometries(n, h, w, dtype, kwargs):
+    rng = np.random.default_rng(h * w)
+    frames = [rng.integers(0, np.iinfo(dtype).max + 1, (h, w, 3)).astype(dtype) for _ in range(n)]
+    du.assert_within_1lsb(du.emu_focus_stack(frames, **kwargs), dmo.focus_stack(frames, **kwargs), "edge geometry",
+                          max_frac=0.2)
+
+
+def test_flat_stack_documented_deviation():
+    # zero energy in every frame: the reference's np.divide(where=) leaves the weights uninitialised; here they are 0
+    frames = [np.full((30, 40, 3), 77, np.uint8)] * 3
+    assert not du.emu_focus_stack(frames).any() and not dmo.focus_stack(frames).any()

@@ -293,3 +293,19 @@ def test_frame_sharding_peer_gather_on_one_gpu(oracle):
     _check(lib.ss_finish_collapse(root._h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
     golden_util.assert_matches(out, root.get_depth_maps(), dict(fused=ref, best=info["best"], best_e=info["best_e"],
                                                                 best_d=info["best_d"], levels=info["levels"]), "peer gather")
+
+
+def test_file_interface_maps_uncompressed_tiffs(tmp_path):
+    # the files the reference's write_img produces (uncompressed TIFF) take the zero-decode path (fastio)
+    import cv2
+    from shinestacker_b200 import fastio
+    frames = synthetic.make_stack(6, 200, 264, np.uint16, 51)
+    paths = []
+    for i, f in enumerate(frames):
+        p = str(tmp_path / f"{i:03d}.tif")
+        cv2.imwrite(p, f, [int(cv2.IMWRITE_TIFF_COMPRESSION), 1])
+        assert fastio.open_plain_tiff(p) is not None
+        paths.append(p)
+    expect = PyramidStack().focus_stack_arrays(frames)
+    for threads in (0, 4):
+        assert np.array_equal(PyramidStack(decode_threads=threads, batch_frames=4).focus_stack(paths), expect)

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""T_e2e of SURVEY.md section 8d: TIFF files -> fused image through PyramidStack.focus_stack (decode + upload +
+kernels + download), files in tmpfs, with the mapped-TIFF fast path (shinestacker_b200/fastio.py) and with
+cv2.imread decoding only."""
+import json
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def measure(host, steps=2, threads=4):
+    import cv2
+    from shinestacker_b200 import PyramidStack, fastio
+    root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="ssb200_", dir=root)
+    try:
+        paths = []
+        for i, f in enumerate(host):
+            p = os.path.join(d, f"{i:04d}.tif")
+            cv2.imwrite(p, f, [int(cv2.IMWRITE_TIFF_COMPRESSION), 1])      # what the reference's write_img does
+            paths.append(p)
+        n, h, w = len(host), host[0].shape[0], host[0].shape[1]
+        res = {"workload": f"{n} uncompressed TIFFs {w}x{h} {host[0].dtype} in tmpfs -> fused image, "
+                           f"PyramidStack.focus_stack, {threads} decode threads"}
+        outs = {}
+        for label, enabled in (("mapped_tiff", True), ("cv2_imread", False)):
+            fastio.ENABLED = enabled
+            algo = PyramidStack(decode_threads=threads)
+            algo.focus_stack(paths)                                         # warm-up (handle, page cache)
+            ts = []
+            for _ in range(steps):
+                t0 = time.perf_counter()
+                outs[label] = algo.focus_stack(paths)
+                ts.append(time.perf_counter() - t0)
+            algo.close()
+            t = float(np.median(ts))
+            res[label] = {"ms_per_stack": t * 1e3, "mp_per_s": n * h * w / 1e6 / t}
+        fastio.ENABLED = True
+        res["same_result"] = bool(np.array_equal(outs["mapped_tiff"], outs["cv2_imread"]))
+        return res
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    from shinestacker_b200 import synthetic
+    n, h, w = (int(v) for v in (sys.argv[1:4] + [16, 1536, 2048][len(sys.argv) - 1:])[:3])
+    print(json.dumps(measure(synthetic.make_stack(n, h, w, np.uint8, seed=2))))

@@ -135,17 +135,19 @@ def next_rows(a, host):
     `value`): DepthMapStack (device-resident chain + end to end from host frames) and the AlignFrames warp
     stage (one frame: warp + mask + 21x21 blur fill) with cv2 on the host cores beside it."""
     out = {}
-    try:
-        from tools import time_depthmap, time_align, time_ecc, time_pipeline, time_files
-        out["depth_map"] = time_depthmap.measure(a.frames, a.height, a.width, a.dtype, steps=3, warmup=1,
-                                                 host=list(host), pinned=True)
-        out["align_warp"] = time_align.measure(a.height, a.width, a.dtype, steps=5)
-        out["files_e2e"] = time_files.measure(list(host), steps=2)
-        if a.dtype == "uint8":
-            out["align_ecc_estimator"] = time_ecc.measure(a.height, a.width, steps=3, with_features=True)
-            out["align_ecc_plus_stack_config5"] = time_pipeline.measure(list(host), steps=2)
-    except Exception as e:  # pylint: disable=broad-except
-        out["error"] = f"{type(e).__name__}: {e}"
+    from tools import time_depthmap, time_align, time_ecc, time_pipeline, time_files
+    jobs = [("depth_map", lambda: time_depthmap.measure(a.frames, a.height, a.width, a.dtype, steps=3, warmup=1,
+                                                        host=list(host), pinned=True)),
+            ("align_warp", lambda: time_align.measure(a.height, a.width, a.dtype, steps=5)),
+            ("files_e2e", lambda: time_files.measure(list(host), steps=2))]
+    if a.dtype == "uint8":
+        jobs += [("align_ecc_estimator", lambda: time_ecc.measure(a.height, a.width, steps=3, with_features=True)),
+                 ("align_ecc_plus_stack_config5", lambda: time_pipeline.measure(list(host), steps=2))]
+    for name, job in jobs:      # each entry on its own: a failure must not take the others (or the headline) with it
+        try:
+            out[name] = job()
+        except Exception as e:  # pylint: disable=broad-except
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 
@@ -365,7 +367,10 @@ def main():
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline(a, max(1, min(a.cpu_sample_frames, N)), frames=list(host))
         if world == 1 and not a.no_next_rows:
-            line["next_rows"] = next_rows(a, host)
+            try:
+                line["next_rows"] = next_rows(a, host)
+            except Exception as e:  # pylint: disable=broad-except
+                line["next_rows"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     lib.ss_host_free(pin)
     lib.ss_host_free(out_pin)

@@ -17,16 +17,27 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def measure(host, steps=2, threads=4):
     import cv2
     from shinestacker_b200 import PyramidStack, fastio
-    root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    need = int(sum(f.nbytes for f in host) * 1.1) + (64 << 20)
+    root = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if os.path.isdir(cand) and shutil.disk_usage(cand).free > need:
+                root = cand
+                break
+        except OSError:
+            pass
+    if root is None:
+        raise RuntimeError(f"no scratch directory with {need >> 20} MiB free")
     d = tempfile.mkdtemp(prefix="ssb200_", dir=root)
     try:
         paths = []
         for i, f in enumerate(host):
             p = os.path.join(d, f"{i:04d}.tif")
-            cv2.imwrite(p, f, [int(cv2.IMWRITE_TIFF_COMPRESSION), 1])      # what the reference's write_img does
+            if not cv2.imwrite(p, f, [int(cv2.IMWRITE_TIFF_COMPRESSION), 1]):   # what the reference's write_img does
+                raise RuntimeError(f"cannot write {p}")
             paths.append(p)
         n, h, w = len(host), host[0].shape[0], host[0].shape[1]
-        res = {"workload": f"{n} uncompressed TIFFs {w}x{h} {host[0].dtype} in tmpfs -> fused image, "
+        res = {"workload": f"{n} uncompressed TIFFs {w}x{h} {host[0].dtype} in {root} -> fused image, "
                            f"PyramidStack.focus_stack, {threads} decode threads"}
         outs = {}
         for label, enabled in (("mapped_tiff", True), ("cv2_imread", False)):

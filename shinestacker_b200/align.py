@@ -22,19 +22,8 @@ import logging
 import numpy as np
 
 from . import _native
-from .exceptions import InvalidOptionError, FocusStackError, ShapeError, BitDepthError
+from .exceptions import InvalidOptionError, FocusStackError, ShapeError, BitDepthError, AlignmentError
 from .pyramid import _check
-
-try:  # pragma: no cover - depends on the environment
-    from shinestacker.core.exceptions import AlignmentError  # type: ignore
-except Exception:  # pylint: disable=broad-except
-    class AlignmentError(FocusStackError):
-        """reference src/shinestacker/core/exceptions.py:29-33."""
-
-        def __init__(self, index, details):
-            self.index = index
-            self.details = details
-            super().__init__(f"Alignment failed for image {index}: {details}")
 
 # reference src/shinestacker/config/constants.py:64-110
 ALIGN_HOMOGRAPHY, ALIGN_RIGID = "ALIGN_HOMOGRAPHY", "ALIGN_RIGID"

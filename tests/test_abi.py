@@ -131,3 +131,24 @@ def test_read_img_contract(tmp_path):
     q = str(tmp_path / "a.bmp")
     cv2.imwrite(q, (img >> 8).astype(np.uint8))
     assert pyramid.read_img(q) is None      # unsupported extension -> None, like the reference
+
+
+def test_stand_in_exceptions_carry_the_reference_messages():
+    # reference src/shinestacker/core/exceptions.py:2-52: same names, constructor arguments, attributes and text
+    import importlib.util
+    from shinestacker_b200 import exceptions as ex
+    path = "/root/reference/src/shinestacker/core/exceptions.py"
+    if not os.path.isfile(path):
+        pytest.skip("reference tree not present on this box")
+    spec = importlib.util.spec_from_file_location("ref_exceptions", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cases = [("InvalidOptionError", ("float_type", "x"), {}), ("InvalidOptionError", ("a", 3), {"details": " valid"}),
+             ("ImageLoadError", ("/p/a.tif",), {}), ("ImageLoadError", ("/p", "bad"), {}),
+             ("AlignmentError", (3, "too few"), {}), ("BitDepthError", (np.uint8, np.uint16), {}),
+             ("ShapeError", ((10, 20), (11, 20)), {}), ("RunStopException", ("job",), {}), ("RunStopException", ("",), {})]
+    for name, args, kwargs in cases:
+        mine, theirs = getattr(ex, name)(*args, **kwargs), getattr(ref, name)(*args, **kwargs)
+        assert str(mine) == str(theirs) and isinstance(mine, ex.FocusStackError)
+    e = ex.InvalidOptionError("o", "v", details="d")
+    assert (e.option, e.value, e.details) == ("o", "v", "d") and ex.ImageLoadError("p").path == "p"

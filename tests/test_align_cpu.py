@@ -137,3 +137,38 @@ def test_frames_smaller_than_the_blur_kernel(h, w, dtype):
         for mode in au.MODES:
             assert np.array_equal(emu.warp(img, m, mode, kernel=k), au.cv2_warp_stage(img, m, mode))
     emu.close()
+
+
+def test_randomised_transforms_match_cv2():
+    # large rotations, mirrors, frames mapped (almost) completely outside, arbitrary affine matrices, strong
+    # homographies (uint8), random border values (saturated like cv2) and three blur sigmas
+    rng = np.random.default_rng(123)
+    kernels = {(dt, s): ao.fixed_point_kernel(dt, 21, s) for dt in (np.uint8, np.uint16) for s in (50, 5, 1.5)}
+    for t in range(40):
+        dt = [np.uint8, np.uint16][t % 2]
+        h, w = int(rng.integers(8, 90)), int(rng.integers(8, 120))
+        img = rng.integers(0, np.iinfo(dt).max + 1, (h, w, 3)).astype(dt)
+        kind = t % 5
+        if kind == 0:
+            m = au.rigid(rng.uniform(-180, 180), rng.uniform(0.5, 2), rng.uniform(-w, w), rng.uniform(-h, h))
+        elif kind == 1:
+            m = au.rigid(rng.uniform(-5, 5), rng.uniform(0.9, 1.1), rng.uniform(-3 * w, 3 * w), rng.uniform(-3 * h, 3 * h))
+        elif kind == 2:
+            m = np.array([[-1.0, 0.0, w - 1.0], [0.0, 1.0, 0.0]]) + rng.normal(0, 1e-3, (2, 3))
+        elif kind == 3:
+            m = rng.normal(0, 1, (2, 3))
+            m[:, 2] *= 20
+        else:
+            if dt == np.uint16:
+                continue
+            m = au.homography(rng.uniform(-20, 20), rng.uniform(0.8, 1.2), rng.uniform(-20, 20), rng.uniform(-20, 20),
+                              rng.uniform(-1e-3, 1e-3), rng.uniform(-1e-3, 1e-3))
+        sigma = float(rng.choice([50, 5, 1.5]))
+        k = kernels[(dt, sigma)]
+        emu = au.EmuWarper(h, w, dt)
+        for mode in au.MODES:
+            bval = tuple(rng.integers(0, 300, 4).tolist()) if mode == "BORDER_CONSTANT" else (0, 0, 0, 0)
+            ref = au.cv2_warp_stage(img, m, mode, bval, sigma)
+            assert np.array_equal(ao.warp_and_fill(img, m, au.MODES[mode], bval, k), ref), (t, mode)
+            assert np.array_equal(emu.warp(img, m, mode, bval, k), ref), (t, mode)
+        emu.close()

@@ -179,3 +179,21 @@ def test_flat_stack_documented_deviation():
     # zero energy in every frame: the reference's np.divide(where=) leaves the weights uninitialised; here they are 0
     frames = [np.full((30, 40, 3), 77, np.uint8)] * 3
     assert not du.emu_focus_stack(frames).any() and not dmo.focus_stack(frames).any()
+
+
+def test_randomised_options_host_build_vs_oracle():
+    rng = np.random.default_rng(77)
+    for t in range(14):
+        dtype = [np.uint8, np.uint16][t % 2]
+        n, h, w = int(rng.integers(1, 6)), int(rng.integers(12, 80)), int(rng.integers(12, 100))
+        kwargs = dict(map_type=str(rng.choice(["average", "max"])), energy=str(rng.choice(["laplacian", "sobel"])),
+                      kernel_size=int(rng.choice([5, 7, 9])), blur_size=int(rng.choice([1, 3, 5, 7, 11])),
+                      smooth_size=int(rng.choice([0, 3, 8, 15])), temperature=float(rng.choice([0.05, 0.1, 1.0])),
+                      levels=int(rng.integers(1, 5)))
+        frames = synthetic.make_noise_stack(n, h, w, np.dtype(dtype), 100 + t)
+        st, ost = {}, None
+        out = du.emu_focus_stack(frames, stages=st, **kwargs)
+        ref, ost = dmo.focus_stack(frames, return_stages=True, **kwargs)
+        du.assert_within_1lsb(out, ref, f"case {t} {kwargs}", max_frac=0.2)
+        assert np.array_equal(st["energy"], ost["energy"]), (t, kwargs)
+        assert np.abs(st["weights"] - ost["weights"]).max() < 5e-6, (t, kwargs)

@@ -1,7 +1,6 @@
 """GPU parity tests of the AlignFrames warp stage (through ctypes -> C ABI, include/shinestack_b200_align.h)
 against cv2 itself -- the library the reference calls at align.py:228-251 -- bit-exact for uint8 and for
 uint16 + rigid transforms, in all three border modes."""
-import ctypes
 
 import numpy as np
 import pytest

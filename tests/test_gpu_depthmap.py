@@ -2,7 +2,6 @@
 the CUDA kernels against the golden vectors of the live reference and against the numpy oracle.
 DepthMapStack blends with soft weights, so the contract is the fused image within 1 LSB (SURVEY.md 8f);
 the focus energy of 8-bit stacks is integer-valued in float32 and must be bit-exact."""
-import os
 
 import numpy as np
 import pytest

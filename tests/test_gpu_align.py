@@ -156,3 +156,29 @@ def test_fused_align_and_stack_pipeline_recovers_the_undisplaced_result():
     inner = (slice(60, -60), slice(60, -60))
     a, b = out[inner].astype(np.float64).ravel(), plain[inner].astype(np.float64).ravel()
     assert np.corrcoef(a, b)[0, 1] > 0.8
+
+
+def test_device_resident_sources():
+    # ssal_warp_device / ssdm_push_frame_device: frames that already live in HBM (here: the output of another warp)
+    import ctypes
+    from shinestacker_b200 import DepthMapStack
+    frames = synthetic.make_noise_stack(3, 120, 168, np.uint8, 41)
+    m1, m2 = au.rigid(0.5, 1.01, 3.0, -2.0), au.rigid(-0.25, 0.995, -1.5, 4.0)
+    a, b = al.Warper(frames[0].shape[:2], np.uint8), al.Warper(frames[0].shape[:2], np.uint8)
+    dm, dm_ref = DepthMapStack(), DepthMapStack()
+    dm._ensure_handle(frames[0].shape, frames[0].dtype, 3)
+    staged = []
+    for f in frames:
+        first = a.warp(f, m1, al.ALIGN_RIGID, "BORDER_REPLICATE")
+        ptr, pitch = a.result_device()
+        out = np.empty_like(f)
+        mat = np.ascontiguousarray(m2, np.float64)
+        _check(b._lib.ssal_warp_device(b._h, ptr, pitch, mat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 0, 1, None,
+                                       None, 0, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+        assert np.array_equal(out, au.cv2_warp_stage(first, m2, "BORDER_REPLICATE"))
+        _check(dm._lib.ssdm_push_frame_device(dm._h, ptr, pitch))
+        _check(dm._lib.ssdm_sync_copies(dm._h))
+        _check(dm._lib.ssdm_get_plane(dm._h, 2, len(staged), np.empty((120, 168), np.float32).ctypes.data_as(ctypes.c_void_p)))
+        staged.append(first)
+    fused = dm._blend_and_finish(3, frames[0].shape[:2], frames[0].dtype)
+    assert np.array_equal(fused, dm_ref.focus_stack_arrays(staged))

@@ -14,8 +14,10 @@ sum-reduce of the winners' coefficients (shinestacker_b200/sharded.py).
 Printed JSON (rank 0, one line): value = throughput with the frames already resident in HBM;
 e2e = the same stack through the public host-buffer API (H2D of every frame from pinned host memory
 and D2H of the fused image inside the timed region); roofline = level-0 fused kernel, algorithmic
-bytes / CUDA-event time against MEASURED_PEAKS.json; cpu_baseline = the CPU oracle (a port of the
-reference's arithmetic, oracle/) on a bounded sample of the same workload.
+bytes / CUDA-event time against MEASURED_PEAKS.json; cpu_baseline = the UNMODIFIED reference (baseline/_ref, its own
+StackJob -> FocusStack -> PyramidStack from TIFF files) on a bounded sample of the same workload, with the CPU oracle
+(a multi-threaded C port of the reference's arithmetic, oracle/) on the whole stack beside it; parity = the GPU result
+of the timed run compared with the oracle's result on the same full stack (fused image and level-0 arg-max).
 """
 import argparse
 import ctypes
@@ -50,6 +52,11 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=64,
                     help="frames of the stack the CPU baseline fuses (64 = the whole workload, ~10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample-frames", type=int, default=0,
+                    help="frames per stack the unmodified reference fuses (0 = bounded automatically: ~10-30 s of CPU)")
+    ap.add_argument("--check-parity", default="auto", choices=["auto", "on", "off"],
+                    help="compare the GPU result with the oracle on the full stack (auto: whenever the CPU baseline "
+                         "runs on all frames at N=1; 'on' also at N>1, rank 0 runs the streaming oracle)")
     ap.add_argument("--no-next-rows", action="store_true",
                     help="skip the short DepthMapStack / AlignFrames measurements appended as 'next_rows' (N=1 only)")
     return ap.parse_args()
@@ -111,9 +118,9 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": float(max(power))}
 
 
-def cpu_baseline(a, n_sample, threads=None, frames=None):
-    """The oracle (CPU port of the reference arithmetic) on a bounded sample: the first n_sample
-    frames of the same synthetic stack.  The oracle is O(frames), so MP/s is representative."""
+def cpu_port(a, n_sample, threads=None, frames=None):
+    """The oracle (CPU port of the reference arithmetic, C + OpenMP) on the first n_sample frames of the same
+    synthetic stack.  Returns (entry, fused image, info) -- the result is what the parity check compares with."""
     from oracle import pyramid_oracle as po
     from shinestacker_b200 import synthetic
     po.build()
@@ -122,12 +129,60 @@ def cpu_baseline(a, n_sample, threads=None, frames=None):
         frames = synthetic.make_stack(a.frames, a.height, a.width, np.dtype(a.dtype), seed=2)
     frames = frames[:n_sample]
     t0 = time.perf_counter()
-    po.focus_stack(frames)
+    out, info = po.focus_stack(frames)
     dt = time.perf_counter() - t0
     mp = n_sample * a.height * a.width / 1e6
     return {"value": mp / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {n_sample} of the {a.frames} frames ({workload_name(a)}), oracle/pyramid_oracle "
-                      f"(C + OpenMP, {cores} threads), {dt:.2f} s"}, frames
+                      f"(C + OpenMP, {cores} threads), {dt:.2f} s"}, out, info
+
+
+def reference_stack_time(a, frames, steps=1, warmup=0):
+    """The UNMODIFIED reference (baseline/_ref): its own StackJob -> FocusStack -> PyramidStack (the path of the
+    reference's tests/test_0060_stack.py:7-14) over `frames` written as uncompressed TIFFs to a RAM disk (the format
+    its own write_img produces, utils.py:23-30).  Returns (seconds per stack, fused image) or None if it is absent."""
+    from tools import ref_loader
+    if ref_loader.load() is None:
+        return None
+    import shutil
+    import tempfile
+    import cv2
+    from shinestacker.algorithms.pyramid import PyramidStack as RefPyramidStack
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    work = tempfile.mkdtemp(prefix="ss_ref_", dir=base)
+    try:
+        os.makedirs(os.path.join(work, "in"))
+        for i, f in enumerate(frames):
+            cv2.imwrite(os.path.join(work, "in", f"f{i:04d}.tif"), f, [int(cv2.IMWRITE_TIFF_COMPRESSION), 1])
+        out_path = None
+        for _ in range(warmup):
+            ref_loader.run_stack_job(work, "in", RefPyramidStack(), output_subdir="out")
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out_path = ref_loader.run_stack_job(work, "in", RefPyramidStack(), output_subdir="out")
+        dt = (time.perf_counter() - t0) / steps
+        img = cv2.imread(out_path, cv2.IMREAD_UNCHANGED) if out_path else None
+        return dt, img
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def cpu_baseline(a, frames):
+    """cpu_baseline of our arm: the unmodified reference on a bounded sample (kind "reference"); without
+    baseline/_ref the oracle port stands in (kind "port")."""
+    from tools import ref_loader
+    n = a.ref_sample_frames if a.ref_sample_frames > 0 else (4 if a.height * a.width > 4e6 else 8)
+    n = max(2, min(n, len(frames)))
+    res = reference_stack_time(a, frames[:n])
+    if res is None:
+        return None
+    dt, _ = res
+    mp = n * a.height * a.width / 1e6
+    return {"value": mp / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+            "sample": f"first {n} of the {a.frames} frames ({workload_name(a)}) through the unmodified reference "
+                      f"(StackJob -> FocusStack -> PyramidStack, uncompressed TIFFs on a RAM disk -> written image), "
+                      f"1 process, {os.cpu_count()} cores visible, {ref_loader.versions()}, {dt:.2f} s; the path is "
+                      f"O(frames) and effectively single-threaded"}
 
 
 def next_rows(a, host):
@@ -152,35 +207,49 @@ def next_rows(a, host):
 
 
 def run_reference(a):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python
-    (numpy + cv2) and cannot travel to the GPU box, so this arm times the oracle port of its arithmetic
-    (oracle/, validated bit-exact against the live reference in the build container) with every host
-    thread; each step is a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores -- the UNMODIFIED
+    reference from baseline/_ref through its public module API (StackJob -> FocusStack -> PyramidStack, TIFF files in,
+    image file out).  Each step fuses a bounded sample of the workload's frames, sized so that the K + W steps end
+    within a few minutes (the reference needs ~2.5 s and ~0.6 GB per 12.6 MP frame and is O(frames)).  If the
+    reference is not installed the oracle port (oracle/, all host threads) stands in and says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyramid_oracle as po
     from shinestacker_b200 import synthetic
-    po.build()
-    cores = po.set_threads(os.cpu_count() or 1)
-    n_sample = max(1, min(a.cpu_sample_frames, a.frames, 16))   # bounded: K + W steps must end within minutes
-    frames = synthetic.make_stack(a.frames, a.height, a.width, np.dtype(a.dtype), seed=2)[:n_sample]
-    for _ in range(a.warmup):
-        po.focus_stack(frames[:1])
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        po.focus_stack(frames)
-    dt = (time.perf_counter() - t0) / a.steps
-    mp = n_sample * a.height * a.width / 1e6
-    val = mp / dt
-    sample = (f"each step = first {n_sample} of the {a.frames} frames ({workload_name(a)}) through "
-              f"oracle/pyramid_oracle (C + OpenMP port of reference pyramid.py, {cores} threads)")
+    from tools import ref_loader
+    mpx = a.height * a.width / 1e6
+    if ref_loader.load() is not None:
+        budget_frames = max(2, int(240.0 / (0.21 * mpx)))          # ~0.21 s per megapixel-frame measured here
+        n_sample = a.ref_sample_frames if a.ref_sample_frames > 0 else budget_frames // max(1, a.steps + a.warmup)
+        n_sample = max(2, min(n_sample, a.frames, 16))
+        frames = synthetic.make_stack(a.frames, a.height, a.width, np.dtype(a.dtype), seed=2)[:n_sample]
+        dt, _ = reference_stack_time(a, frames, steps=a.steps, warmup=a.warmup)
+        kind, cores = "reference", os.cpu_count() or 1
+        sample = (f"each step = first {n_sample} of the {a.frames} frames ({workload_name(a)}) through the unmodified "
+                  f"reference StackJob -> FocusStack -> PyramidStack (baseline/_ref; uncompressed TIFFs on a RAM disk in, "
+                  f"image file out), 1 process, {cores} cores visible, {ref_loader.versions()}")
+    else:
+        from oracle import pyramid_oracle as po
+        po.build()
+        cores = po.set_threads(os.cpu_count() or 1)
+        n_sample = max(1, min(a.ref_sample_frames or 16, a.frames, 16))
+        frames = synthetic.make_stack(a.frames, a.height, a.width, np.dtype(a.dtype), seed=2)[:n_sample]
+        for _ in range(a.warmup):
+            po.focus_stack(frames[:1])
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            po.focus_stack(frames)
+        dt = (time.perf_counter() - t0) / a.steps
+        kind = "port"
+        sample = (f"baseline/_ref absent: each step = first {n_sample} of the {a.frames} frames ({workload_name(a)}) "
+                  f"through oracle/pyramid_oracle (C + OpenMP port of reference pyramid.py, {cores} threads)")
+    val = n_sample * mpx / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "levels": 6, "sample_frames": n_sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -277,6 +346,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt_res = float(t.item())
     fused_resident = out.copy() if rank == 0 else None
+    argmax_l0 = None
+    if rank == 0:          # level-0 arg-max of the timed run (after the exchange the root holds the global map)
+        argmax_l0 = np.empty((H, W), dtype=np.int32)
+        _check(lib.ss_get_argmax(algo._h, 0, argmax_l0.ctypes.data_as(ctypes.c_void_p)))
     res.algo.close()
 
     # ---- leg 2: end to end through the public host-buffer API ---------------------------------------
@@ -364,14 +437,45 @@ def main():
         line["roofline_fp32"] = {"bound": "fp32 issue", "achieved": fp32_rate, "peak": 36.2, "unit": "TFMA/s",
                                  "frac": fp32_rate / 36.2, "algorithmic_chain_steps_per_pixel": 73.5,
                                  "peak_source": "tools/microbench.cu on B200 (scalar FFMA, 124.5 of 128 lanes/clk/SM)"}
+        # ---- CPU side: reference baseline, oracle port, parity of the timed GPU result ------------------
+        n_cpu = max(1, min(a.cpu_sample_frames, N))
+        want_parity = a.check_parity == "on" or (a.check_parity == "auto" and world == 1 and
+                                                 not a.no_cpu_baseline and n_cpu == N)
+        oracle_out = oracle_info = None
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_baseline(a, max(1, min(a.cpu_sample_frames, N)), frames=list(host))
+            port, oracle_out, oracle_info = cpu_port(a, n_cpu, frames=list(host))
+            ref_entry = cpu_baseline(a, list(host))
+            line["cpu_baseline"] = ref_entry if ref_entry is not None else port
+            line["cpu_port"] = port
+        elif want_parity:      # N > 1: rank 0 streams the whole stack through the oracle (not a timed baseline)
+            from oracle import pyramid_oracle as po
+            po.build()
+            po.set_threads(os.cpu_count() or 1)
+            sharp, blurred = synthetic.make_scene(H, W, dtype, seed=2)
+            sharp = np.clip(sharp, 0, maxv).astype(dtype)
+            blurred = np.clip(blurred, 0, maxv).astype(dtype)
+            oracle_out, oracle_info = po.focus_stack(
+                synthetic.frame_from_scene(sharp, blurred, i, N, dtype) for i in range(N))
+        if want_parity and oracle_out is not None:
+            fused_equal = bool(np.array_equal(fused_resident, oracle_out))
+            e2e_equal = bool(np.array_equal(out, oracle_out))
+            argmax_equal = bool(np.array_equal(argmax_l0, oracle_info["best"][0]))
+            line["parity"] = {"fused_equal": fused_equal, "e2e_fused_equal": e2e_equal,
+                              "argmax_l0_equal": argmax_equal,
+                              "oracle_crc32": int(zlib.crc32(np.ascontiguousarray(oracle_out).tobytes())),
+                              "frames_compared": N, "checker": "oracle/pyramid_oracle on the same full stack"}
+            parity_ok = fused_equal and e2e_equal and argmax_equal
+        else:
+            parity_ok = True
         if world == 1 and not a.no_next_rows:
             try:
                 line["next_rows"] = next_rows(a, host)
             except Exception as e:  # pylint: disable=broad-except
                 line["next_rows"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
+        if not parity_ok:
+            sys.stdout.flush()
+            raise SystemExit("bench.py: the GPU result differs from the oracle (see \"parity\" in the line above)")
     lib.ss_host_free(pin)
     lib.ss_host_free(out_pin)
     if world > 1:

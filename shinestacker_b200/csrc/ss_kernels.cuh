@@ -149,7 +149,10 @@ SS_DEV float ss_u16_to_f32(uint32_t w, int k)
 // expand stage's 4-column windows (jj = 2tx+1..2tx+4) are 8-byte aligned
 #define SS_P1W 36
 #define SS_P1H 36
-#define SS_P1S 40
+#ifndef SS_P1S
+#define SS_P1S 38            // row stride (floats): even (8-byte aligned windows) and = 6 mod 32, so that the lanes of the
+                             // halo-ring strips, which walk down the rows, spread over the banks
+#endif
 #define SS_P1P (SS_P1H * SS_P1S + 4)
 #define SS_P1O 1
 // gray^2 patch SQ: rows y in [y0-2, y0+66), columns x in [x0-2, x0+66)
@@ -277,24 +280,25 @@ SS_DEV void ss_reduce_block(const float *p0c, int ii0, int jj0, const float *k25
 {
 #pragma unroll
     for (int i = 0; i < 18; ++i) acc[i] = 0.f;
-    // taps of output jj are patch columns 2*jj + 2 .. 2*jj + 6 (SS_P0X = 8 and j0 = x0/2 - 2)
-    const float *base = p0c + (2 * ii0) * SS_P0S + 2 * jj0 + 2;
+    // taps of output jj are patch columns 2*jj + 2 .. 2*jj + 6 (SS_P0X = 8 and j0 = x0/2 - 2).  The row segment
+    // 2*jj0 + 2 .. 2*jj0 + 16 is fetched as the 16-byte aligned chunks at 2*jj0 .. 2*jj0 + 15 (jj0 is a multiple of
+    // 6, so 2*jj0 floats = 48 bytes * cb) plus one scalar: 5 shared loads per row, and the 8 lanes of a quarter
+    // warp (6 column blocks, then the next channel: plane stride = 8 mod 32 floats) hit 8 distinct bank groups.
+    const float *base = p0c + (2 * ii0) * SS_P0S + 2 * jj0;
     float vv[2][16];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const ss_f2 t = *(const ss_f2 *)(base + 2 * q);
-        vv[0][2 * q] = t.x; vv[0][2 * q + 1] = t.y;
+#define SS_S1_LOAD_ROW(dst, src)                                                                   \
+    {                                                                                              \
+        const ss_f4 a_ = *(const ss_f4 *)(src), b_ = *(const ss_f4 *)((src) + 4),                  \
+                    c_ = *(const ss_f4 *)((src) + 8), d_ = *(const ss_f4 *)((src) + 12);           \
+        (dst)[0] = a_.z; (dst)[1] = a_.w; (dst)[2] = b_.x; (dst)[3] = b_.y; (dst)[4] = b_.z;       \
+        (dst)[5] = b_.w; (dst)[6] = c_.x; (dst)[7] = c_.y; (dst)[8] = c_.z; (dst)[9] = c_.w;       \
+        (dst)[10] = d_.x; (dst)[11] = d_.y; (dst)[12] = d_.z; (dst)[13] = d_.w; (dst)[14] = (src)[16]; \
     }
+    SS_S1_LOAD_ROW(vv[0], base)
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
         // next row's shared loads are issued before this row's FMAs (latency hidden by ~90 FMAs)
-        if (r + 1 < 9) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const ss_f2 t = *(const ss_f2 *)(base + (r + 1) * SS_P0S + 2 * q);
-                vv[(r + 1) & 1][2 * q] = t.x; vv[(r + 1) & 1][2 * q + 1] = t.y;
-            }
-        }
+        if (r + 1 < 9) SS_S1_LOAD_ROW(vv[(r + 1) & 1], base + (r + 1) * SS_P0S)
         const float *v = vv[r & 1];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
@@ -307,6 +311,7 @@ SS_DEV void ss_reduce_block(const float *p0c, int ii0, int jj0, const float *k25
                     acc[o * 6 + c] = ss_fma(v[2 * c + dx], k25[dy * 5 + dx], acc[o * 6 + c]);
         }
     }
+#undef SS_S1_LOAD_ROW
 }
 
 // Expand taps for an N x N pixel block whose top-left pixel has even image coordinates (N = 2 or 4), one
@@ -446,6 +451,38 @@ SS_DEV void ss_s0_convert_u8(float *P0, int tid, const char *raw)
 
 
 
+// uint8 interior tiles, S0 in "owner" form: every thread converts the 4 x 4 pixel block it owns in the later stages
+// (so its stores over the Laplacians parked there need no barrier after its own energy stage) plus two 4-pixel
+// chunks of the 6/8-pixel frame around the 64 x 64 interior (rows 0-5 and 70-75 of the patch: 20 chunks each; rows
+// 6-69: chunks 0, 1, 18, 19).  A chunk = 12 raw bytes -> 3 x 4 floats.  Lane -> 3 consecutive words (interior: stride
+// 3 words over tx, +16 banks for the second row of blocks of the warp): conflict-free.
+SS_DEV void ss_s0_chunk_u8(float *P0, const char *raw, int row, int c4)
+{
+    const uint32_t *src = (const uint32_t *)(raw + row * SS_RAWS + 12 * c4);
+    const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
+    float *dst = P0 + row * SS_P0S + 4 * c4;
+    *(ss_f4 *)dst = ss_mk4(ss_u8_to_f32(w0, 0), ss_u8_to_f32(w0, 3), ss_u8_to_f32(w1, 2), ss_u8_to_f32(w2, 1));
+    *(ss_f4 *)(dst + SS_P0P) = ss_mk4(ss_u8_to_f32(w0, 1), ss_u8_to_f32(w1, 0), ss_u8_to_f32(w1, 3), ss_u8_to_f32(w2, 2));
+    *(ss_f4 *)(dst + 2 * SS_P0P) = ss_mk4(ss_u8_to_f32(w0, 2), ss_u8_to_f32(w1, 1), ss_u8_to_f32(w2, 0), ss_u8_to_f32(w2, 3));
+}
+
+SS_DEV void ss_s0_owner_u8(float *P0, int tid, const char *raw)
+{
+    const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ss_s0_chunk_u8(P0, raw, 4 * ty + SS_P0Y + r, tx + 2);
+    {
+        const int rr = tid / 20, c4 = tid - rr * 20;                 // tid < 240: the top / bottom six rows
+        const int k = tid - 240;                                     // else: left / right chunks of rows 6 ..
+        if (tid < 240) ss_s0_chunk_u8(P0, raw, rr < 6 ? rr : SS_TY + rr, c4);
+        else ss_s0_chunk_u8(P0, raw, SS_P0Y + (k >> 2), (k & 3) < 2 ? (k & 3) : 16 + (k & 3));
+    }
+    {
+        const int k = tid + 16;                                      // items 256 .. 495 are all of the second kind
+        if (k < 256) ss_s0_chunk_u8(P0, raw, SS_P0Y + (k >> 2), (k & 3) < 2 ? (k & 3) : 16 + (k & 3));
+    }
+}
+
 // S0 for tiles that touch an image border: same 8-pixel units as the interior path whenever a unit lies
 // inside the image (vector loads from the REFLECT101-mapped row), per-pixel reflected loads otherwise.
 template <typename InT>
@@ -534,6 +571,9 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
     int32_t *const st_idx = p.best_idx + group * p.group_stride;
     float *const st_fused = p.fused + 3 * group * p.group_stride;
     // rows of the coefficient planes 16-byte aligned?  (vector stores of the first frame's coefficients)
+    // g_{l+1} rows 8-byte aligned?  (pair stores from the reduce stage; the base level is tightly packed)
+    const bool gpair = (((p.gnext_pitch | p.gnext_plane_stride | p.gnext_frame_stride) & 1) == 0) &&
+                       ((((unsigned long long)p.gnext) & 7) == 0);
     const bool state_vec4 = ((p.w & 3) == 0) && ((plane_px & 3) == 0) && ((((unsigned long long)st_fused) & 15) == 0);
 
     SS_PT_DECL(float, be, 16);
@@ -562,6 +602,8 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + f_begin * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
         ss_mbar_wait(mbar, mbar_phase);
         mbar_phase ^= 1;
+        ss_s0_owner_u8(P0, threadIdx.x, (const char *)P1);
+        __syncthreads();
     }
 #else
     (void)tmap;
@@ -579,8 +621,13 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             ss_cp_async_wait();
         }
         SS_SYNC();
+        SS_THREADS(tid) { ss_s0_owner_u8(P0, tid, (const char *)P1); }
+        SS_SYNC();
     }
 #endif
+    // uint8 interior tiles: the float patch of frame f is produced at the END of frame f-1's energy stage (each thread
+    // converts the block it owns + a share of the frame around the interior), so the loop body starts with S1
+    const bool s0_owner = interior && sizeof(InT) == 1;
     if (!fresh) {
         SS_THREADS(tid)
         {
@@ -599,14 +646,12 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
         const char *frame = (const char *)p.in + (long long)f * p.in_frame_stride;
         const bool first_frame = fresh && f == f_begin;   // every in-image pixel takes this frame
         // ---- S0: g_l patch -------------------------------------------------------------------------
-        if (interior) {
+        if (s0_owner) {
+            // nothing to do: P0 was filled before the loop / at the end of the previous iteration
+        } else if (interior) {
             SS_THREADS(tid)
             {
-                if constexpr (sizeof(InT) == 1) {
-                    // the raw bytes were copied asynchronously during the previous energy stage (or, for
-                    // the first frame, just before the loop)
-                    ss_s0_convert_u8(P0, tid, (const char *)P1);
-                } else if constexpr (sizeof(InT) == 2) {
+                if constexpr (sizeof(InT) == 2) {
                     ss_s0_async_u16(p, frame, x0, y0, tid, (char *)P1);
                     ss_cp_async_wait();
                 } else if (!pref32) {
@@ -621,7 +666,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
         } else {
             SS_THREADS(tid) { ss_s0_border<InT>(p, frame, x0, y0, tid, P0); }
         }
-        SS_SYNC();
+        if (!s0_owner) SS_SYNC();
         // ---- S1: reduce -> P1 ------------------------------------------------------------------------
         if (fast) {
             SS_THREADS(tid)
@@ -636,6 +681,37 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     for (int o = 0; o < 3; ++o)
 #pragma unroll
                         for (int c = 0; c < 6; ++c) dst[o * SS_P1S + c] = acc[o * 6 + c];
+                    // the 32 x 32 interior of P1 is this tile's share of g_{l+1}: straight from the registers to
+                    // global memory as aligned pairs (J is even: j0, jj0 and c are).  Row / pair validity is hoisted
+                    // into six predicates so that the stores compile to predicated STG.64 without branches.
+                    float *gdst = p.gnext + f * p.gnext_frame_stride + ch * p.gnext_plane_stride +
+                                  (long long)(i0 + ii0) * p.gnext_pitch + j0 + jj0;
+                    bool rok[3], cok[3];
+#pragma unroll
+                    for (int o = 0; o < 3; ++o)
+                        rok[o] = (ii0 + o >= 2) & (ii0 + o < SS_P1H - 2) & (i0 + ii0 + o < p.h2);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        cok[c] = (jj0 + 2 * c >= 2) & (jj0 + 2 * c < SS_P1W - 2) & (j0 + jj0 + 2 * c + 1 < p.w2);
+                    if (gpair) {
+#pragma unroll
+                        for (int o = 0; o < 3; ++o)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                if (rok[o] & cok[c])
+                                    *(ss_f2 *)(gdst + o * p.gnext_pitch + 2 * c) = ss_mk2(acc[o * 6 + 2 * c], acc[o * 6 + 2 * c + 1]);
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < 3; ++o)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                if (rok[o] & cok[c]) {
+                                    gdst[o * p.gnext_pitch + 2 * c] = acc[o * 6 + 2 * c];
+                                    gdst[o * p.gnext_pitch + 2 * c + 1] = acc[o * 6 + 2 * c + 1];
+                                }
+                    }
+                    // (fast tiles never contain the last column of an odd-width g_{l+1}: either 2*w2 is a multiple of
+                    // 8, or the tile ends at least 4 columns before the tail columns -- so no pair straddles w2)
                 }
             }
         } else {
@@ -674,7 +750,7 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             SS_SYNC();
         }
         // ---- S2: g_{l+1} interior -> global; Laplacian (parked in P0), gray^2 -> SQ ----------------------
-        SS_THREADS(tid)
+        if (!fast) SS_THREADS(tid)
         {
             // the 32 x 32 interior of P1 is this tile's share of g_{l+1}: thread -> (row tid>>3, 4 columns
             // 4*(tid&7)..) of every channel, written as one 16-byte store when the row pitch allows it
@@ -774,17 +850,18 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
 #pragma unroll
                             for (int b = 0; b < 3; ++b) win[a][b] = r1c[a * SS_P1S + b];
                         ss_expand_block<2>(win, p.k25, acc);
-#pragma unroll
-                        for (int r = 0; r < 2; ++r)
-#pragma unroll
-                            for (int c = 0; c < 2; ++c)
-                                gr[r * 2 + c] = ss_fma(ss_fma(-4.f, acc[r * 2 + c], r0c[r * SS_P0S + c]), wgt, gr[r * 2 + c]);
+                        // g_l of the quad: two aligned pairs (pp is even)
+                        const ss_f2 g0 = *(const ss_f2 *)r0c, g1 = *(const ss_f2 *)(r0c + SS_P0S);
+                        gr[0] = ss_fma(ss_fma(-4.f, acc[0], g0.x), wgt, gr[0]);
+                        gr[1] = ss_fma(ss_fma(-4.f, acc[1], g0.y), wgt, gr[1]);
+                        gr[2] = ss_fma(ss_fma(-4.f, acc[2], g1.x), wgt, gr[2]);
+                        gr[3] = ss_fma(ss_fma(-4.f, acc[3], g1.y), wgt, gr[3]);
                         const int step = it == 0 ? -1 : 2;
                         r1c += step * SS_P1P;
                         r0c += step * SS_P0P;
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) SQ[(qq + (q >> 1)) * SS_SQS + pp + (q & 1)] = ss_mul(gr[q], gr[q]);
+                    *(ss_f2 *)(SQ + qq * SS_SQS + pp) = ss_mk2(ss_mul(gr[0], gr[0]), ss_mul(gr[1], gr[1]));
+                    *(ss_f2 *)(SQ + (qq + 1) * SS_SQS + pp) = ss_mk2(ss_mul(gr[2], gr[2]), ss_mul(gr[3], gr[3]));
                 }
             }
         } else {
@@ -832,6 +909,11 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             SS_SYNC();
         }
         // ---- S3: energy + running arg-max ----------------------------------------------------------
+#ifdef SS_HOST_EMU
+        if (s0_owner && f + 1 < f_end) {   // stands in for the TMA copy that runs during the energy stage
+            SS_THREADS(tid) { ss_s0_async_u8(p, frame + p.in_frame_stride, x0, y0, tid, (char *)P1); }
+        }
+#endif
         SS_THREADS(tid)
         {
             const int tx = tid & 15, ty = tid >> 4;
@@ -839,14 +921,10 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             const bool take_all = first_frame;
             if (pref32 && f + 1 < f_end)   // P0 is not read any more in this frame
                 ss_s0_bulk_f32(p, frame + p.in_frame_stride, x0, y0, tid, P0, mbar);
-            if (interior && sizeof(InT) == 1 && f + 1 < f_end) {   // P1 is dead until the next S1
 #ifndef SS_HOST_EMU
-                if (tid == 0)
-                    ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + (f + 1) * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
-#else
-                ss_s0_async_u8(p, frame + p.in_frame_stride, x0, y0, tid, (char *)P1);
+            if (s0_owner && f + 1 < f_end && tid == 0)   // P1 is dead until the next S1: raw bytes of the next frame
+                ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + (f + 1) * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
 #endif
-            }
             float e[16];
             if (fast) {
 #pragma unroll
@@ -925,17 +1003,22 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     }
                 }
             }
-        }
-        // S3 reads the parked Laplacians from P0, so it must finish before the next frame's S0; the
-        // asynchronous copies of the next frame's raw patch must have landed as well
+            // uint8 interior tiles: S0 of the next frame.  This thread is done with the Laplacians parked in its own
+            // block, and nobody reads the frame around the interior after S2, so no barrier is needed first; the raw
+            // bytes of the next frame must have landed
+            if (s0_owner && f + 1 < f_end) {
 #ifndef SS_HOST_EMU
-        if (((interior && sizeof(InT) == 1) || pref32) && f + 1 < f_end) {
+                ss_mbar_wait(mbar, mbar_phase);
+#endif
+                ss_s0_owner_u8(P0, tid, (const char *)P1);
+            }
+        }
+        // float32 levels: the bulk copies of the next frame's patch must have landed
+#ifndef SS_HOST_EMU
+        if (s0_owner && f + 1 < f_end) mbar_phase ^= 1;
+        if (pref32 && f + 1 < f_end) {
             ss_mbar_wait(mbar, mbar_phase);
             mbar_phase ^= 1;
-        }
-#else
-        if (interior && sizeof(InT) == 1) {
-            SS_THREADS(tid) { ss_cp_async_wait(); }
         }
 #endif
         SS_SYNC();

@@ -925,7 +925,13 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
         p.init = h->have_state ? 0 : 1;
         memcpy(p.k25, h->k25, sizeof(p.k25));
         dim3 grid((v.w + SS_TX - 1) / SS_TX, (v.h + SS_TY - 1) / SS_TY, groups);
-        const size_t smem = SS_SMEM_BYTES;
+        size_t smem = SS_SMEM_BYTES;
+        if (const char *xs = getenv("SS_EXTRA_SMEM")) {   // experiment knob: e.g. 20000 forces one CTA per SM
+            smem += (size_t)atoi(xs);
+            cudaFuncSetAttribute(ss_level_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(ss_level_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(ss_level_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
         if (h->profile) {
             if (h->ltimers_used == h->ltimers.size()) {
                 ss_handle::LevelTimer t;

@@ -131,6 +131,84 @@ def open_plain_tiff(path):
         return None
 
 
+def probe_header(path):
+    """(height, width, channels, dtype) that ``read_img`` (reference utils.py:11-20) would deliver for ``path``, read
+    from the file header only, or ``None`` when the header does not settle it (the caller then decodes the file).
+    Covers what the reference's own pipeline produces and consumes: baseline / progressive JPEG without an EXIF
+    block (cv2 rotates by the EXIF orientation), 8/16-bit RGB PNG, 8/16-bit RGB classic TIFF."""
+    try:
+        ext = path.split(".")[-1]
+        with open(path, "rb") as f:
+            head = f.read(32)
+            if ext in ("tif", "tiff"):
+                if head[:4] == b"II*\x00":
+                    e = "<"
+                elif head[:4] == b"MM\x00*":
+                    e = ">"
+                else:
+                    return None
+                (ifd,) = struct.unpack(e + "I", head[4:8])
+                f.seek(ifd)
+                (n,) = struct.unpack(e + "H", f.read(2))
+                raw = f.read(12 * n)
+                if len(raw) < 12 * n:
+                    return None
+                vals = {}
+                for i in range(n):
+                    tag, typ, cnt = struct.unpack(e + "HHI", raw[12 * i:12 * i + 8])
+                    if tag not in (256, 257, 258, 262, 277, 339) or typ not in (3, 4):
+                        continue
+                    fmt, size = ("H", 2) if typ == 3 else ("I", 4)
+                    if cnt * size <= 4:
+                        data = raw[12 * i + 8:12 * i + 8 + cnt * size]
+                    else:
+                        (off,) = struct.unpack(e + "I", raw[12 * i + 8:12 * i + 12])
+                        f.seek(off)
+                        data = f.read(cnt * size)
+                    vals[tag] = struct.unpack(e + fmt * cnt, data)
+                if any(t not in vals for t in (256, 257, 258, 262)):
+                    return None
+                spp = vals.get(277, (1,))[0]
+                bits = vals[258]
+                if vals[262][0] != 2 or spp != 3 or len(bits) != 3 or any(v != 1 for v in vals.get(339, (1,))):
+                    return None
+                if all(b == 8 for b in bits):
+                    dt = np.uint8
+                elif all(b == 16 for b in bits):
+                    dt = np.uint16
+                else:
+                    return None
+                return int(vals[257][0]), int(vals[256][0]), 3, np.dtype(dt)
+            if ext == "png":
+                if head[:8] != b"\x89PNG\r\n\x1a\n" or head[12:16] != b"IHDR":
+                    return None
+                w, h, depth, ctype = struct.unpack(">IIBB", head[16:26])
+                if ctype != 2 or depth not in (8, 16):
+                    return None
+                return int(h), int(w), 3, np.dtype(np.uint8 if depth == 8 else np.uint16)
+            if ext in ("jpg", "jpeg"):
+                if head[:2] != b"\xff\xd8":
+                    return None
+                f.seek(2)
+                while True:
+                    b = f.read(4)
+                    if len(b) < 4 or b[0] != 0xFF:
+                        return None
+                    marker, (length,) = b[1], struct.unpack(">H", b[2:4])
+                    if marker == 0xE1:
+                        return None          # APP1 (EXIF): cv2.imread may rotate the image
+                    if marker in (0xC0, 0xC1, 0xC2):
+                        d = f.read(5)
+                        h, w = struct.unpack(">HH", d[1:5])
+                        return int(h), int(w), 3, np.dtype(np.uint8)     # default imread flags: 8-bit BGR
+                    if marker == 0xDA or length < 2:
+                        return None
+                    f.seek(length - 2, 1)
+    except (OSError, ValueError, struct.error, IndexError):
+        return None
+    return None
+
+
 def read_frame(path, read_img):
     """What the stackers' decode-ahead workers call: the mapped file when the fast path applies (``.tif`` /
     ``.tiff`` only), otherwise ``read_img(path)`` (cv2.imread, as the reference)."""

@@ -326,13 +326,50 @@ class PyramidStack(PyramidBase):
             out.append(a)
         return out
 
+    def _probe(self, path):
+        """(shape, dtype, ndim, channels) of what read_img would return for ``path``: from the header when that is
+        conclusive, else by decoding the file (like the reference's validation pass, pyramid.py:157-158)."""
+        if not os.path.isfile(path):
+            raise RuntimeError("File does not exist: " + path)     # reference utils.py:12-13
+        hdr = fastio.probe_header(path) if fastio.ENABLED else None
+        if hdr is not None:
+            h, w, ch, dtype = hdr
+            return (h, w, ch), dtype
+        img = read_img(path)
+        if img is None:
+            return None
+        return img.shape, img.dtype
+
     def focus_stack(self, filenames):
-        """reference pyramid.py:150-179: list of image paths -> fused H x W x 3 BGR array of the
-        input dtype.  Each file is decoded once (the reference decodes it twice); progress steps
-        ``i`` (validated) and ``i + n`` (processed) are reported for every frame like the reference."""
+        """reference pyramid.py:150-179: list of image paths -> fused H x W x 3 BGR array of the input dtype.
+
+        Two passes in the reference's order: every file is validated first (steps 0 .. n-1: shape / bit depth of
+        all frames against the first one, pyramid.py:155-169 -- here from the file headers, so a mismatch in
+        frame k surfaces before any GPU work), then processed (steps n .. 2n-1, pyramid.py:170-177; each file is
+        decoded once, ahead of the upload, on worker threads)."""
         n = len(filenames)
         metadata = None
-        ring = None
+        for i, img_path in enumerate(filenames):
+            self.print_message(f": validating file {img_path.split('/')[-1]}")
+            probed = self._probe(img_path)
+            if probed is None:
+                raise ImageLoadError(img_path)
+            shape, dtype = probed
+            if metadata is None:
+                if len(shape) != 3 or shape[2] != 3 or dtype not in (np.uint8, np.uint16):
+                    raise ImageLoadError(img_path, "expected a 3-channel 8 or 16 bit image")
+                metadata = (tuple(shape[:2]), np.dtype(dtype))
+                self.dtype = metadata[1]
+                self.num_pixel_values = 256 if self.dtype == np.uint8 else 65536
+                self.max_pixel_value = 255 if self.dtype == np.uint8 else 65535
+            else:
+                if tuple(shape[:2]) != metadata[0]:
+                    raise ShapeError(metadata[0], tuple(shape[:2]))
+                if np.dtype(dtype) != metadata[1]:
+                    raise BitDepthError(metadata[1], np.dtype(dtype))
+            self._callbacks(i)
+        if metadata is None:
+            raise ImageLoadError("", "empty file list")
         # decode ahead on worker threads (cv2.imread releases the GIL); frames are consumed in stack order
         pool = ThreadPoolExecutor(max_workers=self.decode_threads) if self.decode_threads > 0 and n > 1 else None
         pending = {}
@@ -347,26 +384,19 @@ class PyramidStack(PyramidBase):
             return pending.pop(i).result()
 
         try:
+            self._ensure_handle(metadata[0], metadata[1], n)
+            frame_bytes = metadata[0][0] * metadata[0][1] * 3 * metadata[1].itemsize
+            ring = self._staging(frame_bytes, 2 * max(self.batch_frames, 1))
             for i, img_path in enumerate(filenames):
-                self.print_message(f": validating file {img_path.split('/')[-1]}")
+                self.print_message(f": processing file {img_path.split('/')[-1]}")
                 img = fetch(i)
                 if img is None:
                     raise ImageLoadError(img_path)
-                if metadata is None:
-                    metadata = (img.shape[:2], img.dtype)
-                    if img.ndim != 3 or img.shape[2] != 3 or img.dtype not in (np.uint8, np.uint16):
-                        raise ImageLoadError(img_path, "expected a 3-channel 8 or 16 bit image")
-                    self._set_metadata(img)
-                    self._ensure_handle(img.shape, img.dtype, n)
-                    ring = self._staging(img.nbytes, 2 * max(self.batch_frames, 1))
-                else:
-                    self._validate(img, *metadata)
-                self._callbacks(i)
-                self.print_message(f": processing file {img_path.split('/')[-1]}")
+                if img.ndim != 3 or img.shape[2] != 3:
+                    raise ImageLoadError(img_path, "expected a 3-channel 8 or 16 bit image")
+                self._validate(img, *metadata)      # the decoder has the last word (header and decoder agree normally)
                 self._push(i, img, ring)
                 self._callbacks(i + n)
-            if metadata is None:
-                raise ImageLoadError("", "empty file list")
             self.print_message(': pyramids fusion completed')
             return self._finish(n, metadata[0])
         except BaseException:
@@ -376,7 +406,13 @@ class PyramidStack(PyramidBase):
         finally:
             if pool is not None:
                 for fut in pending.values():
-                    fut.cancel()
+                    if not fut.cancel():
+                        try:                      # a decoded-ahead mapped TIFF must not leak its mapping
+                            res = fut.result()
+                            if isinstance(res, fastio.PlainTiff):
+                                res.close()
+                        except Exception:  # pylint: disable=broad-except
+                            pass
                 pool.shutdown(wait=True)
 
     def focus_stack_arrays(self, frames):

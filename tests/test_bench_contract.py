@@ -1,5 +1,5 @@
-"""The JSON-line contract of bench.py, checked without a GPU: the reference arm (the CPU oracle port) really runs
-here on a tiny sample, and the committed line of the last GPU run (profiles/r1_final2_bench.json) carries every key
+"""The JSON-line contract of bench.py, checked without a GPU: the reference arm (the unmodified reference from
+baseline/_ref when it is installed, else the CPU oracle port) really runs here on a tiny sample, and the committed line of the last GPU run (profiles/r1_final2_bench.json) carries every key
 the driver reads."""
 import json
 import os
@@ -9,6 +9,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 COMMON = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
           "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"}
 
@@ -22,8 +23,19 @@ def test_reference_arm_prints_one_valid_line():
     d = json.loads(lines[0])
     assert COMMON <= set(d) and d["impl"] == "reference" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["unit"] == "MP/s" and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from tools import ref_loader
+    expected = "reference" if ref_loader.reference_root() else "port"
+    assert d["cpu_baseline"]["kind"] == expected and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_falls_back_to_the_port_without_the_reference(tmp_path):
+    env = dict(os.environ, SHINESTACKER_REF="", SS_NO_REFERENCE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--frames", "2",
+                          "--height", "96", "--width", "128", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, env=env, check=True).stdout.strip().splitlines()
+    d = json.loads([ln for ln in out if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["kind"] == "port" and "absent" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_is_silent_on_other_ranks():

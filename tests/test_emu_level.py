@@ -67,6 +67,8 @@ def run_levels(emu, oracle, frames, split=None):
     ("noise", 2, 288, 512, np.uint8, 8, None),      # interior (fast-path) tiles at levels 0 and 1
     ("stack", 3, 300, 448, np.uint16, 9, 2),
     ("noise", 2, 384, 700, np.uint8, 10, None),     # interior tile + tail columns (700 % 8 == 4)
+    ("stack", 5, 224, 320, np.uint8, 11, None),     # interior tiles, 5 frames through the prefetch pipeline
+    ("stack", 4, 224, 320, np.uint8, 12, 3),        # ... and a second batch that continues the running state
 ])
 def test_emulated_level_kernel_matches_oracle(emu, oracle, gen, n, h, w, dtype, seed, split):
     f = synthetic.make_stack if gen == "stack" else synthetic.make_noise_stack

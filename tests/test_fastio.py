@@ -92,3 +92,27 @@ def test_stackers_stage_mapped_frames_in_order(tmp_path, monkeypatch, algo_cls, 
     assert kinds == ["PlainTiff", "PlainTiff", "ndarray", "PlainTiff", "PlainTiff"]
     for got, f in zip(staged, frames):
         assert np.array_equal(got, f)
+
+
+@pytest.mark.parametrize("ext,dtype,params", [
+    ("tif", np.uint8, UNCOMPRESSED), ("tif", np.uint16, UNCOMPRESSED), ("tif", np.uint8, []), ("tif", np.uint16, []),
+    ("png", np.uint8, []), ("png", np.uint16, []), ("jpg", np.uint8, []), ("jpeg", np.uint8, [int(cv2.IMWRITE_JPEG_PROGRESSIVE), 1]),
+])
+def test_header_probe_agrees_with_read_img(tmp_path, ext, dtype, params):
+    """The validation pass reads headers only; what it reports must be what read_img (reference utils.py:11-20) delivers."""
+    img = np.random.default_rng(5).integers(0, np.iinfo(dtype).max + 1, (37, 61, 3)).astype(dtype)
+    p = str(tmp_path / f"a.{ext}")
+    cv2.imwrite(p, img, params)
+    ref = read_img(p)
+    assert fastio.probe_header(p) == (ref.shape[0], ref.shape[1], ref.shape[2], ref.dtype)
+
+
+def test_header_probe_declines_what_it_cannot_settle(tmp_path):
+    img = np.random.default_rng(6).integers(0, 256, (20, 30, 3)).astype(np.uint8)
+    cv2.imwrite(str(tmp_path / "gray.tif"), img[..., 0])
+    cv2.imwrite(str(tmp_path / "rgba.png"), np.dstack([img, img[..., :1]]))
+    cv2.imwrite(str(tmp_path / "gray.png"), img[..., 0])
+    (tmp_path / "junk.tif").write_bytes(b"not a tiff at all")
+    (tmp_path / "empty.jpg").write_bytes(b"")
+    for name in ("gray.tif", "rgba.png", "gray.png", "junk.tif", "empty.jpg", "missing.tif"):
+        assert fastio.probe_header(str(tmp_path / name)) is None

@@ -115,7 +115,7 @@ def test_file_interface_errors_and_callbacks(tmp_path, oracle):
     out = algo.focus_stack(paths)
     ref, _ = oracle.focus_stack(frames)
     assert np.array_equal(out, ref)
-    assert sorted(algo.process.steps) == list(range(8))          # 2 steps per frame
+    assert algo.process.steps == list(range(8))                  # validation pass first, then processing (2 steps per frame)
     algo.process = Proc(stop_at=3)
     with pytest.raises(RunStopException):
         algo.focus_stack(paths)

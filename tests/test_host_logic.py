@@ -66,7 +66,10 @@ def test_frames_are_pushed_in_order_with_two_steps_each(tmp_path, stubbed, threa
     assert [i for i, _ in stubbed] == list(range(7))
     for (_, img), f in zip(stubbed, frames):
         assert np.array_equal(img, f)
-    assert sorted(algo.process.steps) == list(range(14))          # steps_per_frame = 2
+    # the reference's order (pyramid.py:155-177): every file is validated (steps 0..n-1) before any is processed
+    assert algo.process.steps == list(range(14))                  # steps_per_frame = 2
+    msgs = [m for m in algo.process.msgs if "file" in m]
+    assert all("validating" in m for m in msgs[:7]) and all("processing" in m for m in msgs[7:])
     assert any("validating file f000.tif" in m for m in algo.process.msgs)
     assert any("processing file f006.tif" in m for m in algo.process.msgs)
 
@@ -92,6 +95,20 @@ def test_validation_errors_match_the_reference_types(tmp_path, stubbed):
     cv2.imwrite(gray, np.zeros((40, 56), np.uint8))
     with pytest.raises(ImageLoadError):
         PyramidStack().focus_stack([gray] + paths)
+
+
+def test_shape_error_surfaces_before_any_frame_is_uploaded(tmp_path, stubbed):
+    """reference pyramid.py:155-169: the validation pass covers ALL files before the first pyramid is built."""
+    import cv2
+    frames = synthetic.make_noise_stack(4, 40, 56, np.uint8, 5)
+    paths = _write(tmp_path, frames)
+    cv2.imwrite(paths[2], np.zeros((44, 56, 3), np.uint8))
+    algo = PyramidStack()
+    algo.process = Proc()
+    algo.do_step_callback = True
+    with pytest.raises(ShapeError):
+        algo.focus_stack(paths)
+    assert stubbed == [] and algo.process.steps == [0, 1]
 
 
 def test_cancellation_raises_run_stop(tmp_path, stubbed):

@@ -112,6 +112,37 @@ SS_DEV void ss_mbar_wait(uint64_t *bar, unsigned parity)
 }
 #endif
 
+// Tensor memory (TMEM, 512 columns x 128 lanes x 32 bit per SM) as a per-thread scratchpad: lane 32*(warp%4) + lane of
+// the warp, 48 columns per thread (warps 4-7 use columns 48..95).  The Laplacians of a thread's own 4 x 4 block are
+// parked there between the Laplacian stage and the arg-max update of the same thread -- data that never crosses
+// threads, so it need not occupy shared-memory bandwidth (tcgen05.st / tcgen05.ld run on their own datapath).
+#define SS_TM_COLS 128
+#ifndef SS_HOST_EMU
+SS_DEV void ss_tm_st16(uint32_t taddr, const float *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+                 "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+                 "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+                 "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+SS_DEV void ss_tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+SS_DEV void ss_tm_ld16(uint32_t taddr, float *v)
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+#endif
+
 SS_DEV ss_f2 ss_mk2(float a, float b) { ss_f2 r; r.x = a; r.y = b; return r; }
 SS_DEV ss_f4 ss_mk4(float a, float b, float c, float d) { ss_f4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 
@@ -167,7 +198,7 @@ SS_DEV float ss_u16_to_f32(uint32_t w, int k)
                            // 76 x 496-byte uint16 staging area that continues into SQ
 #define SS_P1OFF ((3 * SS_P0P + 31) / 32 * 32)   // P1 / raw staging starts 128-byte aligned (TMA destination)
 #define SS_SMEM_FLOATS (SS_P1OFF + SS_P1REGION + SS_SQH * SS_SQS)
-#define SS_SMEM_BYTES (SS_SMEM_FLOATS * 4 + 16)   // + the mbarrier
+#define SS_SMEM_BYTES (SS_SMEM_FLOATS * 4 + 16 + 64)   // + the mbarrier + per-warp maxima of gray^2 (energy-stage skip)
 
 struct SsLevelParams {
     int h, w;            // size of g_l
@@ -199,8 +230,30 @@ struct SsLevelParams {
                          // next frame's patch while the energy stage runs
     int tma_row0;        // uint8 level 0: row of the batch's first frame in the frame-store tensor map (the store
                          // begins 8 bytes into its allocation, so byte column 8 + 3*(x0-8) is 16-byte aligned)
+    float skip_factor;   // > 0: the energy stage of a warp is skipped for a frame when skip_factor * (largest gray^2 the
+                         // warp's windows can see) < (smallest running best energy of the warp's pixels); see ss_skip_factor
     float k25[25];
 };
+
+// Exactness of the skip: with all 25 taps >= 0 every energy is a chain e = fma(v_24, k_24, ... fma(v_0, k_0, +0)) of
+// non-negative terms, so e <= (sum k_i) * max(v) * (1 + 2^-24)^25 < (sum k_i) * (1 + 2^-18) * max(v).  If that bound is
+// below the running best of every pixel of the warp, no pixel can satisfy the strict '>' and the stage has no effect.
+// Returns 0 (skip disabled) when a tap is negative (gen_kernel > 0.5).
+static inline float ss_skip_factor(const float *k25)
+{
+    double sum = 0.0;
+    for (int i = 0; i < 25; ++i) {
+        if (!(k25[i] >= 0.f)) return 0.f;
+        sum += (double)k25[i];
+    }
+    float f = (float)(sum * (1.0 + 1.0 / 262144.0));
+    while ((double)f < sum * (1.0 + 1.0 / 262144.0)) f = __builtin_nextafterf(f, 2.f * f + 1.f);
+    return f;
+}
+
+#ifdef SS_HOST_EMU
+static long long ss_emu_skipped_threads = 0;   // test statistic: thread-frames whose energy stage was skipped
+#endif
 
 SS_DEV int ss_reflect_clamp(int i, int n)
 {
@@ -577,11 +630,29 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
     const bool state_vec4 = ((p.w & 3) == 0) && ((plane_px & 3) == 0) && ((((unsigned long long)st_fused) & 15) == 0);
 
     SS_PT_DECL(float, be, 16);
+    SS_PT_DECL(float, bemin, 1);   // smallest of the 16 (energy-stage skip)
+    // exact skip of the energy stage (see ss_skip_factor): register-blocked tiles that lie fully inside the image
+    const bool skip_on = p.skip_factor > 0.f && fast && full;
+    float *const wmax = smem + SS_SMEM_FLOATS + 4;   // 8 + 5 floats behind the mbarrier
 
-    // float32 levels, interior fast tiles: own-block Laplacians go to a per-CTA global scratch instead of being
-    // parked in P0, and the NEXT frame's patch is bulk-copied into P0 while the energy stage runs
-    const bool pref32 = sizeof(InT) == 4 && interior && fast && p.lap_scratch != nullptr;
-    float *const scratch = pref32 ? p.lap_scratch + (long long)cta_linear * (3 * SS_TX * SS_TY) : nullptr;
+    // register-blocked tiles park the own-block Laplacians in tensor memory (per-thread data), so P0 is dead after S2;
+    // float32 levels, interior fast tiles: the NEXT frame's patch is bulk-copied into P0 while the energy stage runs
+    const bool pref32 = sizeof(InT) == 4 && interior && fast;
+    (void)cta_linear;
+#ifdef SS_HOST_EMU
+    SS_PT_DECL(float, tmv, 48);    // stands in for the thread's 48 tensor-memory columns
+#else
+    uint32_t *tm_slot = (uint32_t *)(smem + SS_SMEM_FLOATS + 4 + 14);
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ss_saddr(tm_slot)), "n"(SS_TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_base = *tm_slot;
+    const uint32_t tm_addr = tm_base + ((((threadIdx.x >> 5) & 3) * 32u) << 16) + ((threadIdx.x >> 7) ? 48u : 0u);
+#endif
     // uint8, interior tiles: raw patch of frame f arrives by TMA (device) / memcpy (host emulation)
 #ifndef SS_HOST_EMU
     uint64_t *mbar = (uint64_t *)(smem + SS_SMEM_FLOATS);
@@ -639,6 +710,12 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     const int x = x0 + 4 * tx + c, y = y0 + 4 * ty + r;
                     if (x < p.w && y < p.h) SS_PT(be)[r * 4 + c] = st_e[(long long)y * p.w + x];
                 }
+            if (skip_on) {
+                float m = SS_PT(be)[0];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) m = fminf(m, SS_PT(be)[q]);
+                SS_PT(bemin)[0] = m;
+            }
         }
     }
 
@@ -796,41 +873,54 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                         win[a][0] = u.x; win[a][1] = u.y; win[a][2] = v.x; win[a][3] = v.y;
                     }
                     ss_expand_block<4>(win, p.k25, acc);
+                    const int chi = it == 0 ? 1 : (it == 1 ? 0 : 2);   // plane of this iteration
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        float *gp = p0c + r * SS_P0S;
-                        const ss_f4 g = *(const ss_f4 *)gp;
-                        const float l0 = ss_fma(-4.f, acc[r * 4 + 0], g.x), l1 = ss_fma(-4.f, acc[r * 4 + 1], g.y);
-                        const float l2 = ss_fma(-4.f, acc[r * 4 + 2], g.z), l3 = ss_fma(-4.f, acc[r * 4 + 3], g.w);
+                        const ss_f4 g = *(const ss_f4 *)(p0c + r * SS_P0S);
+                        // the Laplacians replace the expand sums in their registers
+                        acc[r * 4 + 0] = ss_fma(-4.f, acc[r * 4 + 0], g.x); acc[r * 4 + 1] = ss_fma(-4.f, acc[r * 4 + 1], g.y);
+                        acc[r * 4 + 2] = ss_fma(-4.f, acc[r * 4 + 2], g.z); acc[r * 4 + 3] = ss_fma(-4.f, acc[r * 4 + 3], g.w);
                         if (pref32 && first_frame) {   // all pixels win: straight into the running state (0 + lap)
-                            float *fd = st_fused + (it == 0 ? 1 : (it == 1 ? 0 : 2)) * plane_px +
-                                        (long long)(y0 + 4 * ty + r) * p.w + x0 + 4 * tx;
+                            float *fd = st_fused + chi * plane_px + (long long)(y0 + 4 * ty + r) * p.w + x0 + 4 * tx;
                             if (state_vec4) {
-                                *(ss_f4 *)fd = ss_mk4(ss_add(0.f, l0), ss_add(0.f, l1), ss_add(0.f, l2), ss_add(0.f, l3));
+                                *(ss_f4 *)fd = ss_mk4(ss_add(0.f, acc[r * 4]), ss_add(0.f, acc[r * 4 + 1]),
+                                                      ss_add(0.f, acc[r * 4 + 2]), ss_add(0.f, acc[r * 4 + 3]));
                             } else {
-                                fd[0] = ss_add(0.f, l0); fd[1] = ss_add(0.f, l1);
-                                fd[2] = ss_add(0.f, l2); fd[3] = ss_add(0.f, l3);
+                                fd[0] = ss_add(0.f, acc[r * 4]); fd[1] = ss_add(0.f, acc[r * 4 + 1]);
+                                fd[2] = ss_add(0.f, acc[r * 4 + 2]); fd[3] = ss_add(0.f, acc[r * 4 + 3]);
                             }
-                        } else if (pref32)   // own-block Laplacian -> per-CTA global scratch (re-read by this thread only)
-                            *(ss_f4 *)(scratch + ((it == 0 ? 1 : (it == 1 ? 0 : 2)) * SS_TY + 4 * ty + r) * SS_TX + 4 * tx) =
-                                ss_mk4(l0, l1, l2, l3);
-                        else          // park it in place of g_l: this position is read by no other thread
-                            *(ss_f4 *)gp = ss_mk4(l0, l1, l2, l3);
-                        gray[r * 4 + 0] = ss_fma(l0, wgt, gray[r * 4 + 0]);
-                        gray[r * 4 + 1] = ss_fma(l1, wgt, gray[r * 4 + 1]);
-                        gray[r * 4 + 2] = ss_fma(l2, wgt, gray[r * 4 + 2]);
-                        gray[r * 4 + 3] = ss_fma(l3, wgt, gray[r * 4 + 3]);
+                        }
+                        gray[r * 4 + 0] = ss_fma(acc[r * 4 + 0], wgt, gray[r * 4 + 0]);
+                        gray[r * 4 + 1] = ss_fma(acc[r * 4 + 1], wgt, gray[r * 4 + 1]);
+                        gray[r * 4 + 2] = ss_fma(acc[r * 4 + 2], wgt, gray[r * 4 + 2]);
+                        gray[r * 4 + 3] = ss_fma(acc[r * 4 + 3], wgt, gray[r * 4 + 3]);
+                    }
+                    // park the block's Laplacians of this plane in the thread's tensor-memory columns
+                    if (!(pref32 && first_frame)) {
+#ifdef SS_HOST_EMU
+                        for (int q = 0; q < 16; ++q) SS_PT(tmv)[chi * 16 + q] = acc[q];
+#else
+                        ss_tm_st16(tm_addr + chi * 16, acc);
+#endif
                     }
                     const int step = it == 0 ? -1 : 2;
                     p1c += step * SS_P1P;
                     p0c += step * SS_P0P;
                 }
+                float sqmax = 0.f;   // largest gray^2 of the block (squares are >= +0)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     float *dst = SQ + (4 * ty + r + 2) * SS_SQS + 4 * tx + 2;
-                    *(ss_f2 *)dst = ss_mk2(ss_mul(gray[r * 4], gray[r * 4]), ss_mul(gray[r * 4 + 1], gray[r * 4 + 1]));
-                    *(ss_f2 *)(dst + 2) = ss_mk2(ss_mul(gray[r * 4 + 2], gray[r * 4 + 2]), ss_mul(gray[r * 4 + 3], gray[r * 4 + 3]));
+                    const float s0 = ss_mul(gray[r * 4], gray[r * 4]), s1 = ss_mul(gray[r * 4 + 1], gray[r * 4 + 1]);
+                    const float s2 = ss_mul(gray[r * 4 + 2], gray[r * 4 + 2]), s3 = ss_mul(gray[r * 4 + 3], gray[r * 4 + 3]);
+                    *(ss_f2 *)dst = ss_mk2(s0, s1);
+                    *(ss_f2 *)(dst + 2) = ss_mk2(s2, s3);
+                    if (skip_on) sqmax = fmaxf(fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)), sqmax);
                 }
+#ifndef SS_HOST_EMU
+                ss_tm_wait_st();
+#endif
+                float ringmax = 0.f;
                 // halo ring of SQ (2 pixels wide): 132 aligned 2x2 quads
                 if (tid < 132) {
                     int qq, pp;
@@ -860,8 +950,26 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                         r1c += step * SS_P1P;
                         r0c += step * SS_P0P;
                     }
-                    *(ss_f2 *)(SQ + qq * SS_SQS + pp) = ss_mk2(ss_mul(gr[0], gr[0]), ss_mul(gr[1], gr[1]));
-                    *(ss_f2 *)(SQ + (qq + 1) * SS_SQS + pp) = ss_mk2(ss_mul(gr[2], gr[2]), ss_mul(gr[3], gr[3]));
+                    const float s0 = ss_mul(gr[0], gr[0]), s1 = ss_mul(gr[1], gr[1]), s2 = ss_mul(gr[2], gr[2]), s3 = ss_mul(gr[3], gr[3]);
+                    *(ss_f2 *)(SQ + qq * SS_SQS + pp) = ss_mk2(s0, s1);
+                    *(ss_f2 *)(SQ + (qq + 1) * SS_SQS + pp) = ss_mk2(s2, s3);
+                    ringmax = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+                }
+                if (skip_on) {
+                    // per-warp maxima: wmax[w] = own blocks (rows 8w .. 8w+7 of the tile), wmax[8 + w] = the warp's ring quads
+                    const int wp = tid >> 5;
+#ifdef SS_HOST_EMU
+                    if ((tid & 31) == 0) { wmax[wp] = 0.f; if (wp < 5) wmax[8 + wp] = 0.f; }
+                    wmax[wp] = fmaxf(wmax[wp], sqmax);
+                    if (wp < 5) wmax[8 + wp] = fmaxf(wmax[8 + wp], ringmax);
+#else
+                    const unsigned m1 = __reduce_max_sync(0xffffffffu, __float_as_uint(sqmax));
+                    if ((tid & 31) == 0) wmax[wp] = __uint_as_float(m1);
+                    if (wp < 5) {
+                        const unsigned m2 = __reduce_max_sync(0xffffffffu, __float_as_uint(ringmax));
+                        if ((tid & 31) == 0) wmax[8 + wp] = __uint_as_float(m2);
+                    }
+#endif
                 }
             }
         } else {
@@ -914,6 +1022,13 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             SS_THREADS(tid) { ss_s0_async_u8(p, frame + p.in_frame_stride, x0, y0, tid, (char *)P1); }
         }
 #endif
+#ifdef SS_HOST_EMU
+        float warp_bemin[SS_NT / 32];
+        for (int wq = 0; wq < SS_NT / 32; ++wq) {
+            warp_bemin[wq] = bemin[32 * wq][0];
+            for (int l = 1; l < 32; ++l) warp_bemin[wq] = fminf(warp_bemin[wq], bemin[32 * wq + l][0]);
+        }
+#endif
         SS_THREADS(tid)
         {
             const int tx = tid & 15, ty = tid >> 4;
@@ -925,7 +1040,29 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             if (s0_owner && f + 1 < f_end && tid == 0)   // P1 is dead until the next S1: raw bytes of the next frame
                 ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + (f + 1) * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
 #endif
+            bool skip = false;
+            if (skip_on && !first_frame) {
+                // largest gray^2 the windows of this warp can contain: own rows and the two neighbouring warps' rows
+                // (the window reaches 2 rows up and down) plus the whole ring
+                const int wp = tid >> 5;
+                float mx = fmaxf(fmaxf(wmax[8], wmax[9]), fmaxf(fmaxf(wmax[10], wmax[11]), wmax[12]));
+                mx = fmaxf(mx, wmax[wp]);
+                if (wp > 0) mx = fmaxf(mx, wmax[wp - 1]);
+                if (wp < 7) mx = fmaxf(mx, wmax[wp + 1]);
+#ifdef SS_HOST_EMU
+                const float lo = warp_bemin[wp];
+#else
+                const float lo = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(SS_PT(bemin)[0])));
+#endif
+                skip = ss_mul(mx, p.skip_factor) < lo;
+            }
             float e[16];
+            if (skip) {
+                // no pixel of this warp can win: nothing to do
+#ifdef SS_HOST_EMU
+                ss_emu_skipped_threads++;
+#endif
+            } else {
             if (fast) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) e[q] = 0.f;
@@ -980,7 +1117,36 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     won |= w ? (1u << q) : 0u;
                 }
             }
-            if (won) {
+            if (fast) {
+                // register-blocked tiles: the parked Laplacians come back from tensor memory, one plane at a time;
+                // the loads are warp-wide, so they run whenever any lane of the warp has a winner
+#ifdef SS_HOST_EMU
+                const bool anywon = won != 0;
+#else
+                const bool anywon = __any_sync(0xffffffffu, won != 0);
+#endif
+                if (anywon) {
+                    const long long o0 = (long long)(y0 + 4 * ty) * p.w + x0 + 4 * tx;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (won & (1u << q)) st_idx[o0 + (long long)(q >> 2) * p.w + (q & 3)] = gidx;
+                    if (!(pref32 && first_frame)) {   // (else the coefficients were stored by S2)
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float l[16];
+#ifdef SS_HOST_EMU
+                            for (int q = 0; q < 16; ++q) l[q] = SS_PT(tmv)[ch * 16 + q];
+#else
+                            ss_tm_ld16(tm_addr + ch * 16, l);
+#endif
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                if (won & (1u << q))
+                                    st_fused[ch * plane_px + o0 + (long long)(q >> 2) * p.w + (q & 3)] = ss_add(0.f, l[q]);
+                        }
+                    }
+                }
+            } else if (won) {
                 const long long o0 = (long long)(y0 + 4 * ty) * p.w + x0 + 4 * tx;
                 const float *lsrc = P0 + (4 * ty + SS_P0Y) * SS_P0S + 4 * tx + SS_P0X;
 #pragma unroll
@@ -988,21 +1154,22 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                     if (won & (1u << q)) {
                         const long long o = o0 + (long long)(q >> 2) * p.w + (q & 3);
                         st_idx[o] = gidx;
-                        if (pref32 && first_frame) continue;   // coefficients were stored by S2
-                        float l0, l1, l2;
-                        if (pref32) {
-                            const float *ls = scratch + (4 * ty + (q >> 2)) * SS_TX + 4 * tx + (q & 3);
-                            l0 = ls[0]; l1 = ls[SS_TX * SS_TY]; l2 = ls[2 * SS_TX * SS_TY];
-                        } else {
-                            const float *ls = lsrc + (q >> 2) * SS_P0S + (q & 3);
-                            l0 = ls[0]; l1 = ls[SS_P0P]; l2 = ls[2 * SS_P0P];
-                        }
-                        st_fused[o] = ss_add(0.f, l0);
-                        st_fused[plane_px + o] = ss_add(0.f, l1);
-                        st_fused[2 * plane_px + o] = ss_add(0.f, l2);
+                        const float *ls = lsrc + (q >> 2) * SS_P0S + (q & 3);
+                        st_fused[o] = ss_add(0.f, ls[0]);
+                        st_fused[plane_px + o] = ss_add(0.f, ls[SS_P0P]);
+                        st_fused[2 * plane_px + o] = ss_add(0.f, ls[2 * SS_P0P]);
                     }
                 }
             }
+            if (won) {
+                if (skip_on) {
+                    float m = SS_PT(be)[0];
+#pragma unroll
+                    for (int q = 1; q < 16; ++q) m = fminf(m, SS_PT(be)[q]);
+                    SS_PT(bemin)[0] = m;
+                }
+            }
+            }   // !skip
             // uint8 interior tiles: S0 of the next frame.  This thread is done with the Laplacians parked in its own
             // block, and nobody reads the frame around the interior after S2, so no barrier is needed first; the raw
             // bytes of the next frame must have landed
@@ -1035,4 +1202,10 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
                 if (x < p.w && y < p.h) st_e[(long long)y * p.w + x] = SS_PT(be)[r * 4 + c];
             }
     }
+#ifndef SS_HOST_EMU
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "n"(SS_TM_COLS) : "memory");
+#endif
 }

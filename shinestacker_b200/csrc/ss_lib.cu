@@ -924,6 +924,7 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
         p.frame_index0 = h->cfg.frame_index_base + f0;
         p.init = h->have_state ? 0 : 1;
         memcpy(p.k25, h->k25, sizeof(p.k25));
+        p.skip_factor = getenv("SS_NO_SKIP") ? 0.f : ss_skip_factor(h->k25);
         dim3 grid((v.w + SS_TX - 1) / SS_TX, (v.h + SS_TY - 1) / SS_TY, groups);
         size_t smem = SS_SMEM_BYTES;
         if (const char *xs = getenv("SS_EXTRA_SMEM")) {   // experiment knob: e.g. 20000 forces one CTA per SM

@@ -27,6 +27,7 @@ extern "C" int emu_level(const void *in, int bytes_per_sample /*1,2: interleaved
     p.best_e = best_e; p.best_idx = best_idx; p.fused = fused;
     p.n_frames = n_frames; p.frame_index0 = frame_index0; p.init = init; p.groups = 1; p.group_stride = 0;
     memcpy(p.k25, k25, sizeof(p.k25));
+    p.skip_factor = getenv("SS_EMU_NO_SKIP") ? 0.f : ss_skip_factor(k25);
     float *smem = (float *)malloc(SS_SMEM_BYTES);
     float *scratch = (float *)malloc(sizeof(float) * 3 * SS_TX * SS_TY);
     p.lap_scratch = scratch;
@@ -41,4 +42,11 @@ extern "C" int emu_level(const void *in, int bytes_per_sample /*1,2: interleaved
     free(smem);
     free(scratch);
     return 0;
+}
+
+extern "C" long long emu_skipped_threads(int reset)
+{
+    const long long v = ss_emu_skipped_threads;
+    if (reset) ss_emu_skipped_threads = 0;
+    return v;
 }

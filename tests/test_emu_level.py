@@ -81,3 +81,22 @@ def test_emulated_level_kernel_matches_oracle(emu, oracle, gen, n, h, w, dtype, 
         assert np.array_equal(fu.transpose(1, 2, 0), info["fused_pyramid"][l]), f"level {l} coefficients"
     gp = oracle.gaussian_pyramid(oracle.split_planes(frames[-1]), len(res), oracle.make_kernel(0.4))
     assert np.array_equal(gp[-1], base[-1])
+
+
+def test_energy_stage_skip_triggers_and_is_exact(emu, oracle, monkeypatch):
+    """The exact skip of the energy stage (ss_skip_factor): on a staircase stack the frames after the sharp one are
+    skipped in the interior tiles, and the result is unchanged (bit-exact against the oracle, with and without)."""
+    frames = synthetic.make_stack(6, 224, 384, np.uint8, 13)      # bands of 64 columns = one tile column each
+    _, info = oracle.focus_stack(frames)
+    emu.emu_skipped_threads.restype = ctypes.c_longlong
+    emu.emu_skipped_threads(1)
+    res, _ = run_levels(emu, oracle, frames)
+    skipped = emu.emu_skipped_threads(1)
+    assert skipped > 0 and skipped % 32 == 0                      # whole warps only
+    for l, (bi, fu) in enumerate(res):
+        assert np.array_equal(bi, info["best"][l]) and np.array_equal(fu.transpose(1, 2, 0), info["fused_pyramid"][l])
+    monkeypatch.setenv("SS_EMU_NO_SKIP", "1")
+    res2, _ = run_levels(emu, oracle, frames)
+    assert emu.emu_skipped_threads(1) == 0
+    for (bi, fu), (bi2, fu2) in zip(res, res2):
+        assert np.array_equal(bi, bi2) and np.array_equal(fu, fu2)

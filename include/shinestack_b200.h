@@ -166,6 +166,15 @@ int ss_get_base_gray(ss_handle *h, int32_t *out);
 int ss_finish_select_base_f64(ss_handle *h, const double *log_prob, int per_px);
 int ss_finish_select_base_px(ss_handle *h, const float *log_prob_px);
 int ss_finish_collapse(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
+/* The same base step without any host round trip (float-32): PyramidBase.entropy's np.log(probabilities)
+ * (pyramid.py:67-69,77) only ever sees the n_base + 1 values float32(c) / n_base, c = 0 .. n_base = hL * wL, so the host
+ * supplies that table once (ss_set_log_lut: computed with numpy by the Python binding, libm's logf by default) and
+ * the device indexes it with its own histogram.  ss_finish_base_device = ss_finish_begin + base selection, all
+ * asynchronous; ss_finish_collapse(h, NULL, 0) then leaves the fused image on the device and ss_download_output
+ * fetches it. */
+int ss_set_log_lut(ss_handle *h, const float *lut, int n);
+int ss_finish_base_device(ss_handle *h);
+int ss_download_output(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
 /* Time of the i-th timed segment (one per launched batch, then histogram, base select, collapse). */
 int ss_segment_time_ms(ss_handle *h, int i, float *ms);
 

@@ -105,6 +105,9 @@ SIGNATURES = {
     "ss_finish_select_base_px": (_i, [_vp, _vp]),
     "ss_finish_collapse": (_i, [_vp, _vp, _sz]),
     "ss_segment_time_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float)]),
+    "ss_set_log_lut": (_i, [_vp, _vp, _i]),
+    "ss_finish_base_device": (_i, [_vp]),
+    "ss_download_output": (_i, [_vp, _vp, _sz]),
     "ss_get_best_energy": (_i, [_vp, _i, _vp]),
     "ss_get_gauss_level": (_i, [_vp, _i, _i, _vp]),
     "ss_test_collapse_step": (_i, [_vp, _i, _i, _vp, _i, _i, ctypes.c_double, _vp]),

@@ -147,8 +147,13 @@ __device__ float ss_np_pairwise_sum(const float *a, int n)
 
 // Base level, step 2a (reference pyramid.py:66-93): per (pixel, frame) the window entropy
 // -sum(v*log p[v]) and the window variance, both in numpy's evaluation order.
+// log p[v] comes in one of three forms: per_px == 0: a per-frame table indexed by the value; per_px == 1: the
+// log-probability of every base pixel's own value, indexed by the pixel; per_px == 2: lut[counts[f][v]], lut being
+// the table log(float32(c) / n_px) for every possible count c = 0 .. n_px (computed once by the host -- with numpy
+// when Python drives the library, so that it is numpy's log -- which removes the host round trip of the histogram).
 __global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, int per_px, int h, int w,
-                                       int num_values, int side, float *ent_out, float *dev_out)
+                                       int num_values, int side, float *ent_out, float *dev_out,
+                                       const unsigned int *counts = nullptr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
@@ -161,7 +166,8 @@ __global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, 
     const int32_t *g = gray + (size_t)f * n_px;
     // log p[v]: either a per-frame table indexed by the value, or (16-bit stacks) the log-probability of
     // every base pixel's own value, indexed by the pixel
-    const float *lp = log_p + (size_t)f * (per_px ? n_px : num_values);
+    const float *lp = per_px == 2 ? log_p : log_p + (size_t)f * (per_px ? n_px : num_values);
+    const unsigned int *cnt = counts + (size_t)f * num_values;
     int c = 0;
     long long s = 0;
     for (int dy = -pad; dy <= pad; ++dy) {
@@ -172,7 +178,7 @@ __global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, 
             while (xx < 0 || xx >= w) xx = xx < 0 ? -xx : 2 * w - 2 - xx;
             const int v = g[yy * w + xx];
             vals[c] = v;
-            buf[c] = __fmul_rn((float)v, lp[per_px ? yy * w + xx : v]);
+            buf[c] = __fmul_rn((float)v, per_px == 2 ? lp[cnt[v]] : lp[per_px ? yy * w + xx : v]);
             s += v;
             ++c;
         }
@@ -440,6 +446,7 @@ struct ss_handle {
     float *base = nullptr;           // max_frames x 3 x hL x wL
     int32_t *gray = nullptr;         // max_frames x hL x wL
     unsigned int *counts = nullptr;  // max_frames x num_values
+    float *log_lut = nullptr;        // n_base + 1 entries: log(float32(c) / n_base), see ss_set_log_lut
     float *log_p = nullptr;          // max_frames x num_values
     // contiguous running state in exchange order: [level 0 .. L-1 | base entropy | base deviation]
     float *state_val = nullptr;      // n_keys floats
@@ -566,6 +573,7 @@ SS_EXPORT void ss_destroy(ss_handle *h)
     }
     cudaFree(h->lap_scratch);
     cudaFree(h->frames); cudaFree(h->base); cudaFree(h->gray); cudaFree(h->counts);
+    cudaFree(h->log_lut);
     cudaFree(h->log_p); cudaFree(h->state_val); cudaFree(h->state_idx); cudaFree(h->state_coef);
     cudaFree(h->ent); cudaFree(h->dev);
     cudaFree(h->fused_base);
@@ -700,6 +708,14 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
     if ((rc = ss_dalloc(&h->gray, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->counts, (size_t)cfg->max_frames * h->num_values))) return rc;
     if ((rc = ss_dalloc(&h->log_p, (size_t)cfg->max_frames * ((size_t)h->num_values > nb ? (size_t)h->num_values : nb)))) return rc;
+    {
+        // default count -> log-probability table from libm; ss_set_log_lut replaces it (numpy's log from Python)
+        if ((rc = ss_dalloc(&h->log_lut, nb + 1))) return rc;
+        std::vector<float> lut(nb + 1);
+        for (size_t c = 0; c <= nb; ++c)
+            lut[c] = c ? logf((float)((double)(float)c / (double)nb)) : -INFINITY;
+        SS_CUDA(cudaMemcpy(h->log_lut, lut.data(), (nb + 1) * sizeof(float), cudaMemcpyHostToDevice));
+    }
     if ((rc = ss_dalloc(&h->ent, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->dev, (size_t)cfg->max_frames * nb))) return rc;
     if ((rc = ss_dalloc(&h->fused_base, 3 * nb))) return rc;
@@ -1139,6 +1155,53 @@ static int ss_select_base_impl(ss_handle *h, const float *log_prob, int per_px)
 
 SS_EXPORT int ss_finish_select_base(ss_handle *h, const float *log_prob) { return ss_select_base_impl(h, log_prob, 0); }
 
+// The table log(float32(c) / n_base) for c = 0 .. n_base (n = n_base + 1 entries), as the caller's log computes it.
+SS_EXPORT int ss_set_log_lut(ss_handle *h, const float *lut, int n)
+{
+    if (!h || !lut) return ss_fail(SS_ERR_STATE, "null argument");
+    const int nb = h->lh[h->L] * h->lw[h->L];
+    if (n != nb + 1) return ss_fail(SS_ERR_SHAPE, "log table must have %d entries (base level %d x %d), got %d", nb + 1,
+                                    h->lh[h->L], h->lw[h->L], n);
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    SS_CUDA(cudaMemcpyAsync(h->log_lut, lut, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->s_comp));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    return 0;
+}
+
+// Histogram + base-level selection entirely on the device (no host round trip, no synchronisation): flushes
+// pending frames, then gray / histogram, window entropy through the count -> log-probability table, deviation,
+// arg-max and winners' pixels.  float-32 handles only.
+SS_EXPORT int ss_finish_base_device(ss_handle *h)
+{
+    if (!h) return ss_fail(SS_ERR_STATE, "null handle");
+    if (h->f64) return ss_fail(SS_ERR_STATE, "float-64 handle: use ss_finish_begin + ss_finish_select_base_f64");
+    int rc = ss_finish_begin(h, nullptr);
+    if (rc) return rc;
+    const int nb = h->lh[h->L] * h->lw[h->L];
+    if ((rc = ss_timer_begin(h))) return rc;
+    dim3 g((nb + 63) / 64, h->n_pushed);
+    ss_base_metrics_kernel<<<g, 64, 0, h->s_comp>>>(h->gray, h->log_lut, 2, h->lh[h->L], h->lw[h->L], h->num_values,
+                                                      h->side, h->ent, h->dev, h->counts);
+    ss_base_select_kernel<<<(nb + 127) / 128, 128, 0, h->s_comp>>>(h->ent, h->dev, h->base, nb, h->n_pushed,
+        h->cfg.frame_index_base, h->best_ve, h->best_ie, h->best_vd, h->best_id, h->pix_e, h->pix_d);
+    h->launches += 2;
+    SS_CUDA(cudaGetLastError());
+    return ss_timer_end(h);
+}
+
+// The fused image of the last ss_finish_collapse(h, NULL, 0), device -> host.
+SS_EXPORT int ss_download_output(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes)
+{
+    if (!h || !out_bgr) return ss_fail(SS_ERR_STATE, "null argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t row = (size_t)h->cfg.width * 3 * h->cfg.bytes_per_sample;
+    if (out_row_pitch_bytes < row) return ss_fail(SS_ERR_SHAPE, "output pitch too small");
+    SS_CUDA(cudaMemcpy2DAsync(out_bgr, out_row_pitch_bytes, h->out_dev, h->out_pitch, row, h->cfg.height,
+                              cudaMemcpyDeviceToHost, h->s_comp));
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    return 0;
+}
+
 // Same, with the table given per base pixel: log_prob_px[f][i] = log(probability of the gray value of pixel i
 // of frame f).  Cheap for 16-bit stacks, where a 65536-entry table per frame is mostly empty.
 SS_EXPORT int ss_finish_select_base_px(ss_handle *h, const float *log_prob_px)
@@ -1282,6 +1345,11 @@ SS_EXPORT int ss_finish_end(ss_handle *h, const float *log_prob, void *out_bgr, 
 
 SS_EXPORT int ss_finish(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes)
 {
+    if (h && !h->f64) {
+        const int rc = ss_finish_base_device(h);
+        if (rc) return rc;
+        return ss_finish_collapse(h, out_bgr, out_row_pitch_bytes);
+    }
     int rc = ss_finish_begin(h, nullptr);
     if (rc) return rc;
     return ss_finish_end(h, nullptr, out_bgr, out_row_pitch_bytes);

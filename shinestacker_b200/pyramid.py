@@ -78,9 +78,24 @@ def log_prob_per_pixel(gray, dtype=np.float32):
     return out
 
 
+def log_prob_lut(n_base, dtype=np.float32):
+    """np.log(probabilities) of PyramidBase.entropy (reference pyramid.py:67-69,77) for every value a probability
+    can take: ``probabilities[v] = counts.astype(float32)[v] / counts.sum()`` with ``counts.sum() == n_base`` (every
+    base pixel is counted once), evaluated like the reference (float32 array / int64 scalar -> float64, stored as
+    float32) and passed through numpy's own ``log``.  Entry ``c`` belongs to a value that occurs ``c`` times."""
+    c = np.arange(n_base + 1, dtype=np.int64)
+    prob = (c.astype(dtype) / np.int64(n_base)).astype(dtype)
+    with np.errstate(divide="ignore"):
+        return np.ascontiguousarray(np.log(prob))
+
+
 def select_base(lib, h, n_frames, num_values, float_type=np.float32):
-    """ss_finish_begin + host-side log table (numpy) + base-level arg-max on the device."""
+    """Base-level arg-max on the device.  float-32: one asynchronous call (the device indexes the log table set by
+    ``_ensure_handle`` with its own histogram); float-64: histogram to the host, numpy log table back."""
     f64 = float_type == np.float64
+    if not f64:
+        _check(lib.ss_finish_base_device(h))
+        return
     if num_values <= 256:
         counts = np.empty((n_frames, num_values), dtype=np.int64)
         _check(lib.ss_finish_begin(h, counts.ctypes.data_as(ctypes.c_void_p)))
@@ -220,6 +235,12 @@ class PyramidStack(PyramidBase):
         hp = ctypes.c_void_p()
         _check(self._lib.ss_create(ctypes.byref(cfg), ctypes.byref(hp)))
         self._h = hp
+        if cfg.float_bits == 32:
+            L = self._lib.ss_num_levels(hp)
+            hh, ww = ctypes.c_int32(), ctypes.c_int32()
+            _check(self._lib.ss_level_size(hp, L, ctypes.byref(hh), ctypes.byref(ww)))
+            lut = log_prob_lut(hh.value * ww.value)
+            _check(self._lib.ss_set_log_lut(hp, lut.ctypes.data_as(ctypes.c_void_p), lut.size))
         self._geom = geom
         self._max_frames = cfg.max_frames
         self._resident = cfg.resident_frames

@@ -8,10 +8,13 @@ arg-max select over the frames + base-level fusion + collapse).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N > 1 is launched under torchrun (one rank per GPU); the frames of the ONE stack are sharded over the
-ranks (strong scaling) and merged with one NCCL max all-reduce on packed (energy, index) keys plus one
-sum-reduce of the winners' coefficients (shinestacker_b200/sharded.py).
+ranks (strong scaling) and merged by the library's fused peer exchange over NVLink (every rank merges and collapses
+one band of image rows straight out of the peers' memory; shinestacker_b200/sharded.py, include/shinestack_b200.h).
+torch.distributed (NCCL) is used by this script only for the timing plumbing the bench contract prescribes (barrier,
+max over ranks); the product path has no PyTorch and no collective library.
 
-Printed JSON (rank 0, one line): value = throughput with the frames already resident in HBM;
+Printed JSON (rank 0, one line): value = throughput with the frames already resident in HBM (fused image left in
+HBM; it is downloaded once after the timed loop for the parity check);
 e2e = the same stack through the public host-buffer API (H2D of every frame from pinned host memory
 and D2H of the fused image inside the timed region); roofline = level-0 fused kernel, algorithmic
 bytes / CUDA-event time against MEASURED_PEAKS.json; cpu_baseline = the UNMODIFIED reference (baseline/_ref, its own
@@ -276,6 +279,8 @@ def main():
     lib = _native.load()
     if lib.ss_device_count() < 1:
         raise SystemExit("bench.py: no sm_100 GPU visible (there is no CPU fallback path)")
+    from shinestacker_b200 import rendezvous
+    rdv = rendezvous.TcpRendezvous.from_env()      # bootstrap of the peer exchange (one all-gather per native handle)
 
     def barrier():
         torch.cuda.synchronize(local)
@@ -306,7 +311,7 @@ def main():
     pitch = W * 3 * dtype.itemsize
 
     # ---- leg 1: frames resident in HBM, one launch per level over all local frames ------------------
-    res = ShardedPyramidStack(rank, world, device=local, batch_frames=n_local)
+    res = ShardedPyramidStack(rank, world, device=local, rendezvous=rdv, batch_frames=n_local)
     algo = res.begin(host[0], n_local, N, resident=True)
     for i in range(n_local):
         _check(lib.ss_push_frame(algo._h, host[i].ctypes.data_as(ctypes.c_void_p), pitch))
@@ -315,7 +320,7 @@ def main():
 
     def step_resident():
         _check(lib.ss_rerun_resident(algo._h))
-        return res.finish(n_local, (H, W), out=out)
+        return res.finish(n_local, (H, W), download=False)     # device-resident in, device-resident out
 
     # nvidia-smi needs ~100 ms to deliver its first sample: start it before the warm-up steps so that it is
     # sampling during the timed region; only samples taken under load (power) enter the median
@@ -345,7 +350,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt_res = float(t.item())
-    fused_resident = out.copy() if rank == 0 else None
+    fused_resident = res.download((H, W), out).copy() if rank == 0 else None
     argmax_l0 = None
     if rank == 0:          # level-0 arg-max of the timed run (after the exchange the root holds the global map)
         argmax_l0 = np.empty((H, W), dtype=np.int32)
@@ -353,7 +358,7 @@ def main():
     res.algo.close()
 
     # ---- leg 2: end to end through the public host-buffer API ---------------------------------------
-    e2e = ShardedPyramidStack(rank, world, device=local, batch_frames=min(a.batch, n_local))
+    e2e = ShardedPyramidStack(rank, world, device=local, rendezvous=rdv, batch_frames=min(a.batch, n_local))
 
     def step_e2e():
         al = e2e.begin(host[0], n_local, N)
@@ -410,7 +415,9 @@ def main():
             "config": {"workload": workload_name(a), "levels": 6, "frames_per_gpu": n_local,
                        "l2": f"inputs ({N * frame_bytes / 1e9:.2f} GB) larger than the 126 MB L2; every "
                              "step re-reads all frames from HBM",
-                       "parallelism": f"frames sharded over {world} GPU(s)",
+                       "parallelism": f"frames sharded over {world} GPU(s)" + ("; fused peer exchange over NVLink "
+                                      "(banded merge + collapse, epoch flags), no collective on the data path" if world > 1 else ""),
+                       "output": "value: fused image left in HBM; e2e: downloaded to pinned host memory",
                        "numa_node_rank0": numa_node},
             "clocks": clocks,
             "e2e": {"value": mp / (dt_e2e / a.steps), "unit": UNIT, "ms_per_step": dt_e2e / a.steps * 1e3,

@@ -124,29 +124,35 @@ int ss_level_kernel_time_ms(ss_handle *h, int level, float *total_ms, int32_t *l
 /* Number of kernel launches since the last ss_reset. */
 int ss_launch_count(ss_handle *h, int64_t *launches);
 
-/* ---- multi-GPU exchange (frames of one stack sharded over ranks) ------------
- * After ss_finish_begin on every rank, the per-level running state (energy, global frame index,
- * winning coefficients) and the base-level planes are merged so that the root rank holds the state
- * of the whole stack.  The library exposes the packed device buffers; the caller runs the collective
- * (NCCL through torch.distributed in bench.py) and then calls ss_finish_end on the root. */
-/* Packs (energy_bits << 32 | ~global_index) keys for every level into one device buffer; returns its
- * device address and element count. */
-int ss_exchange_keys(ss_handle *h, uint64_t **d_keys, size_t *count);
-/* After the keys were max-reduced across ranks: zero every coefficient this rank did not win and
- * return the packed float32 coefficient buffer (device address, element count) for a sum-reduce. */
-int ss_exchange_mask_losers(ss_handle *h, float **d_coeffs, size_t *count);
-/* On the root after both reductions: unpack winners' indices from the reduced keys. */
-int ss_exchange_adopt(ss_handle *h);
-/* Alternative to ss_exchange_mask_losers + sum-reduce + ss_exchange_adopt: the root gathers the winners'
- * coefficients itself over NVLink peer memory.  Every rank publishes the 64-byte CUDA IPC handle of its
- * coefficient state; after the key max-reduction the root calls ss_exchange_pull with all handles and the
- * world+1 shard boundaries (global frame indices); the other ranks only wait. */
-int ss_exchange_ipc_handle(ss_handle *h, void *handle64);
-int ss_exchange_pull(ss_handle *h, const void *handles, const int32_t *shard_start, int world, int rank);
-/* The same gather with the ranks' coefficient states given as device pointers addressable from this device
- * (several handles in one process; tests), and the accessor that yields such a pointer. */
-int ss_exchange_pull_ptrs(ss_handle *h, const void *const *coef_ptrs, const int32_t *shard_start, int world, int rank);
-int ss_exchange_coef_ptr(ss_handle *h, float **d_coeffs, size_t *count);
+/* ---- multi-GPU, fused peer exchange (one process per GPU of a box; no collective library, no host in the loop) ----
+ * Frames of one stack are sharded over the ranks in contiguous blocks (frame_index_base = first global index).  The
+ * rows of every pyramid level are cut into one band per rank.  After its last frame a rank signals READY through an
+ * epoch flag in every peer's memory; its merge kernel then reads, for its bands (+ the halo rows its collapse needs),
+ * the running values of all ranks over NVLink, takes np.argmax's first maximum (rank order == frame order, strict
+ * '>'; pyramid.py:51-54 over the whole stack), pulls the winner's coefficients, collapses its band (pyramid.py:57-64)
+ * and stores its rows of the fused image into the root's output buffer (peer stores); the root waits for every
+ * band's OUT flag and downloads the image.
+ *   setup, once per handle:  ss_peer_export on every rank -> the caller all-gathers the 384-byte blobs (any
+ *   transport; shinestacker_b200/rendezvous.py uses a TCP socket) -> ss_peer_connect on every rank.
+ *   per stack: push frames as usual, then ss_peer_finish on every rank (out_bgr only meaningful on the root).
+ * ss_peer_ptrs / ss_peer_connect_ptrs: the same for several handles inside one process (tests). */
+int ss_peer_export(ss_handle *h, void *blob384);
+int ss_peer_connect(ss_handle *h, const void *blobs, int world, int rank, int root);
+int ss_peer_ptrs(ss_handle *h, void **ptrs6);
+int ss_peer_connect_ptrs(ss_handle *h, void *const *ptrs, int world, int rank, int root);
+int ss_peer_finish(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
+/* The two halves of ss_peer_finish: enqueue this rank's part (returns at once) / wait for it (root: for all bands,
+ * then download).  A process that drives several ranks must enqueue all of them before it waits for any. */
+int ss_peer_finish_async(ss_handle *h);
+int ss_peer_wait(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
+/* ss_peer_finish_async in its three phases (1: base selection + READY; 2: wait READY, merge, DONE, banded collapse,
+ * OUT; 3: root waits for every OUT).  Only needed when one process drives several ranks on one device (tests): submit
+ * phase p of every rank before phase p + 1 of any. */
+int ss_peer_phase(ss_handle *h, int phase);
+/* Test hook (no GPU needed): the row bands ss_peer_connect derives for an image of this size; out receives
+ * 4 x (L + 2) int32 (merge rows [row0, row1) and owned rows [own0, own1) per segment: levels 0..L-1, two base planes),
+ * level_h (may be NULL) the L + 1 level heights; returns L. */
+int ss_test_peer_bands(int height, int width, int min_size, int world, int rank, int32_t *out, int32_t *level_h);
 
 /* Re-run the kernel chain over the frames still resident in HBM (requires resident_frames >= frames
  * pushed).  Used by bench.py for the "inputs already in HBM" throughput. */

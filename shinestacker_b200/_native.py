@@ -91,13 +91,6 @@ SIGNATURES = {
     "ss_set_profiling": (_i, [_vp, _i]),
     "ss_level_kernel_time_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)]),
     "ss_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),
-    "ss_exchange_keys": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
-    "ss_exchange_mask_losers": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
-    "ss_exchange_adopt": (_i, [_vp]),
-    "ss_exchange_ipc_handle": (_i, [_vp, _vp]),
-    "ss_exchange_pull": (_i, [_vp, _vp, _vp, _i, _i]),
-    "ss_exchange_pull_ptrs": (_i, [_vp, _vp, _vp, _i, _i]),
-    "ss_exchange_coef_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ss_rerun_resident": (_i, [_vp]),
     "ss_finish_select_base": (_i, [_vp, _vp]),
     "ss_get_base_gray": (_i, [_vp, _vp]),
@@ -105,6 +98,15 @@ SIGNATURES = {
     "ss_finish_select_base_px": (_i, [_vp, _vp]),
     "ss_finish_collapse": (_i, [_vp, _vp, _sz]),
     "ss_segment_time_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float)]),
+    "ss_peer_export": (_i, [_vp, _vp]),
+    "ss_peer_connect": (_i, [_vp, _vp, _i, _i, _i]),
+    "ss_peer_ptrs": (_i, [_vp, _vp]),
+    "ss_peer_connect_ptrs": (_i, [_vp, _vp, _i, _i, _i]),
+    "ss_peer_finish": (_i, [_vp, _vp, _sz]),
+    "ss_peer_finish_async": (_i, [_vp]),
+    "ss_peer_wait": (_i, [_vp, _vp, _sz]),
+    "ss_peer_phase": (_i, [_vp, _i]),
+    "ss_test_peer_bands": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
     "ss_set_log_lut": (_i, [_vp, _vp, _i]),
     "ss_finish_base_device": (_i, [_vp]),
     "ss_download_output": (_i, [_vp, _vp, _sz]),

@@ -231,6 +231,8 @@ struct SsCollapseParams {
     int out_pitch;       // bytes
     int h, w, h2, w2;
     int final_bytes;     // 0: not final; 1 / 2: clip(abs()) and truncate to uint8 / uint16
+    int qy0;             // first quad row of the launch (multi-GPU: every rank collapses a band of rows)
+    int y_end;           // rows >= y_end are not produced (0: all)
     float k25[25];
 };
 
@@ -264,9 +266,9 @@ __device__ __forceinline__ float ss_collapse_px_generic(const float *g, int h2, 
 __global__ void __launch_bounds__(256) ss_collapse_kernel(const __grid_constant__ SsCollapseParams p)
 {
     const int qx = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int qy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int qy = p.qy0 + blockIdx.y * 8 + (threadIdx.x >> 5);
     const int x = 2 * qx, y = 2 * qy;
-    if (x >= p.w || y >= p.h) return;
+    if (x >= p.w || y >= p.h || (p.y_end > 0 && y >= p.y_end)) return;
     const int wz = 2 * p.w2, wz_vec = wz - (wz % 8);
     const bool tail = x + 1 >= wz_vec;
     float v[3][4];
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(256) ss_collapse_kernel(const __grid_constant_
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int yy = y + (q >> 1), xx = x + (q & 1);
-        if (yy >= p.h || xx >= p.w) continue;
+        if (yy >= p.h || xx >= p.w || (p.y_end > 0 && yy >= p.y_end)) continue;
         if (!p.final_bytes) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) p.out[((size_t)ch * p.h + yy) * p.w + xx] = v[ch][q];
@@ -326,9 +328,9 @@ __global__ void __launch_bounds__(256) ss_collapse_kernel(const __grid_constant_
 }
 
 // clip(abs()) + cast of a planar image without any expand (pyramid with no Laplacian level).
-__global__ void ss_finalize_kernel(const float *img, int h, int w, int bytes, void *out, int pitch)
+__global__ void ss_finalize_kernel(const float *img, int h, int w, int bytes, void *out, int pitch, int y_first = 0)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = y_first + blockIdx.y;
     if (x >= w) return;
     const float maxv = bytes == 1 ? 255.f : 65535.f;
     for (int ch = 0; ch < 3; ++ch) {
@@ -340,75 +342,88 @@ __global__ void ss_finalize_kernel(const float *img, int h, int w, int bytes, vo
     }
 }
 
-// ---- multi-GPU exchange helpers ---------------------------------------------
-// The running state of all levels and of the base level lives in three contiguous arrays in exchange
-// order (values, indices, 3-plane coefficients), so the exchange needs ONE kernel per step and no copies.
-// key = (float bits of the non-negative value, canonical +0) << 32 | (0xFFFFFFFF - global frame index):
-// max over ranks == "largest value, ties to the lowest global frame index" == np.argmax.
-__global__ void ss_pack_keys_kernel(const float *val, const int32_t *idx, size_t n,
-                                    unsigned long long *keys)
-{
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float v = val[i];
-    if (v == 0.f) v = 0.f;  // -0 -> +0
-    keys[i] = ((unsigned long long)__float_as_uint(v) << 32) |
-              (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx[i]);
-}
-
+// The running state of all levels and of the base level lives in three contiguous arrays (values, indices, 3-plane
+// coefficients) in one fixed order, so that the multi-GPU exchange addresses every level with one set of offsets.
 struct SsSegments {        // per plane-group (pyramid level / base plane): pixel offset, pixel count, coefficient offset
     int count;
     unsigned long long px_off[12], n_px[12], coef_off[12];
 };
 
-// After the max-reduction: adopt the winning (value, index); zero this rank's coefficients where it
-// lost, so that a float32 sum over ranks reproduces the winner exactly (x + 0 + ... + 0).
-__global__ void ss_adopt_keys_kernel(const unsigned long long *keys, size_t n, const __grid_constant__ SsSegments seg,
-                                     float *val, int32_t *idx, float *coeff)
+// ---- fused peer exchange over NVLink (one process per GPU, no collective library) ---------------------
+// Every rank has built the running state of ITS frames (contiguous block of the stack) for the whole image.  The
+// image rows of every pyramid level are cut into one band per rank; a rank merges its bands (plus the few halo rows
+// its collapse needs) straight out of the peers' memory -- arg-max over the ranks in frame order with the strict '>'
+// of np.argmax, then the winner's three coefficients -- collapses its band of the pyramid and stores its rows of the
+// fused image into the root's output buffer.  Synchronisation is by epoch flags in peer memory.
+#define SS_MAX_RANKS 16
+struct SsPeerState {
+    int world, rank;
+    const float *val[SS_MAX_RANKS];       // running values (energies / base entropy / deviation) of every rank
+    const int32_t *idx[SS_MAX_RANKS];     // global frame indices
+    const float *coef[SS_MAX_RANKS];      // winners' coefficients (3 planes per segment)
+};
+struct SsBandRows {                       // per segment: rows this rank merges, and the rows it owns (depth maps)
+    int count;
+    int row0[12], row1[12], own0[12], own1[12], width[12];
+};
+enum { SS_FLAG_READY = 0, SS_FLAG_DONE = 1, SS_FLAG_OUT = 2 };
+
+__global__ void ss_flag_signal_kernel(unsigned int *const *peer_flags, int world, int kind, int self, unsigned int epoch,
+                                      int only)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long k = keys[i];
-    const int win = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull));
-    const bool mine = (win == idx[i]);
-    val[i] = __uint_as_float((unsigned int)(k >> 32));
-    idx[i] = win;
-    if (!mine) {
-        int s = 0;
-        while (s + 1 < seg.count && i >= seg.px_off[s + 1]) ++s;
-        float *c = coeff + seg.coef_off[s] + (i - seg.px_off[s]);
-        c[0] = 0.f; c[seg.n_px[s]] = 0.f; c[2 * seg.n_px[s]] = 0.f;
-    }
+    const int p = threadIdx.x;
+    if (p >= world || (only >= 0 && p != only)) return;
+    __threadfence_system();   // everything this device wrote before (earlier kernels of the stream) is visible first
+    volatile unsigned int *f = peer_flags[p] + kind * SS_MAX_RANKS + self;
+    *f = epoch;
+    __threadfence_system();
 }
 
-// Root-side gather over NVLink peer memory: after the key max-reduction the root knows every pixel's winning
-// global frame index, hence the owning rank (contiguous frame shards); it reads the three winning coefficients
-// straight from that rank's running state (peer pointer obtained through CUDA IPC) -- no masking pass on the
-// other ranks, no sum-reduction, 12 bytes per pixel cross NVLink exactly once.
-struct SsPeers {
-    int world, rank;
-    int shard_start[17];          // frame index where rank r's shard begins; [world] = total frames
-    const float *coef[16];        // state_coef of every rank (own pointer at [rank])
-};
-
-__global__ void ss_pull_winners_kernel(const unsigned long long *keys, size_t n, const __grid_constant__ SsSegments seg,
-                                       const __grid_constant__ SsPeers peers, float *val, int32_t *idx, float *coeff)
+__device__ __forceinline__ void ss_flag_wait(const unsigned int *flags, int world, int kind, unsigned int epoch)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long k = keys[i];
-    const int win = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull));
-    val[i] = __uint_as_float((unsigned int)(k >> 32));
-    idx[i] = win;
-    int r = 0;
-    while (r + 1 < peers.world && win >= peers.shard_start[r + 1]) ++r;
-    if (r == peers.rank) return;   // the root's own coefficients are already in place
+    if (threadIdx.x < world) {
+        const volatile unsigned int *f = flags + kind * SS_MAX_RANKS + threadIdx.x;
+        while ((int)(*f - epoch) < 0) __nanosleep(64);
+    }
+    __threadfence_system();
+    __syncthreads();
+}
+
+__global__ void ss_flag_wait_kernel(const unsigned int *flags, int world, int kind, unsigned int epoch)
+{
+    ss_flag_wait(flags, world, kind, epoch);
+}
+
+// One thread per pixel of the rows [row0, row1) of every segment.
+__global__ void __launch_bounds__(256) ss_peer_merge_kernel(const __grid_constant__ SsPeerState ps,
+                                                            const __grid_constant__ SsSegments seg,
+                                                            const __grid_constant__ SsBandRows band,
+                                                            const unsigned int *flags, unsigned int epoch,
+                                                            float *mrg_coef, int32_t *root_idx)
+{
+    (void)flags; (void)epoch;   // (the READY wait is a one-CTA kernel launched just before this one: a grid of
+                                // spinning CTAs could starve the very kernels it waits for when ranks share a GPU)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int s = 0;
-    while (s + 1 < seg.count && i >= seg.px_off[s + 1]) ++s;
-    const size_t o = seg.coef_off[s] + (i - seg.px_off[s]);
-    const float *src = peers.coef[r] + o;
-    float *dst = coeff + o;
-    dst[0] = src[0]; dst[seg.n_px[s]] = src[seg.n_px[s]]; dst[2 * seg.n_px[s]] = src[2 * seg.n_px[s]];
+    for (; s < band.count; ++s) {
+        const size_t n = (size_t)(band.row1[s] - band.row0[s]) * band.width[s];
+        if (i < n) break;
+        i -= n;
+    }
+    if (s >= band.count) return;
+    const int row = band.row0[s] + (int)(i / band.width[s]);
+    const size_t px = (size_t)row * band.width[s] + (i % band.width[s]);   // pixel inside the segment
+    const size_t k = seg.px_off[s] + px;
+    float best = ps.val[0][k];
+    int win = 0;
+    for (int r = 1; r < ps.world; ++r) {          // rank order == frame order: strict '>' keeps the first maximum
+        const float v = ps.val[r][k];
+        if (v > best) { best = v; win = r; }
+    }
+    const size_t c = seg.coef_off[s] + px, np_ = seg.n_px[s];
+    const float *src = ps.coef[win];
+    mrg_coef[c] = src[c]; mrg_coef[c + np_] = src[c + np_]; mrg_coef[c + 2 * np_] = src[c + 2 * np_];
+    if (root_idx && row >= band.own0[s] && row < band.own1[s]) root_idx[k] = ps.idx[win][k];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -460,9 +475,19 @@ struct ss_handle {
     float *tmp_a = nullptr, *tmp_b = nullptr;  // collapse ping-pong, 3 x H x W / 4 each... see alloc
     void *out_dev = nullptr;         // interleaved output image
     size_t out_pitch = 0;
-    void *peer_mapped[16] = {};          // state_coef of the other ranks, opened through CUDA IPC (root only)
-    char peer_handle[16][64] = {};       // ... and the IPC handles they were opened from
-    unsigned long long *keys = nullptr;  // exchange buffer
+    // fused peer exchange (ss_peer_*)
+    bool peer_on = false;
+    int peer_world = 1, peer_rank = 0, peer_root = 0;
+    unsigned int peer_epoch = 0;
+    unsigned int *flags = nullptr;               // [3][SS_MAX_RANKS] epoch flags, written by the peers
+    unsigned int **d_peer_flags = nullptr;       // device array of every rank's flags pointer
+    void *peer_open[SS_MAX_RANKS][6] = {};       // IPC-opened allocations of the peers (closed in ss_destroy)
+    SsPeerState pstate;
+    SsBandRows band;
+    float *mrg_coef = nullptr;                   // merged coefficients (exchange layout), rows of `band` only
+    int32_t *mrg_idx = nullptr;                  // root: merged arg-max indices of the whole stack
+    int32_t *root_mrg_idx = nullptr;             // that buffer as seen from this rank
+    void *root_out = nullptr;                    // the root's output image as seen from this rank
     size_t n_keys = 0, n_coeffs = 0;
     // streams / events
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -577,9 +602,11 @@ SS_EXPORT void ss_destroy(ss_handle *h)
     cudaFree(h->log_p); cudaFree(h->state_val); cudaFree(h->state_idx); cudaFree(h->state_coef);
     cudaFree(h->ent); cudaFree(h->dev);
     cudaFree(h->fused_base);
-    for (void *pm : h->peer_mapped)
-        if (pm) cudaIpcCloseMemHandle(pm);
-    cudaFree(h->tmp_a); cudaFree(h->tmp_b); cudaFree(h->out_dev); cudaFree(h->keys);
+    for (auto &row : h->peer_open)
+        for (void *pm : row)
+            if (pm) cudaIpcCloseMemHandle(pm);
+    cudaFree(h->flags); cudaFree(h->d_peer_flags); cudaFree(h->mrg_coef); cudaFree(h->mrg_idx);
+    cudaFree(h->tmp_a); cudaFree(h->tmp_b); cudaFree(h->out_dev);
     for (auto e : h->ev_copied) cudaEventDestroy(e);
     for (auto e : h->ev_done) cudaEventDestroy(e);
     for (auto &t : h->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
@@ -886,6 +913,11 @@ static int ss_launch_batch(ss_handle *h, int f0, int f1)
             if (rc) return rc;
         }
         return 0;
+    }
+    if (h->peer_on && !h->have_state && h->peer_epoch > 0) {
+        // a new stack overwrites the running state: every rank must have finished reading the previous one
+        ss_flag_wait_kernel<<<1, 32, 0, h->s_comp>>>(h->flags, h->peer_world, SS_FLAG_DONE, h->peer_epoch);
+        h->launches++;
     }
     const int nf = f1 - f0;
     const int slot0 = f0 % h->n_slots;
@@ -1363,6 +1395,11 @@ SS_EXPORT int ss_get_argmax(ss_handle *h, int level, int32_t *out)
     size_t n;
     if (level < h->L) { src = h->lv[level].best_idx; n = (size_t)h->lh[level] * h->lw[level]; }
     else { src = level == h->L ? h->best_ie : h->best_id; n = (size_t)h->lh[h->L] * h->lw[h->L]; }
+    if (h->peer_on && h->peer_epoch > 0 && h->peer_world > 1) {
+        // after a peer exchange the merged maps of the whole stack live on the root
+        if (h->peer_rank != h->peer_root) return ss_fail(SS_ERR_STATE, "merged arg-max maps are on the root rank");
+        src = h->mrg_idx + h->seg.px_off[level];
+    }
     SS_CUDA(cudaStreamSynchronize(h->s_comp));
     SS_CUDA(cudaMemcpy(out, src, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return 0;
@@ -1467,122 +1504,304 @@ SS_EXPORT int ss_launch_count(ss_handle *h, int64_t *launches)
     return 0;
 }
 
-// ---- multi-GPU exchange ---------------------------------------------------------------------------
-// Packed layout (== the layout of the running state itself): keys = [level 0 .. L-1 energies | base entropy |
-// base deviation]; coeffs = [level 0 .. L-1 fused (3 planes each) | pix_e (3 planes) | pix_d (3 planes)].
-SS_EXPORT int ss_exchange_keys(ss_handle *h, uint64_t **d_keys, size_t *count)
+// ---- fused peer exchange: host side ------------------------------------------------------------------
+#define SS_PEER_SLOTS 6   // IPC-shared allocations per rank: state_val, state_idx, state_coef, flags, out_dev, mrg_idx
+static int ss_peer_alloc(ss_handle *h)
 {
-    if (!h || !h->finished_begin) return ss_fail(SS_ERR_STATE, "ss_finish_begin/select_base first");
     if (h->f64) return ss_fail(SS_ERR_STATE, "the multi-GPU exchange is implemented for float-32 only");
-    SS_CUDA(cudaSetDevice(h->cfg.device));
     int rc;
-    if (!h->keys && (rc = ss_dalloc(&h->keys, h->n_keys))) return rc;
-    ss_pack_keys_kernel<<<(unsigned)((h->n_keys + 255) / 256), 256, 0, h->s_comp>>>(h->state_val, h->state_idx, h->n_keys, h->keys);
-    h->launches++;
-    SS_CUDA(cudaGetLastError());
-    SS_CUDA(cudaStreamSynchronize(h->s_comp));
-    if (d_keys) *d_keys = (uint64_t *)h->keys;
-    if (count) *count = h->n_keys;
-    return 0;
-}
-
-SS_EXPORT int ss_exchange_mask_losers(ss_handle *h, float **d_coeffs, size_t *count)
-{
-    if (!h || !h->keys) return ss_fail(SS_ERR_STATE, "ss_exchange_keys first");
-    SS_CUDA(cudaSetDevice(h->cfg.device));
-    ss_adopt_keys_kernel<<<(unsigned)((h->n_keys + 255) / 256), 256, 0, h->s_comp>>>(h->keys, h->n_keys, h->seg, h->state_val,
-                                                                                       h->state_idx, h->state_coef);
-    h->launches++;
-    SS_CUDA(cudaGetLastError());
-    SS_CUDA(cudaStreamSynchronize(h->s_comp));
-    if (d_coeffs) *d_coeffs = h->state_coef;   // the running coefficients themselves: reduced in place
-    if (count) *count = h->n_coeffs;
-    return 0;
-}
-
-SS_EXPORT int ss_exchange_adopt(ss_handle *h)
-{
-    // the sum-reduction wrote straight into the root's running state: nothing to copy
-    if (!h || !h->keys) return ss_fail(SS_ERR_STATE, "ss_exchange_mask_losers first");
-    return 0;
-}
-
-// CUDA IPC handle (64 bytes) of this rank's coefficient state, for the root's peer gather.
-SS_EXPORT int ss_exchange_ipc_handle(ss_handle *h, void *handle64)
-{
-    if (!h || !handle64) return ss_fail(SS_ERR_STATE, "null argument");
-    if (h->f64) return ss_fail(SS_ERR_STATE, "the multi-GPU exchange is implemented for float-32 only");
-    SS_CUDA(cudaSetDevice(h->cfg.device));
-    cudaIpcMemHandle_t mh;
-    SS_CUDA(cudaIpcGetMemHandle(&mh, h->state_coef));
-    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    memcpy(handle64, &mh, 64);
-    return 0;
-}
-
-// Root only, after the key max-reduction: adopt the winners and pull their coefficients from the owning ranks'
-// memory.  handles = world x 64 bytes (ss_exchange_ipc_handle of every rank, own entry ignored); shard_start =
-// world + 1 frame indices.  The other ranks must keep their state untouched until the root returns.
-static int ss_pull_launch(ss_handle *h, const SsPeers &peers)
-{
-    ss_pull_winners_kernel<<<(unsigned)((h->n_keys + 255) / 256), 256, 0, h->s_comp>>>(h->keys, h->n_keys, h->seg, peers,
-                                                                                       h->state_val, h->state_idx, h->state_coef);
-    h->launches++;
-    SS_CUDA(cudaGetLastError());
-    SS_CUDA(cudaStreamSynchronize(h->s_comp));
-    return 0;
-}
-
-SS_EXPORT int ss_exchange_pull(ss_handle *h, const void *handles, const int32_t *shard_start, int world, int rank)
-{
-    if (!h || !h->keys || !handles || !shard_start) return ss_fail(SS_ERR_STATE, "ss_exchange_keys first");
-    if (world < 1 || world > 16 || rank < 0 || rank >= world) return ss_fail(SS_ERR_COMM, "bad world/rank");
-    SS_CUDA(cudaSetDevice(h->cfg.device));
-    SsPeers peers;
-    memset(&peers, 0, sizeof(peers));
-    peers.world = world; peers.rank = rank;
-    for (int r = 0; r <= world; ++r) peers.shard_start[r] = shard_start[r];
-    for (int r = 0; r < world; ++r) {
-        if (r == rank) { peers.coef[r] = h->state_coef; continue; }
-        if (h->peer_mapped[r] && memcmp(h->peer_handle[r], (const char *)handles + 64 * r, 64) != 0) {
-            cudaIpcCloseMemHandle(h->peer_mapped[r]);   // the peer re-created its state
-            h->peer_mapped[r] = nullptr;
-        }
-        if (!h->peer_mapped[r]) {
-            cudaIpcMemHandle_t mh;
-            memcpy(&mh, (const char *)handles + 64 * r, 64);
-            SS_CUDA(cudaIpcOpenMemHandle(&h->peer_mapped[r], mh, cudaIpcMemLazyEnablePeerAccess));
-            memcpy(h->peer_handle[r], (const char *)handles + 64 * r, 64);
-        }
-        peers.coef[r] = (const float *)h->peer_mapped[r];
+    if (!h->flags) {
+        if ((rc = ss_dalloc(&h->flags, 3 * SS_MAX_RANKS))) return rc;
+        SS_CUDA(cudaMemset(h->flags, 0, 3 * SS_MAX_RANKS * sizeof(unsigned int)));
     }
-    return ss_pull_launch(h, peers);
-}
-
-// Same gather with the ranks' coefficient states given as device pointers that are directly addressable from
-// this device (several handles inside one process, or memory mapped by the caller) -- used by the tests.
-SS_EXPORT int ss_exchange_pull_ptrs(ss_handle *h, const void *const *coef_ptrs, const int32_t *shard_start, int world,
-                                    int rank)
-{
-    if (!h || !h->keys || !coef_ptrs || !shard_start) return ss_fail(SS_ERR_STATE, "ss_exchange_keys first");
-    if (world < 1 || world > 16 || rank < 0 || rank >= world) return ss_fail(SS_ERR_COMM, "bad world/rank");
-    SS_CUDA(cudaSetDevice(h->cfg.device));
-    SsPeers peers;
-    memset(&peers, 0, sizeof(peers));
-    peers.world = world; peers.rank = rank;
-    for (int r = 0; r <= world; ++r) peers.shard_start[r] = shard_start[r];
-    for (int r = 0; r < world; ++r) peers.coef[r] = r == rank ? h->state_coef : (const float *)coef_ptrs[r];
-    return ss_pull_launch(h, peers);
-}
-
-// Device address and length of this handle's coefficient state (exchange layout).
-SS_EXPORT int ss_exchange_coef_ptr(ss_handle *h, float **d_coeffs, size_t *count)
-{
-    if (!h || !d_coeffs) return ss_fail(SS_ERR_STATE, "null argument");
-    if (h->f64) return ss_fail(SS_ERR_STATE, "the multi-GPU exchange is implemented for float-32 only");
-    *d_coeffs = h->state_coef;
-    if (count) *count = h->n_coeffs;
+    if (!h->mrg_coef && (rc = ss_dalloc(&h->mrg_coef, h->n_coeffs))) return rc;
+    if (!h->mrg_idx && (rc = ss_dalloc(&h->mrg_idx, h->n_keys))) return rc;
+    if (!h->d_peer_flags && (rc = ss_dalloc(&h->d_peer_flags, SS_MAX_RANKS))) return rc;
     return 0;
+}
+
+static void *const *ss_peer_own_ptrs(ss_handle *h, void **out)
+{
+    out[0] = h->state_val; out[1] = h->state_idx; out[2] = h->state_coef;
+    out[3] = h->flags; out[4] = h->out_dev; out[5] = h->mrg_idx;
+    return out;
+}
+
+// 6 CUDA IPC handles (64 bytes each) of this rank's exchangeable allocations.
+SS_EXPORT int ss_peer_export(ss_handle *h, void *blob384)
+{
+    if (!h || !blob384) return ss_fail(SS_ERR_STATE, "null argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = ss_peer_alloc(h);
+    if (rc) return rc;
+    void *own[SS_PEER_SLOTS];
+    ss_peer_own_ptrs(h, own);
+    for (int i = 0; i < SS_PEER_SLOTS; ++i) {
+        cudaIpcMemHandle_t mh;
+        SS_CUDA(cudaIpcGetMemHandle(&mh, own[i]));
+        memcpy((char *)blob384 + 64 * i, &mh, 64);
+    }
+    return 0;
+}
+
+// Row bands: the base level is cut into `world` bands of rows; the band of a finer level is twice the band of the
+// next coarser one (so a band collapses into its own rows).  `need` = the rows of each level a rank must merge to
+// collapse its band: its band, rounded to row pairs, plus the rows its 3-row expand windows reach.
+static void ss_band_rows(const int *lh, int L, int world, int rank, int *row0, int *row1, int *own0, int *own1)
+{
+    std::vector<int> lo(L + 1), hi(L + 1);
+    lo[L] = (int)((long long)rank * lh[L] / world);
+    hi[L] = (int)((long long)(rank + 1) * lh[L] / world);
+    for (int l = L - 1; l >= 0; --l) {
+        lo[l] = 2 * lo[l + 1] < lh[l] ? 2 * lo[l + 1] : lh[l];
+        hi[l] = rank == world - 1 ? lh[l] : (2 * hi[l + 1] < lh[l] ? 2 * hi[l + 1] : lh[l]);
+    }
+    int a = L > 0 ? lo[0] : 0, e = L > 0 ? hi[0] : 0;
+    for (int l = 0; l < L; ++l) {
+        own0[l] = lo[l]; own1[l] = hi[l];
+        a = a / 2 * 2;                       // the collapse works on row pairs
+        row0[l] = a; row1[l] = e;
+        if (e > a) {                         // rows of level l+1 that the quads a/2 .. (e-1)/2 read
+            const int na = a / 2 - 1 > 0 ? a / 2 - 1 : 0;
+            int ne = (e - 1) / 2 + 2;
+            if (ne > lh[l + 1]) ne = lh[l + 1];
+            a = na; e = ne;
+        }
+    }
+    for (int s2 = L; s2 < L + 2; ++s2) {     // base planes: every rank merges them whole (a few thousand pixels)
+        own0[s2] = lo[L]; own1[s2] = hi[L];
+        row0[s2] = 0; row1[s2] = lh[L];
+    }
+}
+
+static void ss_peer_bands(ss_handle *h, int world, int rank)
+{
+    const int L = h->L;
+    SsBandRows &b = h->band;
+    memset(&b, 0, sizeof(b));
+    b.count = L + 2;
+    ss_band_rows(h->lh.data(), L, world, rank, b.row0, b.row1, b.own0, b.own1);
+    for (int s2 = 0; s2 < L + 2; ++s2) b.width[s2] = h->lw[s2 < L ? s2 : L];
+}
+
+// Test hook (no GPU needed): the row bands of ss_peer_connect for an image of the given size; out = 4 x (L + 2) int32
+// (row0 | row1 | own0 | own1 per segment), returns L.
+SS_EXPORT int ss_test_peer_bands(int height, int width, int min_size, int world, int rank, int32_t *out, int32_t *level_h)
+{
+    std::vector<int> lh, lw;
+    const int L = ss_levels_for(height, width, min_size, lh, lw);
+    if (L + 2 > 12 || !out || world < 1 || rank < 0 || rank >= world) return SS_ERR_STATE;
+    int r[4][12];
+    ss_band_rows(lh.data(), L, world, rank, r[0], r[1], r[2], r[3]);
+    for (int k = 0; k < 4; ++k)
+        for (int s2 = 0; s2 < L + 2; ++s2) out[k * (L + 2) + s2] = r[k][s2];
+    if (level_h)
+        for (int l = 0; l <= L; ++l) level_h[l] = lh[l];
+    return L;
+}
+
+static int ss_peer_setup(ss_handle *h, void *const (*ptrs)[SS_PEER_SLOTS], int world, int rank, int root)
+{
+    h->peer_world = world; h->peer_rank = rank; h->peer_root = root;
+    memset(&h->pstate, 0, sizeof(h->pstate));
+    h->pstate.world = world; h->pstate.rank = rank;
+    unsigned int *pf[SS_MAX_RANKS] = {};
+    for (int r = 0; r < world; ++r) {
+        h->pstate.val[r] = (const float *)ptrs[r][0];
+        h->pstate.idx[r] = (const int32_t *)ptrs[r][1];
+        h->pstate.coef[r] = (const float *)ptrs[r][2];
+        pf[r] = (unsigned int *)ptrs[r][3];
+    }
+    h->root_out = ptrs[root][4];
+    h->root_mrg_idx = (int32_t *)ptrs[root][5];
+    SS_CUDA(cudaMemcpy(h->d_peer_flags, pf, sizeof(pf), cudaMemcpyHostToDevice));
+    ss_peer_bands(h, world, rank);
+    h->peer_on = true;
+    return 0;
+}
+
+// blobs = world x 384 bytes (ss_peer_export of every rank, in rank order; the own entry is ignored).
+SS_EXPORT int ss_peer_connect(ss_handle *h, const void *blobs, int world, int rank, int root)
+{
+    if (!h || !blobs) return ss_fail(SS_ERR_STATE, "null argument");
+    if (world < 1 || world > SS_MAX_RANKS || rank < 0 || rank >= world || root < 0 || root >= world)
+        return ss_fail(SS_ERR_COMM, "bad world / rank / root");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = ss_peer_alloc(h);
+    if (rc) return rc;
+    void *ptrs[SS_MAX_RANKS][SS_PEER_SLOTS];
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { ss_peer_own_ptrs(h, ptrs[r]); continue; }
+        for (int i = 0; i < SS_PEER_SLOTS; ++i) {
+            if (h->peer_open[r][i]) { cudaIpcCloseMemHandle(h->peer_open[r][i]); h->peer_open[r][i] = nullptr; }
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, (const char *)blobs + ((size_t)r * SS_PEER_SLOTS + i) * 64, 64);
+            SS_CUDA(cudaIpcOpenMemHandle(&h->peer_open[r][i], mh, cudaIpcMemLazyEnablePeerAccess));
+            ptrs[r][i] = h->peer_open[r][i];
+        }
+    }
+    return ss_peer_setup(h, ptrs, world, rank, root);
+}
+
+// The same with device pointers that are directly addressable from this device (several handles in one process:
+// tests): ptrs = world x 6 pointers in the order state_val, state_idx, state_coef, flags, out_dev, mrg_idx.
+SS_EXPORT int ss_peer_connect_ptrs(ss_handle *h, void *const *ptrs, int world, int rank, int root)
+{
+    if (!h || !ptrs) return ss_fail(SS_ERR_STATE, "null argument");
+    if (world < 1 || world > SS_MAX_RANKS || rank < 0 || rank >= world || root < 0 || root >= world)
+        return ss_fail(SS_ERR_COMM, "bad world / rank / root");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = ss_peer_alloc(h);
+    if (rc) return rc;
+    void *p2[SS_MAX_RANKS][SS_PEER_SLOTS];
+    for (int r = 0; r < world; ++r)
+        for (int i = 0; i < SS_PEER_SLOTS; ++i) p2[r][i] = ptrs[r * SS_PEER_SLOTS + i];
+    ss_peer_own_ptrs(h, p2[rank]);
+    return ss_peer_setup(h, p2, world, rank, root);
+}
+
+// This rank's 6 exchangeable device pointers (for ss_peer_connect_ptrs of the other handles of the process).
+SS_EXPORT int ss_peer_ptrs(ss_handle *h, void **ptrs6)
+{
+    if (!h || !ptrs6) return ss_fail(SS_ERR_STATE, "null argument");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = ss_peer_alloc(h);
+    if (rc) return rc;
+    ss_peer_own_ptrs(h, ptrs6);
+    return 0;
+}
+
+// Enqueue this rank's part of the exchange (all ranks call it once per stack, after their last frame):
+// base selection on the own frames, READY signal, merge of the own bands out of the peers' memory, DONE signal,
+// collapse of the own band into the root's output image, OUT signal.  `wait` != 0: also wait for it -- on the root
+// for every rank's band, followed by the download into out_bgr (may be NULL: the image stays on the device).
+// phase 1: base selection on the own frames, READY signal; phase 2: wait for every rank's READY, merge, DONE signal,
+// banded collapse into the root's image, OUT signal; phase 3 (root): wait for every rank's OUT.
+static int ss_peer_phase1(ss_handle *h)
+{
+    int rc = ss_finish_base_device(h);
+    if (rc) return rc;
+    const unsigned int epoch = ++h->peer_epoch;
+    if ((rc = ss_timer_begin(h))) return rc;
+    ss_flag_signal_kernel<<<1, 32, 0, h->s_comp>>>(h->d_peer_flags, h->peer_world, SS_FLAG_READY, h->peer_rank, epoch, -1);
+    h->launches++;
+    SS_CUDA(cudaGetLastError());
+    return ss_timer_end(h);
+}
+
+static int ss_peer_phase3(ss_handle *h)
+{
+    if (h->peer_rank != h->peer_root) return 0;
+    int rc;
+    if ((rc = ss_timer_begin(h))) return rc;
+    ss_flag_wait_kernel<<<1, 32, 0, h->s_comp>>>(h->flags, h->peer_world, SS_FLAG_OUT, h->peer_epoch);
+    h->launches++;
+    SS_CUDA(cudaGetLastError());
+    return ss_timer_end(h);
+}
+
+static int ss_peer_phase2(ss_handle *h)
+{
+    int rc;
+    const int L = h->L, world = h->peer_world, rank = h->peer_rank;
+    const unsigned int epoch = h->peer_epoch;
+    if ((rc = ss_timer_begin(h))) return rc;
+    size_t total = 0;
+    for (int s2 = 0; s2 < h->band.count; ++s2) total += (size_t)(h->band.row1[s2] - h->band.row0[s2]) * h->band.width[s2];
+    ss_flag_wait_kernel<<<1, 32, 0, h->s_comp>>>(h->flags, world, SS_FLAG_READY, epoch);
+    ss_peer_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->s_comp>>>(h->pstate, h->seg, h->band, h->flags, epoch,
+                                                                                  h->mrg_coef, h->root_mrg_idx);
+    ss_flag_signal_kernel<<<1, 32, 0, h->s_comp>>>(h->d_peer_flags, world, SS_FLAG_DONE, rank, epoch, -1);
+    h->launches += 3;
+    // base blend + banded collapse on the merged coefficients
+    const size_t nb = (size_t)h->lh[L] * h->lw[L];
+    ss_base_fuse_kernel<<<(unsigned)((3 * nb + 255) / 256), 256, 0, h->s_comp>>>(h->mrg_coef + h->seg.coef_off[L],
+        h->mrg_coef + h->seg.coef_off[L + 1], 3 * nb, h->fused_base);
+    h->launches++;
+    const float *img = h->fused_base;
+    if (L == 0) {
+        // no Laplacian level: the blended base is the image; the own rows go to the root
+        const int y0 = h->band.own0[L], y1 = h->band.own1[L];
+        if (y1 > y0) {
+            dim3 g((h->cfg.width + 255) / 256, y1 - y0);
+            ss_finalize_kernel<<<g, 256, 0, h->s_comp>>>(img, h->cfg.height, h->cfg.width, h->cfg.bytes_per_sample,
+                                                          h->root_out, (int)h->out_pitch, y0);
+            h->launches++;
+        }
+    }
+    for (int l = L - 1; l >= 0; --l) {
+        const int r0 = l == 0 ? h->band.own0[0] / 2 * 2 : h->band.row0[l], r1 = l == 0 ? h->band.own1[0] : h->band.row1[l];
+        SsCollapseParams p;
+        memset(&p, 0, sizeof(p));
+        p.img = img;
+        p.layer = h->mrg_coef + h->seg.coef_off[l];
+        p.h = h->lh[l]; p.w = h->lw[l]; p.h2 = h->lh[l + 1]; p.w2 = h->lw[l + 1];
+        memcpy(p.k25, h->k25, sizeof(p.k25));
+        p.qy0 = r0 / 2; p.y_end = r1;
+        if (l == 0) {
+            p.final_bytes = h->cfg.bytes_per_sample;
+            p.out_px = h->root_out;
+            p.out_pitch = (int)h->out_pitch;
+        } else {
+            p.out = (img == h->tmp_a) ? h->tmp_b : h->tmp_a;
+        }
+        if (r1 > r0) {
+            dim3 g((p.w + 63) / 64, (r1 - r0 + 15) / 16);
+            ss_collapse_kernel<<<g, 256, 0, h->s_comp>>>(p);
+            h->launches++;
+        }
+        img = p.out;
+    }
+    ss_flag_signal_kernel<<<1, 32, 0, h->s_comp>>>(h->d_peer_flags, world, SS_FLAG_OUT, rank, epoch, h->peer_root);
+    h->launches++;
+    SS_CUDA(cudaGetLastError());
+    return ss_timer_end(h);
+}
+
+// One phase of the exchange alone (a process that drives several ranks on ONE device must submit phase p of every
+// rank before phase p + 1 of any: kernels of different streams can share a hardware queue, and a waiting kernel
+// submitted ahead of the signal it waits for would block that queue).
+SS_EXPORT int ss_peer_phase(ss_handle *h, int phase)
+{
+    if (!h || !h->peer_on) return ss_fail(SS_ERR_STATE, "ss_peer_connect first");
+    if (h->n_pushed == 0) return ss_fail(SS_ERR_STATE, "no frame pushed");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    if (phase == 1) return ss_peer_phase1(h);
+    if (phase == 2) return ss_peer_phase2(h);
+    if (phase == 3) return ss_peer_phase3(h);
+    return ss_fail(SS_ERR_STATE, "phase must be 1, 2 or 3");
+}
+
+SS_EXPORT int ss_peer_finish_async(ss_handle *h)
+{
+    if (!h || !h->peer_on) return ss_fail(SS_ERR_STATE, "ss_peer_connect first");
+    if (h->n_pushed == 0) return ss_fail(SS_ERR_STATE, "no frame pushed");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = ss_peer_phase1(h);
+    if (!rc) rc = ss_peer_phase2(h);
+    if (!rc) rc = ss_peer_phase3(h);
+    return rc;
+}
+
+SS_EXPORT int ss_peer_wait(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes)
+{
+    if (!h || !h->peer_on) return ss_fail(SS_ERR_STATE, "ss_peer_connect first");
+    SS_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->peer_rank == h->peer_root && out_bgr) {
+        const size_t row = (size_t)h->cfg.width * 3 * h->cfg.bytes_per_sample;
+        if (out_row_pitch_bytes < row) return ss_fail(SS_ERR_SHAPE, "output pitch too small");
+        SS_CUDA(cudaMemcpy2DAsync(out_bgr, out_row_pitch_bytes, h->out_dev, h->out_pitch, row, h->cfg.height,
+                                  cudaMemcpyDeviceToHost, h->s_comp));
+    }
+    SS_CUDA(cudaStreamSynchronize(h->s_comp));
+    return 0;
+}
+
+SS_EXPORT int ss_peer_finish(ss_handle *h, void *out_bgr, size_t out_row_pitch_bytes)
+{
+    const int rc = ss_peer_finish_async(h);
+    if (rc) return rc;
+    return ss_peer_wait(h, out_bgr, out_row_pitch_bytes);
 }
 
 // ---- test hooks -----------------------------------------------------------------------------------

@@ -1,23 +1,24 @@
-"""Frames of ONE stack sharded over the GPUs of a box.
+"""Frames of ONE stack sharded over the GPUs of a box, one process per GPU.
 
-Rank ``r`` of ``G`` fuses the contiguous frame block ``shard_range(n, r, G)`` with its own
-``PyramidStack`` handle (global frame indices via ``frame_index_base``).  The exchange is
-    1. ONE max all-reduce over packed keys ``float_bits(value) << 32 | (0xFFFFFFFF - global_index)``
-       for every pyramid level plus the two base-level planes: unsigned/signed max over ranks ==
-       "largest energy, ties to the lowest global frame index" == ``np.argmax`` over the whole stack
-       (reference pyramid.py:51,104-105);
-    2. every rank zeroes the coefficients it did not win; ONE float32 sum-reduce to the root then
-       reproduces the winners exactly (x + 0 + ... + 0);
-    3. the root blends the base and collapses the pyramid.
-torch.distributed (NCCL on GPUs; gloo in the CPU tests) is only plumbing here: the tensors alias the
-library's device buffers.
+Rank r of G fuses the contiguous frame block [r*N/G, (r+1)*N/G) with the ordinary kernel chain, producing the running
+state of its frames (per level: best energy, global frame index, winner coefficients; base level: best entropy /
+deviation and the winners' pixels).  The ranks are then merged by the library's fused peer exchange
+(include/shinestack_b200.h, ss_peer_*): every rank merges and collapses one band of image rows straight out of the
+peers' memory over NVLink and stores its rows of the fused image into the root's output buffer; epoch flags in peer
+memory are the only synchronisation.  The merge takes the first maximum in rank (= frame) order with a strict '>',
+i.e. np.argmax over the whole stack (reference pyramid.py:51-54), so the result is bit-identical to the single-GPU
+path.  No collective library and no PyTorch: the only host-side communication is one all-gather of CUDA IPC handles
+per native handle (rendezvous.py).
 """
 import ctypes
+import os
 
 import numpy as np
 
-from . import _native
-from .pyramid import PyramidStack, select_base, _check
+from .pyramid import PyramidStack, _check
+from . import rendezvous as _rdv
+
+PEER_BLOB = 384
 
 
 def shard_range(n_frames, rank, world):
@@ -31,7 +32,6 @@ def shard_range(n_frames, rank, world):
 def bind_to_gpu_numa_node(device):
     """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers
     (allocated afterwards) and the upload traffic stay on that socket.  Best effort: returns the node or None."""
-    import os
     import subprocess
     try:
         bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
@@ -54,108 +54,80 @@ def bind_to_gpu_numa_node(device):
     return None
 
 
-def pack_keys(values, indices):
-    """numpy restatement of ss_pack_keys_kernel (csrc/ss_lib.cu) for the CPU (gloo) tests."""
-    v = np.asarray(values, dtype=np.float32).copy()
-    v[v == 0] = 0.0
-    bits = v.view(np.uint32).astype(np.int64)
-    return (bits << 32) | (0xFFFFFFFF - np.asarray(indices).astype(np.int64))
-
-
-def unpack_keys(keys):
-    keys = np.asarray(keys, dtype=np.int64)
-    idx = (0xFFFFFFFF - (keys & 0xFFFFFFFF)).astype(np.int32)
-    val = (keys >> 32).astype(np.uint32).view(np.float32)
-    return val, idx
-
-
-def exchange(keys, mask_losers, root=0, group=None):
-    """The collective part, backend-agnostic: ``keys`` is an int64 torch tensor (all levels
-    concatenated); ``mask_losers()`` is called after the max all-reduce and must return the float32
-    coefficient tensor with this rank's lost entries zeroed.  Returns the reduced coefficients
-    (valid on ``root``)."""
-    import torch.distributed as dist
-    dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
-    coeffs = mask_losers()
-    dist.reduce(coeffs, dst=root, op=dist.ReduceOp.SUM, group=group)
-    return coeffs
-
-
-class _DevArray:
-    def __init__(self, ptr, count, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr,
-                                         "data": (int(ptr), False), "version": 3}
-
-
 class ShardedPyramidStack:
-    """One per rank.  ``focus_stack_arrays(local_frames, n_total)`` returns the fused image on the
-    root rank and None elsewhere."""
+    """One per rank.  ``focus_stack_arrays(local_frames, n_total)`` returns the fused image on the root rank and None
+    elsewhere.  ``rendezvous``: an object with ``all_gather(bytes) -> list[bytes]`` (default: from the torchrun-style
+    environment variables, see rendezvous.py)."""
 
-    def __init__(self, rank, world, device=0, group=None, root=0, exchange="p2p", **kwargs):
-        """``exchange``: "p2p" = key max all-reduce (NCCL) + root-side gather of the winners' coefficients
-        over NVLink peer memory (CUDA IPC); "nccl" = key max all-reduce + masked float32 sum-reduce."""
-        self.rank, self.world, self.device, self.group, self.root = rank, world, device, group, root
-        self.exchange_mode = exchange
+    def __init__(self, rank, world, device=0, root=0, rendezvous=None, **kwargs):
+        self.rank, self.world, self.device, self.root = rank, world, device, root
         self.kwargs = kwargs
         self.algo = None
         self.n_total = None
+        self._rdv = rendezvous
+        self._connected_handle = None
 
     def _algo(self, n_total):
         start, _ = shard_range(n_total, self.rank, self.world)
         if self.algo is None or self.n_total != n_total:
+            if self.algo is not None:
+                self.algo.close()
             self.algo = PyramidStack(device=self.device, frame_index_base=start, keep_depth_maps=False,
                                      **self.kwargs)
             self.n_total = n_total
+            self._connected_handle = None
         return self.algo
+
+    def _connect(self):
+        """All-gather the IPC handles of the native handle's exchangeable buffers and open the peers' (once per
+        native handle; the ranks create their handles in lock step, so they all get here together)."""
+        a = self.algo
+        if self.world == 1 or self._connected_handle == a._h.value:
+            return
+        if self._rdv is None:
+            self._rdv = _rdv.TcpRendezvous.from_env()
+        blob = (ctypes.c_uint8 * PEER_BLOB)()
+        _check(a._lib.ss_peer_export(a._h, blob))
+        blobs = b"".join(self._rdv.all_gather(bytes(blob)))
+        _check(a._lib.ss_peer_connect(a._h, blobs, self.world, self.rank, self.root))
+        self._rdv.barrier()           # nobody signals into a peer's flags before everybody has opened them
+        self._connected_handle = a._h.value
 
     def begin(self, img0, n_local, n_total, resident=False):
         a = self._algo(n_total)
         a._set_metadata(img0)
         a._ensure_handle(img0.shape, img0.dtype, n_local, resident=resident)
+        self._connect()
         return a
 
-    def finish(self, n_local, shape, out=None):
-        """Local base selection, exchange, and (root) collapse.  All ranks must call it."""
-        import torch
+    def finish(self, n_local, shape, out=None, download=True):
+        """Base selection on the own frames, peer exchange, banded collapse.  All ranks must call it; the root
+        returns the fused image (``download=False``: the image stays on the device and True is returned)."""
         a = self.algo
         lib, h = a._lib, a._h
-        select_base(lib, h, n_local, a.num_pixel_values, a.float_type)
-        if self.world > 1:
-            ptr, cnt = ctypes.c_void_p(), ctypes.c_size_t()
-            _check(lib.ss_exchange_keys(h, ctypes.byref(ptr), ctypes.byref(cnt)))
-            dev = f"cuda:{self.device}"
-            keys = torch.as_tensor(_DevArray(ptr.value, cnt.value, "<i8"), device=dev)
-
-            def mask():
-                torch.cuda.synchronize(self.device)
-                p2, c2 = ctypes.c_void_p(), ctypes.c_size_t()
-                _check(lib.ss_exchange_mask_losers(h, ctypes.byref(p2), ctypes.byref(c2)))
-                return torch.as_tensor(_DevArray(p2.value, c2.value, "<f4"), device=dev)
-
-            if self.exchange_mode == "p2p":
-                import torch.distributed as dist
-                dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=self.group)
-                mine = torch.empty(64, dtype=torch.uint8)
-                _check(lib.ss_exchange_ipc_handle(h, ctypes.c_void_p(mine.data_ptr())))
-                allh = torch.empty(64 * self.world, dtype=torch.uint8, device=dev)
-                dist.all_gather_into_tensor(allh, mine.to(dev), group=self.group)
-                allh = allh.cpu()                       # also waits for the key reduction
-                if self.rank == self.root:
-                    starts = np.array([shard_range(self.n_total, r, self.world)[0] for r in range(self.world)]
-                                      + [self.n_total], dtype=np.int32)
-                    _check(lib.ss_exchange_pull(h, ctypes.c_void_p(allh.data_ptr()),
-                                                starts.ctypes.data_as(ctypes.c_void_p), self.world, self.rank))
-                dist.barrier(group=self.group)          # peers keep their state until the root has gathered it
-            else:
-                exchange(keys, mask, self.root, self.group)
-                torch.cuda.synchronize(self.device)
-                if self.rank == self.root:
-                    _check(lib.ss_exchange_adopt(h))
-        if self.rank != self.root:
-            return None
+        if self.world == 1:
+            _check(lib.ss_finish_base_device(h))
+            if not download:
+                _check(lib.ss_finish_collapse(h, None, 0))
+                return True
+            if out is None:
+                out = np.empty((shape[0], shape[1], 3), dtype=a.dtype)
+            _check(lib.ss_finish_collapse(h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+            return out
+        if self.rank != self.root or not download:
+            _check(lib.ss_peer_finish(h, None, 0))
+            return True if self.rank == self.root else None
         if out is None:
             out = np.empty((shape[0], shape[1], 3), dtype=a.dtype)
-        _check(lib.ss_finish_collapse(h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+        _check(lib.ss_peer_finish(h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+        return out
+
+    def download(self, shape, out=None):
+        """The fused image of the last ``finish(download=False)`` (root only)."""
+        a = self.algo
+        if out is None:
+            out = np.empty((shape[0], shape[1], 3), dtype=a.dtype)
+        _check(a._lib.ss_download_output(a._h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
         return out
 
     def focus_stack_arrays(self, local_frames, n_total):
@@ -166,4 +138,5 @@ class ShardedPyramidStack:
         for i, img in enumerate(local_frames):
             a._validate(img, img0.shape[:2], img0.dtype)
             a._push(i, img, ring)
-        return self.finish(len(local_frames), img0.shape[:2])
+        res = self.finish(len(local_frames), img0.shape[:2])
+        return res if self.rank == self.root else None

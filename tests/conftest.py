@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# several native handles (two streams each) play the ranks of a box on ONE device in the peer-exchange tests: give
+# every stream its own hardware queue (must be set before CUDA is initialised)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

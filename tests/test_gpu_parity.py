@@ -169,54 +169,76 @@ def test_full_width_staircase_properties(dtype, n):
     assert err.max() <= max(1, maxv // 128)   # coarse levels may come from another (blurred) frame
 
 
-def test_frame_sharding_merge_on_one_gpu(oracle):
-    """Two handles fuse the two halves of a stack (as two ranks would); the library's key packing /
-    loser masking kernels plus a max and a sum over the shards (done here with torch on the same device
-    instead of NCCL) must reproduce the single-handle result bit for bit."""
-    import torch
-    from shinestacker_b200.sharded import ShardedPyramidStack, shard_range, _DevArray
-    from shinestacker_b200.pyramid import log_prob_table, _check
-    n, h, w = 7, 300, 420
-    frames = synthetic.make_noise_stack(n, h, w, np.uint8, 95)
-    frames[4][:50, :60] = frames[2][:50, :60]          # exact ties across the shard boundary
-    ref, info = oracle.focus_stack(frames)
-    world = 2
-    shards, keys, lib = [], [], _native.load()
+def _peer_stack_on_one_gpu(frames, world, root=0, **kw):
+    """`world` native handles play the ranks of a box on one device: contiguous frame blocks, ss_peer_connect_ptrs
+    (device pointers instead of CUDA IPC), every rank's part enqueued before any is awaited."""
+    from shinestacker_b200.sharded import shard_range
+    from shinestacker_b200.pyramid import _check
+    lib = _native.load()
+    n = len(frames)
+    h, w = frames[0].shape[:2]
+    algos = []
     for r in range(world):
         f0, f1 = shard_range(n, r, world)
-        s = ShardedPyramidStack(r, 1, device=0, batch_frames=2)     # world=1: no collective inside
-        s.world, s.rank = world, r
-        a = PyramidStack(device=0, frame_index_base=f0, keep_depth_maps=False, batch_frames=2)
+        a = PyramidStack(device=0, frame_index_base=f0, keep_depth_maps=False, **kw)
         a._set_metadata(frames[0])
         a._ensure_handle(frames[0].shape, frames[0].dtype, f1 - f0)
-        ring = a._staging(frames[0].nbytes, 4)
-        for i, f in enumerate(frames[f0:f1]):
-            a._push(i, f, ring)
-        counts = np.empty((f1 - f0, 256), dtype=np.int64)
-        _check(lib.ss_finish_begin(a._h, counts.ctypes.data_as(ctypes.c_void_p)))
-        tab = log_prob_table(counts)
-        _check(lib.ss_finish_select_base(a._h, tab.ctypes.data_as(ctypes.c_void_p)))
-        ptr, cnt = ctypes.c_void_p(), ctypes.c_size_t()
-        _check(lib.ss_exchange_keys(a._h, ctypes.byref(ptr), ctypes.byref(cnt)))
-        keys.append(torch.as_tensor(_DevArray(ptr.value, cnt.value, "<i8"), device="cuda:0"))
-        shards.append(a)
-    red = torch.maximum(keys[0], keys[1])
-    coeffs = []
-    for a, k in zip(shards, keys):
-        k.copy_(red)
-        torch.cuda.synchronize()
-        p2, c2 = ctypes.c_void_p(), ctypes.c_size_t()
-        _check(lib.ss_exchange_mask_losers(a._h, ctypes.byref(p2), ctypes.byref(c2)))
-        coeffs.append(torch.as_tensor(_DevArray(p2.value, c2.value, "<f4"), device="cuda:0"))
-    coeffs[0].add_(coeffs[1])
-    torch.cuda.synchronize()
-    root = shards[0]
-    _check(lib.ss_exchange_adopt(root._h))
-    out = np.empty((h, w, 3), np.uint8)
-    _check(lib.ss_finish_collapse(root._h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
-    maps = root.get_depth_maps()
+        algos.append((a, f0, f1))
+    ptrs = (ctypes.c_void_p * (6 * world))()
+    for r, (a, _, _) in enumerate(algos):
+        mine = (ctypes.c_void_p * 6)()
+        _check(lib.ss_peer_ptrs(a._h, mine))
+        for i in range(6):
+            ptrs[6 * r + i] = mine[i]
+    for r, (a, _, _) in enumerate(algos):
+        _check(lib.ss_peer_connect_ptrs(a._h, ptrs, world, r, root))
+    outs = []
+    for rep in range(2):                        # twice: the second stack has to wait for the DONE flags of the first
+        for a, f0, f1 in algos:
+            _check(lib.ss_reset(a._h))
+            ring = a._staging(frames[0].nbytes, 2 * max(a.batch_frames, 1))
+            for i, f in enumerate(frames[f0:f1]):
+                a._push(i, f, ring)
+        for phase in (1, 2, 3):                 # phase by phase: the ranks share one device here
+            for a, _, _ in algos:
+                _check(lib.ss_peer_phase(a._h, phase))
+        out = np.empty((h, w, 3), frames[0].dtype)
+        for r, (a, _, _) in enumerate(algos):
+            if r == root:
+                _check(lib.ss_peer_wait(a._h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+            else:
+                _check(lib.ss_peer_wait(a._h, None, 0))
+        outs.append(out)
+    maps = algos[root][0].get_depth_maps()
+    for a, _, _ in algos:
+        a.close()
+    assert np.array_equal(outs[0], outs[1])
+    return outs[1], maps
+
+
+@pytest.mark.parametrize("world,n,h,w,dtype,seed", [
+    (2, 7, 300, 420, np.uint8, 95),
+    (3, 8, 260, 390, np.uint8, 96),
+    (8, 19, 515, 750, np.uint16, 94),          # odd level sizes, bands of a few rows at the coarse levels
+    (4, 5, 1030, 520, np.uint8, 93),           # more rows than columns; one rank gets a single frame
+])
+def test_fused_peer_exchange_on_one_gpu(oracle, world, n, h, w, dtype, seed):
+    """Frames sharded over `world` ranks, merged by the fused peer exchange (ss_peer_*: epoch flags, banded merge out
+    of the peers' state, banded collapse into the root's image): bit-identical to fusing the stack in one go."""
+    frames = synthetic.make_noise_stack(n, h, w, dtype, seed)
+    frames[4][:50, :60] = frames[2][:50, :60]          # exact ties across shard boundaries
+    frames[n - 1][h - 40:, w - 70:] = frames[0][h - 40:, w - 70:]
+    ref, info = oracle.focus_stack(frames)
+    out, maps = _peer_stack_on_one_gpu(frames, world, batch_frames=2)
     golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
-                                               best_d=info["best_d"], levels=info["levels"]), "sharded")
+                                               best_d=info["best_d"], levels=info["levels"]), f"peer world={world}")
+
+
+def test_fused_peer_exchange_other_root(oracle):
+    frames = synthetic.make_stack(6, 280, 384, np.uint8, 92)
+    ref, _ = oracle.focus_stack(frames)
+    out, _ = _peer_stack_on_one_gpu(frames, 3, root=2, batch_frames=3)
+    assert np.array_equal(out, ref)
 
 
 def test_config4_geometry_tail_columns_u16(oracle):
@@ -252,47 +274,6 @@ def test_float64_matches_oracle(oracle, gen, n, h, w, dtype, seed):
     out, maps, _ = run_gpu(frames, float_type="float-64")
     golden_util.assert_matches(out, maps, dict(fused=ref, best=info["best"], best_e=info["best_e"],
                                                best_d=info["best_d"], levels=info["levels"]), "float-64")
-
-
-def test_frame_sharding_peer_gather_on_one_gpu(oracle):
-    """The NVLink-peer variant of the exchange (ss_exchange_pull): three handles play three ranks on one
-    device; after the key max-reduction the root gathers the winners' coefficients from the other handles'
-    state with ONE kernel (no masking, no sum).  Must equal the single-handle result bit for bit."""
-    import torch
-    from shinestacker_b200.sharded import shard_range, _DevArray
-    from shinestacker_b200.pyramid import select_base, _check
-    n, h, w, world = 8, 260, 390, 3
-    frames = synthetic.make_noise_stack(n, h, w, np.uint8, 96)
-    frames[5][:70, :90] = frames[1][:70, :90]          # exact ties across shard boundaries
-    ref, info = oracle.focus_stack(frames)
-    lib = _native.load()
-    shards, keys, ptrs = [], [], (ctypes.c_void_p * world)()
-    starts = np.array([shard_range(n, r, world)[0] for r in range(world)] + [n], dtype=np.int32)
-    for r in range(world):
-        f0, f1 = shard_range(n, r, world)
-        a = PyramidStack(device=0, frame_index_base=f0, keep_depth_maps=False, batch_frames=2)
-        a._set_metadata(frames[0])
-        a._ensure_handle(frames[0].shape, frames[0].dtype, f1 - f0)
-        ring = a._staging(frames[0].nbytes, 4)
-        for i, f in enumerate(frames[f0:f1]):
-            a._push(i, f, ring)
-        select_base(lib, a._h, f1 - f0, 256)
-        ptr, cnt = ctypes.c_void_p(), ctypes.c_size_t()
-        _check(lib.ss_exchange_keys(a._h, ctypes.byref(ptr), ctypes.byref(cnt)))
-        keys.append(torch.as_tensor(_DevArray(ptr.value, cnt.value, "<i8"), device="cuda:0"))
-        cp, cn = ctypes.c_void_p(), ctypes.c_size_t()
-        _check(lib.ss_exchange_coef_ptr(a._h, ctypes.byref(cp), ctypes.byref(cn)))
-        ptrs[r] = cp.value
-        shards.append(a)
-    red = torch.maximum(torch.maximum(keys[0], keys[1]), keys[2])
-    root = shards[0]
-    keys[0].copy_(red)
-    torch.cuda.synchronize()
-    _check(lib.ss_exchange_pull_ptrs(root._h, ptrs, starts.ctypes.data_as(ctypes.c_void_p), world, 0))
-    out = np.empty((h, w, 3), np.uint8)
-    _check(lib.ss_finish_collapse(root._h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
-    golden_util.assert_matches(out, root.get_depth_maps(), dict(fused=ref, best=info["best"], best_e=info["best_e"],
-                                                                best_d=info["best_d"], levels=info["levels"]), "peer gather")
 
 
 def test_file_interface_maps_uncompressed_tiffs(tmp_path):

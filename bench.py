@@ -52,8 +52,9 @@ def parse():
     ap.add_argument("--width", type=int, default=4096)
     ap.add_argument("--dtype", default="uint8", choices=["uint8", "uint16"])
     ap.add_argument("--batch", type=int, default=8, help="frames per kernel-chain launch on the e2e path")
-    ap.add_argument("--cpu-sample-frames", type=int, default=64,
-                    help="frames of the stack the CPU baseline fuses (64 = the whole workload, ~10 s on 16 cores)")
+    ap.add_argument("--cpu-sample-frames", type=int, default=0,
+                    help="frames of the stack the CPU oracle port fuses (0 = the whole stack, which also enables the "
+                         "parity check; ~10 s for config 2 on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sample-frames", type=int, default=0,
                     help="frames per stack the unmodified reference fuses (0 = bounded automatically: ~10-30 s of CPU)")
@@ -445,7 +446,7 @@ def main():
                                  "frac": fp32_rate / 36.2, "algorithmic_chain_steps_per_pixel": 73.5,
                                  "peak_source": "tools/microbench.cu on B200 (scalar FFMA, 124.5 of 128 lanes/clk/SM)"}
         # ---- CPU side: reference baseline, oracle port, parity of the timed GPU result ------------------
-        n_cpu = max(1, min(a.cpu_sample_frames, N))
+        n_cpu = N if a.cpu_sample_frames <= 0 else max(1, min(a.cpu_sample_frames, N))
         want_parity = a.check_parity == "on" or (a.check_parity == "auto" and world == 1 and
                                                  not a.no_cpu_baseline and n_cpu == N)
         oracle_out = oracle_info = None

@@ -148,6 +148,20 @@ SIGNATURES_ALIGN = {
     "ssal_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),
 }
 
+# every symbol declared in include/shinestack_b200_subactions.h
+SIGNATURES_SUBACTIONS = {
+    "sssub_create": (_i, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_vp)]),
+    "sssub_destroy": (None, [_vp]),
+    "sssub_upload": (_i, [_vp, _vp, _sz]),
+    "sssub_apply_lut": (_i, [_vp, _vp, _i]),
+    "sssub_apply_vignette": (_i, [_vp, _dp, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
+    "sssub_download": (_i, [_vp, _vp, _sz]),
+    "sssub_sync": (_i, [_vp]),
+    "sssub_device_frame": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
+    "sssub_kernel_time_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "sssub_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),
+}
+
 _LIB = None
 
 
@@ -164,7 +178,8 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as e:
         raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
-    for name, (res, args) in list(SIGNATURES.items()) + list(SIGNATURES_DEPTHMAP.items()) + list(SIGNATURES_ALIGN.items()):
+    for name, (res, args) in list(SIGNATURES.items()) + list(SIGNATURES_DEPTHMAP.items()) + \
+            list(SIGNATURES_ALIGN.items()) + list(SIGNATURES_SUBACTIONS.items()):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -1834,3 +1834,4 @@ SS_EXPORT int ss_test_collapse_step(const float *img_planes, int h2, int w2, con
 
 #include "ss_dm_lib.cuh"
 #include "ss_al_lib.cuh"
+#include "ss_sub_lib.cuh"

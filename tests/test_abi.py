@@ -46,6 +46,19 @@ def test_library_exports_every_depthmap_symbol():
     assert b"float" in lib.ss_last_error()
 
 
+def test_library_exports_every_subaction_symbol():
+    lib = _native.load()
+    names = _declared_symbols("shinestack_b200_subactions.h", "sssub_")
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(_native.SIGNATURES_SUBACTIONS), set(names) ^ set(_native.SIGNATURES_SUBACTIONS)
+    h = ctypes.c_void_p()
+    if lib.ss_device_count() == 0:      # no silent CPU fallback for the sub-action passes either
+        assert lib.sssub_create(64, 64, 1, 0, ctypes.byref(h)) == _native.SS_ERR_NO_DEVICE
+    assert lib.sssub_create(64, 64, 3, 0, ctypes.byref(h)) == _native.SS_ERR_BIT_DEPTH
+
+
 def test_library_exports_every_align_symbol():
     lib = _native.load()
     names = _declared_symbols("shinestack_b200_align.h", "ssal_")

@@ -17,6 +17,7 @@ and ``AlignmentError``.  There is no CPU warp here: without the library / an sm_
 ``NativeLibraryError``.
 """
 import ctypes
+import threading
 import logging
 
 import numpy as np
@@ -205,6 +206,7 @@ class Warper:
         self._h = hp
         self._kernels = {}
         self.last_kernel_ms = None
+        self.ecc_generation = 0     # bumped by every ecc_set_reference: identifies the reference pyramid now in HBM
 
     def close(self):
         if getattr(self, "_h", None) is not None:
@@ -264,6 +266,8 @@ class Warper:
         self._check_frame(img)
         img = np.ascontiguousarray(img)
         _check(self._lib.ssal_ecc_set_reference(self._h, img.ctypes.data_as(ctypes.c_void_p), img.strides[0]))
+        self.ecc_generation += 1
+        return self.ecc_generation
 
     def ecc_estimate(self, img, finest_level=0, max_iters=30, eps_px=1e-3, init_m=None):
         """Forward 2x3 similarity (moving -> reference frame, like cv2.estimateAffinePartial2D) of ``img`` by
@@ -298,15 +302,51 @@ class Warper:
 
 
 _WARPERS = {}
+_WARPERS_LOCK = threading.Lock()
+
+
+_SELF_CHECKED = False
+
+
+def _self_check(device=0):
+    """The warp stage promises cv2's results bit for bit, which ties it to the fixed-point kernels of the installed
+    cv2 build (validated: 4.13).  Once per process a small random tile goes through cv2.warpAffine and through the
+    device; a mismatch does not stop the run but is reported."""
+    global _SELF_CHECKED  # pylint: disable=global-statement
+    if _SELF_CHECKED:
+        return
+    _SELF_CHECKED = True
+    try:
+        import cv2  # pylint: disable=import-outside-toplevel
+        rng = np.random.default_rng(7)
+        tile = rng.integers(0, 256, (48, 80, 3)).astype(np.uint8)
+        m = np.array([[0.9993, -0.012, 1.37], [0.012, 0.9993, -0.81]])
+        wp = Warper(tile.shape[:2], tile.dtype, device)
+        try:
+            got = wp.warp(tile, m, ALIGN_RIGID, BORDER_REPLICATE)
+        finally:
+            wp.close()
+        expect = cv2.warpAffine(tile, m, (80, 48), borderMode=cv2.BORDER_REPLICATE)
+        if not np.array_equal(got, expect):
+            import warnings  # pylint: disable=import-outside-toplevel
+            warnings.warn(f"shinestacker_b200.align: the GPU warp differs from cv2 {cv2.__version__}.warpAffine on a "
+                          f"test tile ({int((got != expect).sum())} samples); the bit-exact contract was validated "
+                          "against cv2 4.13 -- results may differ from the reference by a few LSB", RuntimeWarning)
+    except Exception:  # pylint: disable=broad-except
+        pass
 
 
 def _warper_for(img, device=0):
+    """The process-wide warper of this geometry (shared by every caller: whoever relies on state inside it -- the ECC
+    reference pyramid -- must check ``ecc_generation``, see AlignFrames.run_frame)."""
+    _self_check(device)
     key = (img.shape[0], img.shape[1], img.dtype.str, device)
-    if key not in _WARPERS:
-        if len(_WARPERS) >= 4:      # a handful of geometries at most stay resident
-            _WARPERS.pop(next(iter(_WARPERS))).close()
-        _WARPERS[key] = Warper(img.shape[:2], img.dtype, device)
-    return _WARPERS[key]
+    with _WARPERS_LOCK:
+        if key not in _WARPERS:
+            if len(_WARPERS) >= 4:      # a handful of geometries at most stay resident
+                _WARPERS.pop(next(iter(_WARPERS))).close()
+            _WARPERS[key] = Warper(img.shape[:2], img.dtype, device)
+        return _WARPERS[key]
 
 
 def align_images(img_1, img_0, feature_config=None, matching_config=None, alignment_config=None,
@@ -440,8 +480,12 @@ class AlignFrames:
     def run_frame(self, idx, ref_idx, img_0):
         if idx == self.process.ref_idx:
             return img_0
-        if self.alignment_config['estimator'] == ESTIMATOR_ECC and self._ecc_ref == (ref_idx, img_0.shape, img_0.dtype):
-            return self.align_images(idx, None, img_0)      # the reference pyramid is already in HBM
+        if self.alignment_config['estimator'] == ESTIMATOR_ECC and self._ecc_ref is not None:
+            # the reference pyramid of ref_idx may still be in HBM -- but the warper is shared process-wide: only if
+            # it is the same object and nobody has replaced its reference since we set it
+            wp = _warper_for(img_0, self.device)
+            if self._ecc_ref == (ref_idx, img_0.shape, img_0.dtype, id(wp), wp.ecc_generation):
+                return self.align_images(idx, None, img_0)
         return self.align_images(idx, self.process.img_ref(ref_idx), img_0, ref_idx)
 
     def align_images(self, idx, img_1, img_0, ref_idx=None):
@@ -457,7 +501,8 @@ class AlignFrames:
             n_good, _m, img = _align_images_ecc(img_1, img_0, self.alignment_config, callbacks, self.device,
                                                 reference_is_set=img_1 is None)
             if img_1 is not None and ref_idx is not None:
-                self._ecc_ref = (ref_idx, img_0.shape, img_0.dtype)
+                wp = _warper_for(img_0, self.device)
+                self._ecc_ref = (ref_idx, img_0.shape, img_0.dtype, id(wp), wp.ecc_generation)
         else:
             n_good, _m, img = align_images(img_1, img_0, feature_config=self.feature_config,
                                            matching_config=self.matching_config,

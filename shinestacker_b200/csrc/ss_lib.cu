@@ -344,9 +344,10 @@ __global__ void ss_finalize_kernel(const float *img, int h, int w, int bytes, vo
 
 // The running state of all levels and of the base level lives in three contiguous arrays (values, indices, 3-plane
 // coefficients) in one fixed order, so that the multi-GPU exchange addresses every level with one set of offsets.
+#define SS_MAX_SEGMENTS 16   // pyramid levels + 2 base planes: up to 14 Laplacian levels (a 64k x 64k image at min_size 4)
 struct SsSegments {        // per plane-group (pyramid level / base plane): pixel offset, pixel count, coefficient offset
     int count;
-    unsigned long long px_off[12], n_px[12], coef_off[12];
+    unsigned long long px_off[SS_MAX_SEGMENTS], n_px[SS_MAX_SEGMENTS], coef_off[SS_MAX_SEGMENTS];
 };
 
 // ---- fused peer exchange over NVLink (one process per GPU, no collective library) ---------------------
@@ -364,7 +365,7 @@ struct SsPeerState {
 };
 struct SsBandRows {                       // per segment: rows this rank merges, and the rows it owns (depth maps)
     int count;
-    int row0[12], row1[12], own0[12], own1[12], width[12];
+    int row0[SS_MAX_SEGMENTS], row1[SS_MAX_SEGMENTS], own0[SS_MAX_SEGMENTS], own1[SS_MAX_SEGMENTS], width[SS_MAX_SEGMENTS];
 };
 enum { SS_FLAG_READY = 0, SS_FLAG_DONE = 1, SS_FLAG_OUT = 2 };
 
@@ -677,7 +678,8 @@ static int ss_create_impl(const ss_config *cfg, ss_handle *h)
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return ss_fail(SS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
     }
-    if (h->L + 2 > 12) return ss_fail(SS_ERR_SHAPE, "pyramid with %d levels is not supported (max 10)", h->L);
+    if (h->L + 2 > SS_MAX_SEGMENTS)
+        return ss_fail(SS_ERR_SHAPE, "pyramid with %d levels is not supported (max %d)", h->L, SS_MAX_SEGMENTS - 2);
     h->lv.resize(h->L);
     {
         // segments of the contiguous state: every level, then the two base planes
@@ -1590,8 +1592,8 @@ SS_EXPORT int ss_test_peer_bands(int height, int width, int min_size, int world,
 {
     std::vector<int> lh, lw;
     const int L = ss_levels_for(height, width, min_size, lh, lw);
-    if (L + 2 > 12 || !out || world < 1 || rank < 0 || rank >= world) return SS_ERR_STATE;
-    int r[4][12];
+    if (L + 2 > SS_MAX_SEGMENTS || !out || world < 1 || rank < 0 || rank >= world) return SS_ERR_STATE;
+    int r[4][SS_MAX_SEGMENTS];
     ss_band_rows(lh.data(), L, world, rank, r[0], r[1], r[2], r[3]);
     for (int k = 0; k < 4; ++k)
         for (int s2 = 0; s2 < L + 2; ++s2) out[k * (L + 2) + s2] = r[k][s2];

@@ -216,7 +216,10 @@ class PyramidStack(PyramidBase):
     def _ensure_handle(self, shape, dtype, n_frames, resident=False):
         h, w = int(shape[0]), int(shape[1])
         bps = np.dtype(dtype).itemsize
-        geom = (h, w, bps)
+        # everything ss_create bakes into the native handle: changing a public option between two calls must not
+        # silently keep the old configuration
+        geom = (h, w, bps, int(self.min_size), int(self.kernel_size), float(self.gen_kernel_param),
+                64 if self.float_type == np.float64 else 32, self.device, self.batch_frames, self.frame_index_base)
         if self._h is not None and self._geom == geom and n_frames <= self._max_frames and \
                 (not resident or self._resident >= n_frames):
             _check(self._lib.ss_reset(self._h))

@@ -139,6 +139,31 @@ def test_align_frames_sub_action_with_both_estimators():
         action.end()
 
 
+def test_two_ecc_sub_actions_sharing_one_warper_never_align_to_a_stale_reference():
+    """The warper (and the ECC reference pyramid inside it) is shared process-wide per geometry: an AlignFrames whose
+    reference was replaced by somebody else must upload it again instead of trusting its own bookkeeping."""
+    from unittest.mock import MagicMock
+    scene_a, scene_b = au.textured_scene(512, 768, seed=31), au.textured_scene(512, 768, seed=32)
+    mov_a, mov_b = au.moved_frame(scene_a, 0.3, 1.002, 5.0, -3.0)[0], au.moved_frame(scene_b, -0.2, 0.999, -4.0, 6.0)[0]
+    acts = []
+    for ref in (scene_a, scene_b):
+        action, process = al.AlignFrames(estimator="ecc"), MagicMock()
+        process.ref_idx, process.counts = 0, 3
+        process.img_ref.side_effect = lambda idx, ref=ref: ref
+        action.begin(process)
+        acts.append((action, process))
+    inner = (slice(40, -40), slice(40, -40))
+    out = acts[0][0].run_frame(1, 0, mov_a)                      # A sets its reference
+    assert np.abs(out[inner].astype(int) - scene_a[inner].astype(int)).mean() < 3.0
+    out = acts[1][0].run_frame(1, 0, mov_b)                      # B replaces it in the shared warper
+    assert np.abs(out[inner].astype(int) - scene_b[inner].astype(int)).mean() < 3.0
+    out = acts[0][0].run_frame(2, 0, mov_a)                      # A must notice and upload scene_a again
+    assert np.abs(out[inner].astype(int) - scene_a[inner].astype(int)).mean() < 3.0
+    assert acts[0][1].img_ref.call_count == 2 and acts[1][1].img_ref.call_count == 1
+    out = acts[0][0].run_frame(1, 0, mov_a)                      # ... and now it is current again
+    assert acts[0][1].img_ref.call_count == 2
+
+
 def test_fused_align_and_stack_pipeline_recovers_the_undisplaced_result():
     from shinestacker_b200.pipeline import align_and_stack_arrays
     from tools.time_pipeline import displaced_stack

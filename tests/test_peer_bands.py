@@ -11,8 +11,8 @@ from shinestacker_b200 import _native
 
 def bands(h, w, world, rank, min_size=32):
     lib = _native.load()
-    out = (ctypes.c_int32 * (4 * 12))()
-    lh = (ctypes.c_int32 * 12)()
+    out = (ctypes.c_int32 * (4 * 16))()
+    lh = (ctypes.c_int32 * 16)()
     L = lib.ss_test_peer_bands(h, w, min_size, world, rank, out, lh)
     assert L >= 0
     a = np.array(out[:4 * (L + 2)]).reshape(4, L + 2)

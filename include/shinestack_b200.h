@@ -86,6 +86,10 @@ int ss_host_free(void *ptr);
  * order; when batch_frames frames are pending their kernel chain (pyramid build + energy + running
  * arg-max select, pyramid.py:125-139 and :48-55) is launched behind the copy. */
 int ss_push_frame(ss_handle *h, const void *bgr, size_t row_pitch_bytes);
+/* Same for a host frame whose samples are in R, G, B order -- the payload of an uncompressed RGB TIFF, which is what
+ * the reference's write_img produces (utils.py:23-30): uploaded as it is, channels swapped on the device (the result is
+ * the B, G, R frame cv2.imread would have delivered, utils.py:11-20), so the host side only moves bytes. */
+int ss_push_frame_rgb(ss_handle *h, const void *rgb, size_t row_pitch_bytes);
 /* Same, for a frame that already lives in device memory (device pointer, same layout). */
 int ss_push_frame_device(ss_handle *h, const void *d_bgr, size_t row_pitch_bytes);
 /* Block until all pushed work has completed. */

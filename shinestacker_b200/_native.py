@@ -80,6 +80,7 @@ SIGNATURES = {
     "ss_host_free": (_i, [_vp]),
     "ss_push_frame": (_i, [_vp, _vp, _sz]),
     "ss_push_frame_device": (_i, [_vp, _vp, _sz]),
+    "ss_push_frame_rgb": (_i, [_vp, _vp, _sz]),
     "ss_sync": (_i, [_vp]),
     "ss_sync_copies": (_i, [_vp]),
     "ss_finish_begin": (_i, [_vp, _vp]),

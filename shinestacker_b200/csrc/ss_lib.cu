@@ -1037,7 +1037,34 @@ static int ss_launch_pending(ss_handle *h, bool flush)
     return 0;
 }
 
-static int ss_push_impl(ss_handle *h, const void *src, size_t pitch, cudaMemcpyKind kind)
+// R <-> B of every pixel of one stored frame, in place: 4 pixels (three 32-bit words) per thread for 8-bit samples,
+// 2 pixels for 16-bit ones; rows of the frame store are 4-byte aligned.
+template <typename T>
+__global__ void ss_swap_rb_kernel(char *frame, size_t pitch, int w, int h)
+{
+    const int y = blockIdx.y;
+    const int per = sizeof(T) == 1 ? 4 : 2;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * per;
+    if (x >= w || y >= h) return;
+    T *px = (T *)(frame + (size_t)y * pitch) + 3 * x;
+    if (x + per <= w) {
+        uint32_t *wd = (uint32_t *)px;
+        const uint32_t a = wd[0], b = wd[1], c = wd[2];
+        if (sizeof(T) == 1) {   // bytes  R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3  ->  B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+            wd[0] = ((a >> 16) & 0xffu) | (a & 0xff00u) | ((a & 0xffu) << 16) | ((b & 0xff00u) << 16);
+            wd[1] = (b & 0xffu) | ((a >> 24) << 8) | ((c & 0xffu) << 16) | (b & 0xff000000u);
+            wd[2] = ((b >> 16) & 0xffu) | ((c >> 24) << 8) | (c & 0xff0000u) | ((c & 0xff00u) << 16);
+        } else {                // half-words  R0 G0 | B0 R1 | G1 B1  ->  B0 G0 | R0 B1 | G1 R1
+            wd[0] = (b & 0xffffu) | (a & 0xffff0000u);
+            wd[1] = (a & 0xffffu) | (c & 0xffff0000u);
+            wd[2] = (c & 0xffffu) | (b & 0xffff0000u);
+        }
+    } else {
+        for (int k = 0; x + k < w; ++k) { const T t = px[3 * k]; px[3 * k] = px[3 * k + 2]; px[3 * k + 2] = t; }
+    }
+}
+
+static int ss_push_impl(ss_handle *h, const void *src, size_t pitch, cudaMemcpyKind kind, bool swap_rb = false)
 {
     if (!h || !src) return ss_fail(SS_ERR_STATE, "null argument");
     if (h->finished_begin) return ss_fail(SS_ERR_STATE, "push after finish_begin; call ss_reset first");
@@ -1056,6 +1083,16 @@ static int ss_push_impl(ss_handle *h, const void *src, size_t pitch, cudaMemcpyK
         SS_CUDA(cudaMemcpyAsync(dst, src, row * h->cfg.height, kind, h->s_copy));
     else
         SS_CUDA(cudaMemcpy2DAsync(dst, h->frame_pitch, src, pitch, row, h->cfg.height, kind, h->s_copy));
+    if (swap_rb) {     // behind the copy, ahead of the batch's kernels (same stream as the copy)
+        const int per = h->cfg.bytes_per_sample == 1 ? 4 : 2;
+        dim3 g(((h->cfg.width + per - 1) / per + 127) / 128, h->cfg.height);
+        if (h->cfg.bytes_per_sample == 1)
+            ss_swap_rb_kernel<uint8_t><<<g, 128, 0, h->s_copy>>>(dst, h->frame_pitch, h->cfg.width, h->cfg.height);
+        else
+            ss_swap_rb_kernel<uint16_t><<<g, 128, 0, h->s_copy>>>(dst, h->frame_pitch, h->cfg.width, h->cfg.height);
+        h->launches++;
+        SS_CUDA(cudaGetLastError());
+    }
     h->n_pushed++;
     if (h->n_pushed % h->batch == 0) return ss_launch_pending(h, false);
     return 0;
@@ -1064,6 +1101,13 @@ static int ss_push_impl(ss_handle *h, const void *src, size_t pitch, cudaMemcpyK
 SS_EXPORT int ss_push_frame(ss_handle *h, const void *bgr, size_t row_pitch_bytes)
 {
     return ss_push_impl(h, bgr, row_pitch_bytes, cudaMemcpyHostToDevice);
+}
+
+// Same as ss_push_frame for a frame whose samples are in R, G, B order (what an uncompressed TIFF holds): the
+// frame is uploaded as it is and the channels are swapped on the device, so the host only moves bytes.
+SS_EXPORT int ss_push_frame_rgb(ss_handle *h, const void *rgb, size_t row_pitch_bytes)
+{
+    return ss_push_impl(h, rgb, row_pitch_bytes, cudaMemcpyHostToDevice, true);
 }
 SS_EXPORT int ss_push_frame_device(ss_handle *h, const void *d_bgr, size_t row_pitch_bytes)
 {

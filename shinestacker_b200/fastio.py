@@ -26,8 +26,9 @@ class PlainTiff:
     """An uncompressed, chunky 8/16-bit RGB TIFF mapped into memory; quacks enough like the ndarray that
     ``cv2.imread`` would return (shape / dtype / ndim / nbytes) for the validation code of the stackers."""
 
-    def __init__(self, mm, offset, h, w, dtype):
+    def __init__(self, mm, offset, h, w, dtype, path=None):
         self._mm = mm
+        self._path, self._offset = path, offset
         self.shape = (h, w, 3)
         self.dtype = np.dtype(dtype)
         self.ndim = 3
@@ -39,6 +40,19 @@ class PlainTiff:
         import cv2  # pylint: disable=import-outside-toplevel
         cv2.cvtColor(self._rgb, cv2.COLOR_RGB2BGR, dst=dst)
         return dst
+
+    def read_rgb_into(self, dst):
+        """The file's R, G, B samples, unconverted, into the flat uint8 buffer ``dst`` (one read() from the page cache
+        instead of touching the mapping page by page); the caller swaps the channels (on the device)."""
+        with open(self._path, "rb", buffering=0) as f:
+            f.seek(self._offset)
+            view = memoryview(dst)[:self.nbytes]
+            got = 0
+            while got < self.nbytes:
+                k = f.readinto(view[got:])
+                if not k:
+                    raise OSError(f"short read from {self._path}")
+                got += k
 
     def to_array(self):
         return self.into_bgr(np.empty(self.shape, self.dtype))
@@ -126,7 +140,7 @@ def open_plain_tiff(path):
             if start + total > size or (bps == 2 and start % 2):
                 return None
             mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
-        return PlainTiff(mm, start, h, w, np.uint8 if bps == 1 else np.uint16)
+        return PlainTiff(mm, start, h, w, np.uint8 if bps == 1 else np.uint16, path)
     except (OSError, ValueError, struct.error):
         return None
 

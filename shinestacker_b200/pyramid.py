@@ -15,6 +15,7 @@ GPU every call raises ``NativeLibraryError``.
 """
 import ctypes
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -192,7 +193,7 @@ class PyramidStack(PyramidBase):
 
     def __init__(self, min_size=DEFAULT_PY_MIN_SIZE, kernel_size=DEFAULT_PY_KERNEL_SIZE,
                  gen_kernel=DEFAULT_PY_GEN_KERNEL, float_type=DEFAULT_PY_FLOAT,
-                 device=0, batch_frames=8, keep_depth_maps=True, frame_index_base=0, decode_threads=4):
+                 device=0, batch_frames=8, keep_depth_maps=True, frame_index_base=0, decode_threads=8):
         super().__init__(min_size, kernel_size, gen_kernel, float_type)
         self.offset = np.arange(-self.pad_amount, self.pad_amount + 1)
         self.dtype = None
@@ -211,6 +212,9 @@ class PyramidStack(PyramidBase):
         self._geom = None
         self._stage = []
         self._stage_bytes = 0
+        self._frame_shape = None
+        self._rgb_frames = set()
+        self.device_channel_swap = True     # mapped RGB TIFFs: upload the raw payload, swap R <-> B on the device
 
     # ---- native handle management ---------------------------------------------------------------
     def _ensure_handle(self, shape, dtype, n_frames, resident=False):
@@ -308,6 +312,75 @@ class PyramidStack(PyramidBase):
         stage_frame(img, view)
         _check(self._lib.ss_push_frame(self._h, ptr, img.shape[1] * 3 * img.dtype.itemsize))
 
+    def _stream(self, n, load_into, ring, on_frame):
+        """Decode / convert on worker threads straight into the pinned ring, upload from the calling thread.
+
+        ``load_into(i, view)`` (worker thread) fills the flat uint8 ``view`` of a pinned slot with frame ``i`` and
+        returns what ``on_frame(i, info)`` (calling thread, stack order, before the upload) should see -- or raises.
+        Slot ``i % R`` is handed to frame ``i`` only once frame ``i - R`` has reached the device.  The calling
+        thread does nothing but validate, push and run the callbacks, so decode, host copies, PCIe and the kernel
+        chain all overlap."""
+        slots = len(ring)
+        if slots < 1:
+            raise NativeLibraryError("no pinned staging buffers")
+        threads = max(1, min(self.decode_threads if self.decode_threads > 0 else 1, slots, n))
+        cond = threading.Condition()
+        state = {"released": 0, "abort": False}
+
+        def job(i):
+            with cond:
+                while i - slots >= state["released"] and not state["abort"]:
+                    cond.wait(0.05)
+                if state["abort"]:
+                    return None
+            return load_into(i, ring[i % slots][1])
+
+        # the workers are the parallelism: cv2's own thread pool serialises calls that arrive from several threads, so
+        # each conversion (RGB -> BGR of a mapped TIFF) runs single-threaded while the pipeline is active
+        cv2_threads = None
+        if threads > 1:
+            try:
+                import cv2  # pylint: disable=import-outside-toplevel
+                cv2_threads = cv2.getNumThreads()
+                cv2.setNumThreads(1)
+            except Exception:  # pylint: disable=broad-except
+                cv2_threads = None
+        pool = ThreadPoolExecutor(max_workers=threads)
+        futures = [pool.submit(job, i) for i in range(n)]
+        half = max(1, slots // 2)
+        try:
+            for i in range(n):
+                info = futures[i].result()
+                on_frame(i, info)
+                self._push_slot(i, ring[i % slots])
+                self._callbacks_after_push(i)
+                if (i + 1) % half == 0 or i + 1 == n:
+                    self._sync_copies()                            # those frames are on the device: free their slots
+                    with cond:
+                        state["released"] = i + 1
+                        cond.notify_all()
+        finally:
+            with cond:
+                state["abort"] = True
+                cond.notify_all()
+            for fut in futures:
+                fut.cancel()
+            pool.shutdown(wait=True)
+            if cv2_threads is not None:
+                import cv2  # pylint: disable=import-outside-toplevel
+                cv2.setNumThreads(cv2_threads)
+
+    def _push_slot(self, i, slot):
+        """Asynchronous upload of the frame staged in the pinned ``slot`` = (pointer, flat uint8 view)."""
+        push = self._lib.ss_push_frame_rgb if i in self._rgb_frames else self._lib.ss_push_frame
+        _check(push(self._h, slot[0], self._frame_shape[1] * 3 * np.dtype(self.dtype).itemsize))
+
+    def _sync_copies(self):
+        _check(self._lib.ss_sync_copies(self._h))
+
+    def _callbacks_after_push(self, i):
+        """Hook of ``_stream`` (focus_stack reports the "processed" step of frame i here)."""
+
     def _finish(self, n, shape):
         lib, h = self._lib, self._h
         select_base(lib, h, n, self.num_pixel_values, self.float_type)
@@ -355,7 +428,7 @@ class PyramidStack(PyramidBase):
         conclusive, else by decoding the file (like the reference's validation pass, pyramid.py:157-158)."""
         if not os.path.isfile(path):
             raise RuntimeError("File does not exist: " + path)     # reference utils.py:12-13
-        hdr = fastio.probe_header(path) if fastio.ENABLED else None
+        hdr = fastio.probe_header(path)
         if hdr is not None:
             h, w, ch, dtype = hdr
             return (h, w, ch), dtype
@@ -394,50 +467,55 @@ class PyramidStack(PyramidBase):
             self._callbacks(i)
         if metadata is None:
             raise ImageLoadError("", "empty file list")
-        # decode ahead on worker threads (cv2.imread releases the GIL); frames are consumed in stack order
-        pool = ThreadPoolExecutor(max_workers=self.decode_threads) if self.decode_threads > 0 and n > 1 else None
-        pending = {}
+        shape2, dtype = metadata
+        frame_bytes = shape2[0] * shape2[1] * 3 * dtype.itemsize
+        self._frame_shape = (shape2[0], shape2[1], 3)
+        rgb_slots = self._rgb_frames = set()
 
-        def fetch(i):
-            # uncompressed TIFFs (what the reference's write_img produces) are mapped instead of decoded
-            if pool is None:
-                return fastio.read_frame(filenames[i], read_img)
-            for j in range(i, min(n, i + self.decode_threads + 1)):
-                if j not in pending:
-                    pending[j] = pool.submit(fastio.read_frame, filenames[j], read_img)
-            return pending.pop(i).result()
+        def load_into(i, view):
+            # worker thread: uncompressed TIFFs (what the reference's write_img produces) are mapped and converted
+            # straight into the pinned slot; everything else is decoded by cv2.imread like the reference and copied
+            img = fastio.read_frame(filenames[i], read_img)
+            if img is None:
+                return None
+            try:
+                if img.ndim != 3 or img.shape[2] != 3 or tuple(img.shape[:2]) != shape2 or img.dtype != dtype:
+                    return (img.shape, img.dtype, img.ndim)
+                if isinstance(img, fastio.PlainTiff) and self.device_channel_swap:
+                    img.read_rgb_into(view)          # raw R, G, B bytes: the device swaps the channels
+                    rgb_slots.add(i)
+                else:
+                    stage_frame(img, view)
+            finally:
+                if isinstance(img, fastio.PlainTiff):
+                    img.close()
+            return (img.shape, img.dtype, img.ndim)
+
+        def on_frame(i, info):
+            self.print_message(f": processing file {filenames[i].split('/')[-1]}")
+            if info is None:
+                raise ImageLoadError(filenames[i])
+            shape, dt, ndim = info
+            if ndim != 3 or shape[2] != 3:
+                raise ImageLoadError(filenames[i], "expected a 3-channel 8 or 16 bit image")
+            if tuple(shape[:2]) != shape2:                     # the decoder has the last word (reference utils.py:56-63)
+                raise ShapeError(shape2, tuple(shape[:2]))
+            if dt != dtype:
+                raise BitDepthError(dtype, dt)
 
         try:
-            self._ensure_handle(metadata[0], metadata[1], n)
-            frame_bytes = metadata[0][0] * metadata[0][1] * 3 * metadata[1].itemsize
+            self._ensure_handle(shape2, dtype, n)
             ring = self._staging(frame_bytes, 2 * max(self.batch_frames, 1))
-            for i, img_path in enumerate(filenames):
-                self.print_message(f": processing file {img_path.split('/')[-1]}")
-                img = fetch(i)
-                if img is None:
-                    raise ImageLoadError(img_path)
-                if img.ndim != 3 or img.shape[2] != 3:
-                    raise ImageLoadError(img_path, "expected a 3-channel 8 or 16 bit image")
-                self._validate(img, *metadata)      # the decoder has the last word (header and decoder agree normally)
-                self._push(i, img, ring)
-                self._callbacks(i + n)
+            self._callbacks_after_push = lambda i: self._callbacks(i + n)
+            self._stream(n, load_into, ring, on_frame)
             self.print_message(': pyramids fusion completed')
-            return self._finish(n, metadata[0])
+            return self._finish(n, shape2)
         except BaseException:
             if self._h is not None:
                 self._lib.ss_reset(self._h)
             raise
         finally:
-            if pool is not None:
-                for fut in pending.values():
-                    if not fut.cancel():
-                        try:                      # a decoded-ahead mapped TIFF must not leak its mapping
-                            res = fut.result()
-                            if isinstance(res, fastio.PlainTiff):
-                                res.close()
-                        except Exception:  # pylint: disable=broad-except
-                            pass
-                pool.shutdown(wait=True)
+            self._callbacks_after_push = lambda i: None
 
     def focus_stack_arrays(self, frames):
         """In-memory entry point: iterable of H x W x 3 BGR uint8/uint16 arrays -> fused image."""
@@ -450,10 +528,21 @@ class PyramidStack(PyramidBase):
         self._set_metadata(img0)
         self._ensure_handle(img0.shape, img0.dtype, len(frames))
         ring = self._staging(img0.nbytes, 2 * max(self.batch_frames, 1))
+        self._frame_shape = tuple(img0.shape)
+        self._rgb_frames = set()
+        shape2, dtype = img0.shape[:2], img0.dtype
+
+        def load_into(i, view):
+            img = frames[i]
+            if img is not None and img.shape == img0.shape and img.dtype == dtype:
+                stage_frame(img, view)         # pageable -> pinned on a worker thread (numpy releases the GIL)
+            return img
+
+        def on_frame(_i, img):
+            self._validate(img, shape2, dtype)
+
         try:
-            for i, img in enumerate(frames):
-                self._validate(img, img0.shape[:2], img0.dtype)
-                self._push(i, img, ring)
+            self._stream(len(frames), load_into, ring, on_frame)
             return self._finish(len(frames), img0.shape[:2])
         except BaseException:
             if self._h is not None:

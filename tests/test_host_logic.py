@@ -31,15 +31,19 @@ def stubbed(monkeypatch):
     def ensure(self, shape, dtype, n, resident=False):
         self._h = None
 
-    def push(self, i, img, ring):
-        pushed.append((i, img.copy()))
+    def push_slot(self, i, slot):
+        # what the upload would read from the pinned slot the worker thread staged the frame in
+        n = int(np.prod(self._frame_shape)) * np.dtype(self.dtype).itemsize
+        pushed.append((i, slot[1][:n].view(self.dtype).reshape(self._frame_shape).copy()))
 
     def finish(self, n, shape):
         return np.zeros((shape[0], shape[1], 3), self.dtype)
 
     monkeypatch.setattr(PyramidStack, "_ensure_handle", ensure)
-    monkeypatch.setattr(PyramidStack, "_staging", lambda self, nbytes, count: [])
-    monkeypatch.setattr(PyramidStack, "_push", push)
+    monkeypatch.setattr(PyramidStack, "_staging",
+                        lambda self, nbytes, count: [(None, np.zeros(nbytes, np.uint8)) for _ in range(4)])
+    monkeypatch.setattr(PyramidStack, "_push_slot", push_slot)
+    monkeypatch.setattr(PyramidStack, "_sync_copies", lambda self: None)
     monkeypatch.setattr(PyramidStack, "_finish", finish)
     return pushed
 

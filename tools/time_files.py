@@ -14,7 +14,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def measure(host, steps=2, threads=4):
+def measure(host, steps=2, threads=6):
     import cv2
     from shinestacker_b200 import PyramidStack, fastio
     need = int(sum(f.nbytes for f in host) * 1.1) + (64 << 20)
@@ -54,6 +54,19 @@ def measure(host, steps=2, threads=4):
             res[label] = {"ms_per_stack": t * 1e3, "mp_per_s": n * h * w / 1e6 / t}
         fastio.ENABLED = True
         res["same_result"] = bool(np.array_equal(outs["mapped_tiff"], outs["cv2_imread"]))
+        # the in-memory entry point: pageable numpy frames -> fused image (worker threads stage them into pinned memory)
+        algo = PyramidStack(decode_threads=threads)
+        frames = [np.array(f) for f in host]
+        algo.focus_stack_arrays(frames)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            out = algo.focus_stack_arrays(frames)
+            ts.append(time.perf_counter() - t0)
+        algo.close()
+        t = float(np.median(ts))
+        res["arrays"] = {"ms_per_stack": t * 1e3, "mp_per_s": n * h * w / 1e6 / t,
+                         "same_result": bool(np.array_equal(out, outs["mapped_tiff"]))}
         return res
     finally:
         shutil.rmtree(d, ignore_errors=True)
@@ -62,4 +75,5 @@ def measure(host, steps=2, threads=4):
 if __name__ == "__main__":
     from shinestacker_b200 import synthetic
     n, h, w = (int(v) for v in (sys.argv[1:4] + [16, 1536, 2048][len(sys.argv) - 1:])[:3])
-    print(json.dumps(measure(synthetic.make_stack(n, h, w, np.uint8, seed=2))))
+    thr = int(sys.argv[4]) if len(sys.argv) > 4 else 6
+    print(json.dumps(measure(synthetic.make_stack(n, h, w, np.uint8, seed=2), steps=3, threads=thr)))

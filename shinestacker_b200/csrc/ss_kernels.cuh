@@ -657,12 +657,8 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
 #ifndef SS_HOST_EMU
     uint64_t *mbar = (uint64_t *)(smem + SS_SMEM_FLOATS);
     unsigned mbar_phase = 0;
-    if ((interior && sizeof(InT) == 1) || pref32) {
-        if (threadIdx.x == 0) {
-            ss_mbar_init(mbar, 1);
-        }
-        __syncthreads();
-    }
+    if (threadIdx.x == 0) ss_mbar_init(mbar, 1);   // (only the TMA / bulk-copy paths wait on it)
+    __syncthreads();
     if (pref32) {
         ss_s0_bulk_f32(p, (const char *)p.in + (long long)f_begin * p.in_frame_stride, x0, y0, threadIdx.x, P0, mbar);
         ss_mbar_wait(mbar, mbar_phase);

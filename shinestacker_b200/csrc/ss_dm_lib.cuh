@@ -146,6 +146,34 @@ struct DmCudaBackend {
         memcpy(host_sums, h_pinned, sizeof(double) * n_d);
         return 0;
     }
+    // All iterations of one pyramid level on the device (cooperative launch; no host round trip).  d_bar: one
+    // unsigned int behind the state, the grid barrier's counter.
+    int ecc_run_level(const EccLevelArgs &g, EccState *d_state, double *d_sums, unsigned int *d_bar)
+    {
+        static int n_sm = 0, per_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            DM_CUDA(cudaGetDevice(&dev));
+            DM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecc_level_kernel, 256, 0));
+            if (per_sm > 4) per_sm = 4;
+            if (per_sm < 1) per_sm = 1;
+        }
+        const long long n = (long long)g.h * g.w;
+        long long blocks = (n + 255) / 256;
+        if (blocks > (long long)per_sm * n_sm) blocks = (long long)per_sm * n_sm;
+        DM_CUDA(cudaMemsetAsync(d_bar, 0, sizeof(unsigned int), s_comp));
+        void *args[] = {(void *)&g, (void *)&d_state, (void *)&d_sums, (void *)&d_bar};
+        DM_CUDA(cudaLaunchCooperativeKernel((const void *)ecc_level_kernel, dim3((unsigned)blocks), dim3(256), args, 0, s_comp));
+        ++launches;
+        return 0;
+    }
+    int upload_async(void *dst, const void *src, size_t bytes)
+    {
+        DM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s_comp));
+        DM_CUDA(cudaStreamSynchronize(s_comp));      // src is caller stack memory
+        return 0;
+    }
     int elapsed_ms(float *ms)
     {
         *ms = 0.f;

@@ -40,6 +40,26 @@ struct DmHostBackend {
         }
         return 0;
     }
+    int ecc_run_level(const EccLevelArgs &g, EccState *st, double *, unsigned int *)
+    {
+        if (st->fail) return 0;
+        ecc_level_begin(g, *st);
+        while (!st->done) {
+            const EccParams p = ecc_params_of(g, *st);
+            double S[ECC_NSUMS];
+            for (int i = 0; i < ECC_NSUMS; ++i) S[i] = 0;
+            float s[ECC_NSUMS];
+            for (int y = 0; y < p.h; ++y)
+                for (int x = 0; x < p.w; ++x)
+                    if (ecc_pixel(p, x, y, s))
+                        for (int i = 0; i < ECC_NSUMS; ++i) S[i] += s[i];
+            ++launches;
+            ecc_update(g, *st, S);
+        }
+        if (!st->fail) ecc_level_end(g, *st);
+        return 0;
+    }
+    int upload_async(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
 #endif
     int zero(void *p, size_t bytes) { memset(p, 0, bytes); return 0; }
     template <class K>

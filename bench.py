@@ -392,14 +392,19 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
-        traffic = None
+        traffic, traffic_src = None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of one level-0 launch (ncu --set full, profiles/)
-            txt = open(os.path.join(ROOT, "profiles", "r1_final_level0_summary.txt")).read().split()
+            prof = os.path.join("profiles", "r2_level0_summary.txt")
+            txt = open(os.path.join(ROOT, prof)).read().split()
             def _val(key):
                 i = txt.index(key)
                 return float(txt[i + 1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[txt[i + 2]]
-            if N == 64 and H == 3072 and W == 4096 and dtype == np.uint8 and world == 1:
-                traffic = _val("dram__bytes_read.sum") + _val("dram__bytes_write.sum")
+            if H == 3072 and W == 4096 and dtype == np.uint8:
+                # the capture is the 64-frame launch of config 2; the traffic of a launch is proportional to its frames
+                # (inputs read once, g_1 planes written once per frame; the state is a few % of it)
+                traffic = (_val("dram__bytes_read.sum") + _val("dram__bytes_write.sum")) * n_local / 64.0
+                traffic_src = f"{prof} (ncu --set full, one 64-frame launch" + \
+                              (")" if n_local == 64 else f"; scaled to the {n_local} frames of this launch)")
         except (OSError, ValueError, KeyError):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -432,8 +437,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "ss_level_kernel (level 0: reduce + expand/Laplacian + "
                                                    "energy + arg-max select, all frames of the launch)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": "profiles/r1_final_level0_summary.txt (ncu --set full, "
-                         "one launch)" if traffic else None, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_launch,
+                         "traffic": traffic, "traffic_source": traffic_src, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_launch,
                          "peak_source": peak_src},
         }
         # the bound that actually limits this kernel: bit-exact sequential FP32 chains.

@@ -1,5 +1,5 @@
 """The JSON-line contract of bench.py, checked without a GPU: the reference arm (the unmodified reference from
-baseline/_ref when it is installed, else the CPU oracle port) really runs here on a tiny sample, and the committed line of the last GPU run (profiles/r1_final2_bench.json) carries every key
+baseline/_ref when it is installed, else the CPU oracle port) really runs here on a tiny sample, and the committed line of the last GPU run (profiles/r2_final_bench.json) carries every key
 the driver reads."""
 import json
 import os
@@ -47,7 +47,7 @@ def test_reference_arm_is_silent_on_other_ranks():
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    path = os.path.join(ROOT, "profiles", "r1_final2_bench.json")
+    path = os.path.join(ROOT, "profiles", "r2_final_bench.json")
     if not os.path.isfile(path):
         pytest.skip("no committed bench line")
     d = json.loads(open(path).read())

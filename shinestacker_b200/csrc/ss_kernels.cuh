@@ -92,6 +92,16 @@ SS_DEV void ss_tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t
                  ::"r"(ss_saddr(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(ss_saddr(bar))
                  : "memory");
 }
+// The same box only as far as L2 (no shared memory involved): issued one frame ahead of the real load, which then
+// finds its bytes in L2 instead of waiting for HBM.
+SS_DEV void ss_tma_prefetch_2d(const void *tmap, int c0, int c1)
+{
+#ifndef SS_NO_PREFETCH
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+#else
+    (void)tmap; (void)c0; (void)c1;
+#endif
+}
 // 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
 SS_DEV void ss_bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar)
 {
@@ -665,8 +675,11 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
         mbar_phase ^= 1;
     }
     if (interior && sizeof(InT) == 1) {
-        if (threadIdx.x == 0)
+        if (threadIdx.x == 0) {
             ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + f_begin * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
+            if (f_begin + 1 < f_end)
+                ss_tma_prefetch_2d(tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + (f_begin + 1) * p.h + y0 - SS_P0Y);
+        }
         ss_mbar_wait(mbar, mbar_phase);
         mbar_phase ^= 1;
         ss_s0_owner_u8(P0, threadIdx.x, (const char *)P1);
@@ -1033,8 +1046,11 @@ void ss_level_tile(const SsLevelParams &p, const void *tmap, int tile_x, int til
             if (pref32 && f + 1 < f_end)   // P0 is not read any more in this frame
                 ss_s0_bulk_f32(p, frame + p.in_frame_stride, x0, y0, tid, P0, mbar);
 #ifndef SS_HOST_EMU
-            if (s0_owner && f + 1 < f_end && tid == 0)   // P1 is dead until the next S1: raw bytes of the next frame
+            if (s0_owner && f + 1 < f_end && tid == 0) {   // P1 is dead until the next S1: raw bytes of the next frame
                 ss_tma_load_2d(P1, tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + (f + 1) * p.h + y0 - SS_P0Y, mbar, SS_P0H * SS_RAWS);
+                if (f + 2 < f_end)                         // ... and the one after it as far as L2
+                    ss_tma_prefetch_2d(tmap, 8 + (x0 - SS_P0X) * 3, p.tma_row0 + (f + 2) * p.h + y0 - SS_P0Y);
+            }
 #endif
             bool skip = false;
             if (skip_on && !first_frame) {

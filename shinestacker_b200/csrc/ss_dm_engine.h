@@ -13,6 +13,7 @@
 
 #include "ss_dm_kernels.cuh"
 
+#define DM_BLEND_BATCH_MAX 8
 enum { DM_OK = 0, DM_ERR_INVALID_OPTION = -1, DM_ERR_CUDA = -4, DM_ERR_STATE = -6, DM_ERR_NOMEM = -7 };
 
 struct DmOptions {          // DepthMapStack.__init__ (depth_map.py:11-26) + frame geometry
@@ -89,6 +90,9 @@ struct DmEngine {
     DmTaps t_blur, t_a, t_b;
     int bil_r = 0;
     float gmax = 0.f;
+    int batch = DM_BLEND_BATCH_MAX, launched_blend = 0;   // frames per blend launch (SSDM_BLEND_BATCH=1..8)
+    int fold_norm = 0, moments = 3, tiled_pyrdown = 1;
+    int fused_energy = 1;          // SSDM_ENERGY_FUSED=0: the four streaming passes instead of the tiled kernel
 
     int fail(int code, const char *msg) { snprintf(err, sizeof(err), "%s", msg); return code; }
 
@@ -118,6 +122,15 @@ struct DmEngine {
             k.assign(kd, kd + 3); t_a = dm_make_taps(k);
             k.assign(ks, ks + 3); t_b = dm_make_taps(k);
         }
+        const char *bb = getenv("SSDM_BLEND_BATCH");
+        batch = bb ? atoi(bb) : DM_BLEND_BATCH_MAX;
+        if (batch < 1) batch = 1;
+        if (batch > DM_BLEND_BATCH_MAX) batch = DM_BLEND_BATCH_MAX;
+        if (batch > o.max_frames) batch = o.max_frames;
+        const char *pt = getenv("SSDM_PYRDOWN_TILED");
+        tiled_pyrdown = !(pt && pt[0] == '0');
+        const char *fe = getenv("SSDM_ENERGY_FUSED");
+        fused_energy = !(fe && fe[0] == '0');
         L = o.levels;
         lh.assign(L, 0); lw.assign(L, 0);
         lh[0] = h; lw[0] = w;
@@ -139,7 +152,7 @@ struct DmEngine {
         gp.assign(L, nullptr); acc.assign(L, nullptr);
         for (int l = 0; l < L; ++l) {
             const size_t px = (size_t)lh[l] * lw[l];
-            if (l > 0 && (rc = be.alloc((void **)&gp[l], 4 * px * sizeof(float)))) return fail(rc, be.last_error());
+            if (l > 0 && (rc = be.alloc((void **)&gp[l], (size_t)batch * 4 * px * sizeof(float)))) return fail(rc, be.last_error());
             if ((rc = be.alloc((void **)&acc[l], 3 * px * sizeof(float)))) return fail(rc, be.last_error());
         }
         if (o.smooth_size > 0) {
@@ -177,12 +190,38 @@ struct DmEngine {
     {
         int rc = be.sync();
         if (rc) return fail(rc, be.last_error());
-        n = 0; finished = 0; blended = 0; collapsed = 0; weights = nullptr; gmax = 0.f;
+        n = 0; finished = 0; blended = 0; launched_blend = 0; collapsed = 0; weights = nullptr; gmax = 0.f;
         be.reset_counters();
         std::vector<unsigned> init(2 * (size_t)o.max_frames * DM_STAT_SLOTS);
         for (size_t i = 0; i < init.size(); i += 2) { init[i] = 0x7f800000u; init[i + 1] = 0u; }  // min = +inf, max = 0
         if ((rc = be.upload_small(d_slots, init.data(), init.size() * sizeof(unsigned)))) return fail(rc, be.last_error());
         return DM_OK;
+    }
+
+    template <typename InT, int RB, int RD>
+    int energy_tiles(const void *frame, float *e, unsigned *st)
+    {
+        DmEnergyTile<InT, RB, RD> k;
+        k.frame = frame; k.pitch = (long long)frame_pitch; k.h = h; k.w = w;
+        k.tblur = t_blur; k.ta = t_a; k.tb = t_b; k.sobel = o.energy; k.out = e; k.stats = st;
+        const int halo = t_blur.r + (t_a.r > t_b.r ? t_a.r : t_b.r);
+        k.pw = DM_ET_X + 2 * ((halo + 3) / 4 * 4); k.ph = DM_ET_Y + 2 * halo;
+        return be.launch_tiles(k, (w + DM_ET_X - 1) / DM_ET_X, (h + DM_ET_Y - 1) / DM_ET_Y, 1,
+                               sizeof(float) * DM_ET_FLOATS((size_t)k.pw, k.ph));
+    }
+
+    template <int KMAX>
+    int bilateral_tiles(float c1, float c2)
+    {
+        DmBilateralTile<KMAX> k;
+        k.in = d_energy; k.h = h; k.w = w; k.stats = d_stats; k.gmax = gmax; k.out = d_smooth;
+        double m0 = 0;
+        for (int d = 0; d < 8; ++d) k.g[d] = (float)exp(d * d * (-0.5 / (25.0 * 25.0)));
+        for (int i = -7; i <= 7; ++i)
+            for (int j = -7; j <= 7; ++j)
+                if (i * i + j * j <= 49) m0 += (double)k.g[abs(i)] * (double)k.g[abs(j)];
+        k.c1 = c1; k.c2 = c2; k.m0 = (float)m0; k.norm = gmax > 0.f ? gmax : 0.f;
+        return be.launch_tiles(k, (w + DM_BT_X - 1) / DM_BT_X, (h + DM_BT_Y - 1) / DM_BT_Y, n, sizeof(float) * DM_BT_FLOATS);
     }
 
     // pass 1 of one frame that already sits in slot i of the frame store
@@ -193,6 +232,12 @@ struct DmEngine {
         const void *frame = d_frames + (size_t)i * frame_bytes;
         float *e = d_energy + (size_t)i * plane;
         unsigned *st = d_slots + 2 * DM_STAT_SLOTS * (size_t)i;
+        if (fused_energy) {     // one tiled kernel (default); the four-pass form below is its cross-check
+            const int rb = t_blur.r, rd = t_a.r > t_b.r ? t_a.r : t_b.r;
+            if (rb == 2 && rd == 2) return energy_tiles<InT, 2, 2>(frame, e, st);
+            if (rb == 0 && rd == 1) return energy_tiles<InT, 0, 1>(frame, e, st);
+            return energy_tiles<InT, -1, -1>(frame, e, st);
+        }
         if (o.energy == 0) {
             DmGrayRowFilter<InT> a{frame, (long long)frame_pitch, h, w, t_blur, d_t1};
             if ((rc = be.launch(a, w, h, 1))) return rc;
@@ -246,19 +291,28 @@ struct DmEngine {
         }
         if ((rc = be.upload_small(d_stats, st.data(), st.size() * sizeof(unsigned)))) return fail(rc, be.last_error());
         memcpy(&gmax, &mx, 4);
-        if (gmax > 0.f) {
+        const char *pair_env = getenv("SSDM_BILATERAL_PAIR");     // A/B knob: "1" / "0" = the direct kernels
+        const char *mom_env = getenv("SSDM_BILATERAL_MOMENTS");
+        moments = mom_env && atoi(mom_env) == 5 ? 5 : 3;
+        // the tiled bilateral divides by the global maximum as it loads: no normalisation pass, d_energy stays raw
+        fold_norm = o.smooth_size > 0 && bil_r == 7 && !pair_env;
+        if (gmax > 0.f && !fold_norm) {
             DmNormalize k{d_energy, h, w, gmax};
             if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());
         }
         weights = d_energy;
         if (o.smooth_size > 0) {
             const float gc = (float)(-0.5 / (25.0 * 25.0)), c1 = gc, c2 = 0.5f * gc * gc;
-            const char *pair_env = getenv("SSDM_BILATERAL_PAIR");     // A/B knob (default: two pixels per thread)
             if (bil_r == 7 && pair_env && pair_env[0] == '0') {
                 DmBilateralSingle<7> k;
                 k.in = d_energy; k.h = h; k.w = w; k.stats = d_stats; k.gmax = gmax; k.out = d_smooth;
                 for (int i = 0; i < 225; ++i) { k.s0[i] = h_sw[i]; k.s1[i] = h_sw[i] * c1; k.s2[i] = h_sw[i] * c2; }
                 if ((rc = be.launch(k, w, h, n))) return fail(rc, be.last_error());
+            } else if (fold_norm) {
+                // default: tiled kernel in moment form (SSDM_BILATERAL_PAIR=1 / 0 select the direct 149-tap kernels),
+                // three moments (SSDM_BILATERAL_MOMENTS=5: the full colour polynomial)
+                rc = moments == 5 ? bilateral_tiles<5>(c1, c2) : bilateral_tiles<3>(c1, 0.f);
+                if (rc) return fail(rc, be.last_error());
             } else if (bil_r == 7) {
                 DmBilateralFixed<7> k;
                 k.in = d_energy; k.h = h; k.w = w; k.stats = d_stats; k.gmax = gmax; k.out = d_smooth;
@@ -273,47 +327,66 @@ struct DmEngine {
         DmFocusMap f{weights, h, w, n, o.map_type, (float)o.temperature};
         if ((rc = be.launch(f, w, h, 1))) return fail(rc, be.last_error());
         finished = 1;
-        blended = 0;
+        blended = 0; launched_blend = 0;
         return DM_OK;
     }
 
+    // pass 2 of the nb frames i0 .. i0 + nb - 1: Gaussian pyramids of the batch (one launch per level, z = frame),
+    // then one blend launch per level that adds the nb weighted Laplacians in stack order
     template <typename InT>
-    int blend_frame_t(int i)
+    int blend_batch_t(int i0, int nb)
     {
         int rc;
-        DmLevelSrc<InT> s0{d_frames + (size_t)i * frame_bytes, (long long)frame_pitch, nullptr,
-                           weights + (size_t)i * plane, h, w};
-        const int first = blended == 0;
-        if (L > 1) {
-            DmPyrDown<InT> d0{s0, lh[1], lw[1], gp[1]};
-            if ((rc = be.launch(d0, lw[1], lh[1], 1))) return rc;
+        DmLevelSrc<InT> s0{d_frames + (size_t)i0 * frame_bytes, (long long)frame_pitch, nullptr,
+                           weights + (size_t)i0 * plane, h, w, (long long)frame_bytes, 0, plane};
+        const int first = i0 == 0;
+        auto px = [&](int l) { return (long long)lh[l] * lw[l]; };
+        auto level = [&](int l) {
+            return DmLevelSrc<float>{nullptr, 0, gp[l], gp[l] + 3 * px(l), lh[l], lw[l], 0, 4 * px(l), 4 * px(l)};
+        };
+        auto tiles = [](int v, int t) { return (v + t - 1) / t; };
+        if (L > 1 && tiled_pyrdown) {
+            DmPyrDownTile<InT> d0{s0, lh[1], lw[1], gp[1], 4 * px(1)};
+            if ((rc = be.launch_tiles(d0, tiles(lw[1], DM_PD_X), tiles(lh[1], DM_PD_Y), nb, sizeof(float) * DM_PD_FLOATS))) return rc;
+        } else if (L > 1) {
+            DmPyrDown<InT> d0{s0, lh[1], lw[1], gp[1], 4 * px(1)};
+            if ((rc = be.launch(d0, lw[1], lh[1], nb))) return rc;
         }
         for (int l = 1; l + 1 < L; ++l) {
-            DmLevelSrc<float> s{nullptr, 0, gp[l], gp[l] + 3 * (size_t)lh[l] * lw[l], lh[l], lw[l]};
-            DmPyrDown<float> d{s, lh[l + 1], lw[l + 1], gp[l + 1]};
-            if ((rc = be.launch(d, lw[l + 1], lh[l + 1], 1))) return rc;
+            if (tiled_pyrdown) {
+                DmPyrDownTile<float> d{level(l), lh[l + 1], lw[l + 1], gp[l + 1], 4 * px(l + 1)};
+                if ((rc = be.launch_tiles(d, tiles(lw[l + 1], DM_PD_X), tiles(lh[l + 1], DM_PD_Y), nb, sizeof(float) * DM_PD_FLOATS))) return rc;
+            } else {
+                DmPyrDown<float> d{level(l), lh[l + 1], lw[l + 1], gp[l + 1], 4 * px(l + 1)};
+                if ((rc = be.launch(d, lw[l + 1], lh[l + 1], nb))) return rc;
+            }
         }
         {
-            DmBlendLevel<InT> b{s0, L > 1 ? gp[1] : nullptr, L > 1 ? lh[1] : 0, L > 1 ? lw[1] : 0, acc[0], first};
-            if ((rc = be.launch(b, w, h, 1))) return rc;
+            DmBlendLevel<InT> b{s0, L > 1 ? gp[1] : nullptr, L > 1 ? lh[1] : 0, L > 1 ? lw[1] : 0, L > 1 ? 4 * px(1) : 0,
+                                acc[0], first, nb};
+            if ((rc = be.launch(b, (w + 1) / 2, (h + 1) / 2, 1))) return rc;
         }
         for (int l = 1; l < L; ++l) {
-            DmLevelSrc<float> s{nullptr, 0, gp[l], gp[l] + 3 * (size_t)lh[l] * lw[l], lh[l], lw[l]};
             const bool top = l == L - 1;
-            DmBlendLevel<float> b{s, top ? nullptr : gp[l + 1], top ? 0 : lh[l + 1], top ? 0 : lw[l + 1], acc[l], first};
-            if ((rc = be.launch(b, lw[l], lh[l], 1))) return rc;
+            DmBlendLevel<float> b{level(l), top ? nullptr : gp[l + 1], top ? 0 : lh[l + 1], top ? 0 : lw[l + 1],
+                                  top ? 0 : 4 * px(l + 1), acc[l], first, nb};
+            if ((rc = be.launch(b, (lw[l] + 1) / 2, (lh[l] + 1) / 2, 1))) return rc;
         }
         return DM_OK;
     }
 
-    // replaces one iteration of the second loop of focus_stack (depth_map.py:94-115); frames in stack order
+    // replaces one iteration of the second loop of focus_stack (depth_map.py:94-115); frames in stack order.
+    // Frames are collected into batches of `batch` (the last one may be shorter) and launched together.
     int blend_frame(int i)
     {
         if (!finished) return fail(DM_ERR_STATE, "blend before finish_begin");
         if (i != blended || i >= n) return fail(DM_ERR_STATE, "frames must be blended once, in stack order");
-        const int rc = bps == 1 ? blend_frame_t<uint8_t>(i) : blend_frame_t<uint16_t>(i);
-        if (rc) return fail(rc, be.last_error());
         ++blended;
+        if (blended - launched_blend < batch && blended < n) return DM_OK;
+        const int i0 = launched_blend, nb = blended - launched_blend;
+        const int rc = bps == 1 ? blend_batch_t<uint8_t>(i0, nb) : blend_batch_t<uint16_t>(i0, nb);
+        if (rc) return fail(rc, be.last_error());
+        launched_blend = blended;
         return DM_OK;
     }
 
@@ -373,6 +446,9 @@ struct DmEngine {
         else if (what == 1 && finished) src = weights;
         if (!src) return fail(DM_ERR_STATE, "plane not available in this state");
         const int rc = be.download(out, src + (size_t)frame * plane, plane * sizeof(float));
-        return rc ? fail(rc, be.last_error()) : DM_OK;
+        if (rc) return fail(rc, be.last_error());
+        if (what == 0 && fold_norm && gmax > 0.f)       // the normalisation lives in the bilateral's patch load
+            for (long long i = 0; i < plane; ++i) out[i] = out[i] / gmax;
+        return DM_OK;
     }
 };

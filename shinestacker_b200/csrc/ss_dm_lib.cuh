@@ -96,6 +96,19 @@ struct DmCudaBackend {
         ++launches;
         return 0;
     }
+    template <class K>
+    int launch_tiles(const K &k, int tiles_x, int tiles_y, int z, size_t smem_bytes)
+    {
+        static size_t opted = 0;            // per instantiation: largest dynamic shared memory opted in so far
+        if (smem_bytes > 48 * 1024 && smem_bytes > opted) {
+            DM_CUDA(cudaFuncSetAttribute(dm_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            opted = smem_bytes;
+        }
+        dm_tile_kernel<K><<<dim3(tiles_x, tiles_y, z), 256, smem_bytes, s_comp>>>(k);
+        DM_CUDA(cudaGetLastError());
+        ++launches;
+        return 0;
+    }
     int zero(void *p, size_t bytes) { DM_CUDA(cudaMemsetAsync(p, 0, bytes, s_comp)); return 0; }
     // one warp per item of a device-side list whose length sits in device memory (persistent grid)
     template <class K>

@@ -56,7 +56,7 @@ class Emu:
             src = os.path.join(HERE, "emu", "emu_depthmap.cpp")
             so = os.path.join(HERE, "emu", "libemu_depthmap.so")
             csrc = os.path.join(HERE, "..", "shinestacker_b200", "csrc")
-            deps = [src] + [os.path.join(csrc, f) for f in ("ss_dm_kernels.cuh", "ss_dm_engine.h", "ss_kernels.cuh")]
+            deps = [src] + [os.path.join(csrc, f) for f in ("ss_dm_kernels.cuh", "ss_dm_engine.h", "ss_kernels.cuh")] + [os.path.join(HERE, "emu", "emu_backend.h")]
             if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
                 subprocess.run(["g++", "-std=c++17", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC",
                                 "-o", so, src], check=True)

@@ -117,7 +117,7 @@ def test_engine_state_machine_and_reuse():
     first = out.copy()
     # whole chain again over the resident frames (bench path), then a different, shorter stack on the same handle
     assert lib.emu_dm_rerun(e.p) == 0
-    assert lib.emu_dm_launches(e.p) == 3 * 4 + 3 + 3 * 5 + 3
+    assert lib.emu_dm_launches(e.p) == 3 * 1 + 2 + 5 + 3     # energy: one tiled kernel per frame; bilateral (normalising) + focus map; blend: one batch
     out2 = np.empty_like(out)
     assert lib.emu_dm_finish_end(e.p, out2.ctypes.data, out2.strides[0]) == 0  # second call: download only
     assert np.array_equal(out2, first)
@@ -197,3 +197,74 @@ def test_randomised_options_host_build_vs_oracle():
         du.assert_within_1lsb(out, ref, f"case {t} {kwargs}", max_frac=0.2)
         assert np.array_equal(st["energy"], ost["energy"]), (t, kwargs)
         assert np.abs(st["weights"] - ost["weights"]).max() < 5e-6, (t, kwargs)
+
+
+@pytest.mark.parametrize("h,w,dtype,kwargs", [
+    (70, 150, np.uint8, {}),                                           # several 64 x 32 tiles, ragged last ones
+    (33, 65, np.uint16, {}),                                           # one pixel into the second tile row / column
+    (32, 64, np.uint8, {"energy": "sobel"}),                           # exactly one tile
+    (97, 131, np.uint8, {"kernel_size": 9, "blur_size": 11}),          # generic radii (halo 9 > tile edge reflections)
+    (5, 7, np.uint8, {"kernel_size": 7, "blur_size": 7}),              # image smaller than the halo: multiple reflections
+    (40, 200, np.uint16, {"energy": "sobel"}),
+    (66, 34, np.uint8, {"blur_size": 1}),                              # laplacian without blur
+    (100, 200, np.uint8, {}),                                          # interior tiles: the four-pixel path, uint8
+    (104, 204, np.uint16, {}),                                         # ... uint16
+    (100, 200, np.uint8, {"energy": "sobel"}),                         # ... without blur stages
+    (100, 200, np.uint16, {"blur_size": 3}),                           # radii (1, 2): the generic instantiation
+    (100, 202, np.uint8, {}),                                          # width not a multiple of 4: scalar path only
+])
+def test_tiled_energy_kernel_equals_the_four_streaming_passes(h, w, dtype, kwargs, monkeypatch):
+    frames = synthetic.make_noise_stack(2, h, w, np.dtype(dtype), h + w)
+    planes = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SSDM_ENERGY_FUSED", fused)
+        e = du.Emu(h, w, dtype, 2, **kwargs)
+        for f in frames:
+            assert e.push(f) == 0, e.error()
+        planes.append(np.array([e.plane("energy", i) for i in range(2)]))
+        launches = e.lib_.emu_dm_launches(e.p)
+        assert launches == (2 if fused == "1" else 2 * (3 if kwargs.get("energy") == "sobel" else 4))
+        e.close()
+    assert np.isfinite(planes[0]).all()
+    assert np.array_equal(planes[0], planes[1])
+    ref = dmo.focus_stack(frames, return_stages=True, **kwargs)[1]["energy"]
+    assert np.array_equal(planes[0], ref)
+
+
+@pytest.mark.parametrize("dtype,levels", [(np.uint8, 3), (np.uint16, 4), (np.uint8, 1)])
+def test_blend_batches_equal_frame_by_frame_blending(dtype, levels, monkeypatch):
+    frames = synthetic.make_stack(5, 45, 70, np.dtype(dtype), seed=9)
+    outs = []
+    for batch in ("1", "2", "8"):
+        monkeypatch.setenv("SSDM_BLEND_BATCH", batch)
+        outs.append(du.emu_focus_stack(frames, levels=levels))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    du.assert_within_1lsb(outs[0], dmo.focus_stack(frames, levels=levels), "batched blend", max_frac=0.2)
+
+
+@pytest.mark.parametrize("dtype,h,w,levels", [(np.uint16, 75, 140, 3), (np.uint8, 33, 65, 4), (np.uint16, 64, 128, 2),
+                                              (np.uint8, 7, 9, 3)])
+def test_tiled_pyrdown_equals_the_per_pixel_kernel(dtype, h, w, levels, monkeypatch):
+    frames = synthetic.make_noise_stack(3, h, w, np.dtype(dtype), h * w)
+    outs = []
+    for tiled in ("1", "0"):
+        monkeypatch.setenv("SSDM_PYRDOWN_TILED", tiled)
+        outs.append(du.emu_focus_stack(frames, levels=levels))
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_bilateral_forms_agree_with_the_oracle(monkeypatch):
+    # default: tiled, three moments, normalisation folded into the load; SSDM_BILATERAL_MOMENTS=5: full polynomial;
+    # SSDM_BILATERAL_PAIR=1: the direct 149-tap kernel after a separate normalisation pass
+    frames = synthetic.make_stack(4, 90, 140, np.dtype(np.uint16), seed=5)
+    frames[1] = synthetic.make_noise_stack(1, 90, 140, np.dtype(np.uint16), 3)[0]     # large neighbour differences
+    ref, ost = dmo.focus_stack(frames, return_stages=True)
+    for env in ({}, {"SSDM_BILATERAL_MOMENTS": "5"}, {"SSDM_BILATERAL_PAIR": "1"}):
+        for k in ("SSDM_BILATERAL_MOMENTS", "SSDM_BILATERAL_PAIR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        st = {}
+        out = du.emu_focus_stack(frames, stages=st)
+        assert np.abs(st["weights"] - ost["weights"]).max() < 1e-6, env
+        du.assert_within_1lsb(out, ref, str(env), max_frac=0.2)

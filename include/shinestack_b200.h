@@ -79,6 +79,8 @@ int ss_level_size(const ss_handle *h, int level, int32_t *height, int32_t *width
 /* Pinned host staging memory for callers that want zero-copy-speed uploads (optional). */
 int ss_host_alloc(void **ptr, size_t bytes);
 int ss_host_free(void *ptr);
+/* 1 when ptr lies in page-locked host memory known to CUDA (uploads from it are asynchronous), else 0. */
+int ss_host_is_pinned(const void *ptr);
 
 /* Replaces one iteration of the second loop of focus_stack (pyramid.py:170-177: read_img +
  * process_single_image): hands one host frame to the device.  The copy is asynchronous; the frame

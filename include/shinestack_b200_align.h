@@ -63,7 +63,15 @@ int ssal_ecc_set_reference(ssal_handle *h, const void *ref_bgr, size_t pitch_byt
 int ssal_ecc_estimate(ssal_handle *h, const void *mov_bgr, size_t pitch_bytes, int finest_level, int max_iters,
                       double eps_px, const double *init_m, double *m_out, double *info);
 
-/* Device address and row pitch of the last aligned frame (valid until the next ssal_warp on this handle). */
+/* Pipelining of a frame sequence (the reference processes the frames of AlignFrames one by one,
+ * stack_framework.py:246-302; here the upload of frame i+1 hides behind the fit and warp of frame i):
+ * ssal_prefetch starts the asynchronous upload of the NEXT frame (page-locked host memory) into a second source
+ * buffer; ssal_use_prefetched makes it the current frame, which ssal_ecc_estimate / ssal_warp then take with a NULL
+ * source pointer.  At most one prefetched frame can be outstanding. */
+int ssal_prefetch(ssal_handle *h, const void *next_bgr, size_t pitch_bytes);
+int ssal_use_prefetched(ssal_handle *h);
+
+/* Device address and row pitch of the last aligned frame (outputs are double-buffered: valid until the SECOND next ssal_warp on this handle). */
 int ssal_result_device(ssal_handle *h, const void **d_bgr, size_t *pitch_bytes);
 /* Device time of the last warp (CUDA events around its kernels) and kernels launched so far. */
 int ssal_kernel_time_ms(ssal_handle *h, float *ms);

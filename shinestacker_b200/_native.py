@@ -78,6 +78,7 @@ SIGNATURES = {
     "ss_level_size": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "ss_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
     "ss_host_free": (_i, [_vp]),
+    "ss_host_is_pinned": (_i, [_vp]),
     "ss_push_frame": (_i, [_vp, _vp, _sz]),
     "ss_push_frame_device": (_i, [_vp, _vp, _sz]),
     "ss_push_frame_rgb": (_i, [_vp, _vp, _sz]),
@@ -144,6 +145,8 @@ SIGNATURES_ALIGN = {
     "ssal_warp_device": (_i, [_vp, _vp, _sz, _dp, _i, _i, _dp, _ip, _i, _vp, _sz]),
     "ssal_ecc_set_reference": (_i, [_vp, _vp, _sz]),
     "ssal_ecc_estimate": (_i, [_vp, _vp, _sz, _i, _i, ctypes.c_double, _dp, _dp, _dp]),
+    "ssal_prefetch": (_i, [_vp, _vp, _sz]),
+    "ssal_use_prefetched": (_i, [_vp]),
     "ssal_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ssal_kernel_time_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "ssal_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),

@@ -273,13 +273,15 @@ class Warper:
         """Forward 2x3 similarity (moving -> reference frame, like cv2.estimateAffinePartial2D) of ``img`` by
         ECC iterations on the GPU; returns ``(m, info)`` with info = dict(rho, iterations, overlap, last_step).
         The frame stays on the device: ``warp(None, m, ...)`` then warps it without a second upload."""
-        self._check_frame(img)
-        img = np.ascontiguousarray(img)
+        if img is not None:     # None: the frame made current by use_prefetched()
+            self._check_frame(img)
+            img = np.ascontiguousarray(img)
         m = np.zeros(6, np.float64)
         info = np.zeros(4, np.float64)
         init = None if init_m is None else np.ascontiguousarray(np.asarray(init_m, np.float64).reshape(6))
         dp = ctypes.POINTER(ctypes.c_double)
-        _check(self._lib.ssal_ecc_estimate(self._h, img.ctypes.data_as(ctypes.c_void_p), img.strides[0],
+        _check(self._lib.ssal_ecc_estimate(self._h, img.ctypes.data_as(ctypes.c_void_p) if img is not None else None,
+                                           img.strides[0] if img is not None else 0,
                                            int(finest_level), int(max_iters), float(eps_px),
                                            init.ctypes.data_as(dp) if init is not None else None,
                                            m.ctypes.data_as(dp), info.ctypes.data_as(dp)))
@@ -287,6 +289,18 @@ class Warper:
         _check(self._lib.ssal_kernel_time_ms(self._h, ctypes.byref(ms)))
         self.last_kernel_ms = ms.value
         return m.reshape(2, 3), dict(rho=info[0], iterations=int(info[1]), overlap=info[2], last_step=info[3])
+
+    def prefetch(self, img):
+        """Starts the upload of the NEXT frame (``img``: C-contiguous array in page-locked host memory, which the
+        caller keeps alive and unchanged until ``use_prefetched``) behind the work on the current one."""
+        self._check_frame(img)
+        if not img.flags.c_contiguous:
+            raise ValueError("prefetch needs a C-contiguous frame")
+        _check(self._lib.ssal_prefetch(self._h, img.ctypes.data_as(ctypes.c_void_p), img.strides[0]))
+
+    def use_prefetched(self):
+        """Makes the prefetched frame the current one: ``ecc_estimate(None)`` / ``warp(None, ...)`` then work on it."""
+        _check(self._lib.ssal_use_prefetched(self._h))
 
     def _check_frame(self, img):
         if img.shape[:2] != self.shape or img.ndim != 3 or img.shape[2] != 3:

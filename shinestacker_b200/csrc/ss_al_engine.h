@@ -15,7 +15,10 @@ struct AlEngine {
     Backend be;
     int h = 0, w = 0, bps = 0;
     size_t pitch = 0, frame_bytes = 0;
-    uint8_t *d_src = nullptr, *d_warp = nullptr, *d_out = nullptr;
+    uint8_t *d_src = nullptr, *d_next = nullptr;   // the frame being aligned / the frame uploading behind it (prefetch)
+    uint8_t *d_warp = nullptr, *d_out = nullptr;   // outputs of the current warp; d_warp_b / d_out_b: of the previous one
+    uint8_t *d_warp_b = nullptr, *d_out_b = nullptr;
+    bool next_pending = false;
     int *d_tab = nullptr, *d_fill = nullptr;      // d_fill[0] = number of pixels to fill, d_fill[1..] = their indices
     const uint8_t *result = nullptr;
     std::vector<int> tab;
@@ -35,8 +38,11 @@ struct AlEngine {
         frame_bytes = pitch * h;
         int rc;
         if ((rc = be.alloc((void **)&d_src, frame_bytes))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_next, frame_bytes))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_warp, frame_bytes))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_out, frame_bytes))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_warp_b, frame_bytes))) return fail(rc, be.last_error());
+        if ((rc = be.alloc((void **)&d_out_b, frame_bytes))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_fill, sizeof(int) * ((size_t)w * h + 1)))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_tab, sizeof(int) * 2 * ((size_t)w + h)))) return fail(rc, be.last_error());
         tab.resize(2 * ((size_t)w + h));
@@ -47,9 +53,9 @@ struct AlEngine {
     {
         be.sync();
         if (ecc_ready) { ecc.destroy(); ecc_ready = false; }
-        void *ptrs[] = {d_src, d_warp, d_out, d_fill, d_tab};
+        void *ptrs[] = {d_src, d_next, d_warp, d_out, d_warp_b, d_out_b, d_fill, d_tab};
         for (void *p : ptrs) if (p) be.free(p);
-        d_src = d_warp = d_out = nullptr; d_tab = d_fill = nullptr;
+        d_src = d_next = d_warp = d_out = d_warp_b = d_out_b = nullptr; d_tab = d_fill = nullptr;
     }
 
     template <typename T>
@@ -151,15 +157,41 @@ struct AlEngine {
     int ecc_estimate(const void *src, size_t spitch, int on_device, int finest_level, int max_iters, double eps_px,
                      const double *init_m, double *m_out, double *info)
     {
-        if (!src || !m_out) return fail(DM_ERR_INVALID_OPTION, "null argument");
-        if (spitch < pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
+        if ((!src && !src_valid) || !m_out) return fail(DM_ERR_INVALID_OPTION, "null argument");
+        if (src && spitch < pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
         int rc = ecc_prepare();
         if (rc) return rc;
         be.mark_start();
-        if ((rc = be.upload_frame(d_src, pitch, src, spitch, pitch, h, on_device))) return fail(rc, be.last_error());
-        src_valid = true;
+        if (src) {      // src == NULL: the frame made current by use_prefetched()
+            if ((rc = be.upload_frame(d_src, pitch, src, spitch, pitch, h, on_device))) return fail(rc, be.last_error());
+            src_valid = true;
+        }
         if ((rc = ecc.estimate(d_src, pitch, finest_level, max_iters, eps_px, init_m, m_out, info))) return fail(rc, ecc.err);
         be.mark_end();
+        return DM_OK;
+    }
+
+    // Pipelining (config 5): start the upload of the NEXT frame from pinned host memory into the second source
+    // buffer; it runs on the copy stream behind whatever the compute stream is doing (the ECC fit and the warp of
+    // the current frame).  use_prefetched() then makes it the current frame (ecc_estimate / warp with src = NULL).
+    int prefetch(const void *src, size_t spitch)
+    {
+        if (!src) return fail(DM_ERR_INVALID_OPTION, "null argument");
+        if (spitch < pitch) return fail(DM_ERR_INVALID_OPTION, "row pitch smaller than a row");
+        if (next_pending) return fail(DM_ERR_STATE, "a prefetched frame is waiting: call ssal_use_prefetched first");
+        const int rc = be.upload_frame_behind(d_next, pitch, src, spitch, pitch, h);
+        if (rc) return fail(rc, be.last_error());
+        next_pending = true;
+        return DM_OK;
+    }
+    int use_prefetched()
+    {
+        if (!next_pending) return fail(DM_ERR_STATE, "no prefetched frame");
+        uint8_t *t = d_src; d_src = d_next; d_next = t;
+        next_pending = false;
+        const int rc = be.wait_uploads();
+        if (rc) return fail(rc, be.last_error());
+        src_valid = true;
         return DM_OK;
     }
 
@@ -185,6 +217,8 @@ struct AlEngine {
             if (rc) return fail(rc, be.last_error());
             src_valid = true;
         }
+        // the previous result stays intact while this warp runs (its consumer may still be copying it)
+        { uint8_t *t = d_warp; d_warp = d_warp_b; d_warp_b = t; t = d_out; d_out = d_out_b; d_out_b = t; }
         rc = bps == 1 ? run<uint8_t>(m, transform, border_mode, bval, kernel, taps)
                       : run<uint16_t>(m, transform, border_mode, bval, kernel, taps);
         if (rc) return fail(rc, rc == DM_ERR_INVALID_OPTION ? "singular transform" : be.last_error());

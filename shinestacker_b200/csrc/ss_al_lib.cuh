@@ -83,6 +83,18 @@ SS_EXPORT int ssal_ecc_estimate(ssal_handle *h, const void *mov_bgr, size_t pitc
     const int rc = h->eng.ecc_estimate(mov_bgr, pitch, 0, finest_level, max_iters, eps_px, init_m, m_out, info);
     return rc ? ss_fail(rc, "%s", h->eng.err) : SS_OK;
 }
+SS_EXPORT int ssal_prefetch(ssal_handle *h, const void *next_bgr, size_t pitch)
+{
+    SSAL_ENTER(h);
+    const int rc = h->eng.prefetch(next_bgr, pitch);
+    return rc ? ss_fail(rc, "%s", h->eng.err) : SS_OK;
+}
+SS_EXPORT int ssal_use_prefetched(ssal_handle *h)
+{
+    SSAL_ENTER(h);
+    const int rc = h->eng.use_prefetched();
+    return rc ? ss_fail(rc, "%s", h->eng.err) : SS_OK;
+}
 SS_EXPORT int ssal_result_device(ssal_handle *h, const void **d_bgr, size_t *pitch)
 {
     if (!h || !d_bgr || !pitch) return ss_fail(SS_ERR_STATE, "null argument");

@@ -75,6 +75,14 @@ struct DmCudaBackend {
         DM_CUDA(cudaStreamWaitEvent(s_comp, ev_copied, 0));
         return 0;
     }
+    // host frame -> device on the copy stream WITHOUT making the compute stream wait; wait_uploads() adds the wait
+    int upload_frame_behind(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows)
+    {
+        DM_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, cudaMemcpyHostToDevice, s_copy));
+        DM_CUDA(cudaEventRecord(ev_copied, s_copy));
+        return 0;
+    }
+    int wait_uploads() { DM_CUDA(cudaStreamWaitEvent(s_comp, ev_copied, 0)); return 0; }
     int download(void *dst, const void *src, size_t bytes)
     {
         DM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s_comp));

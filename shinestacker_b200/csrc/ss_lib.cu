@@ -866,6 +866,13 @@ SS_EXPORT int ss_host_free(void *ptr)
     SS_CUDA(cudaFreeHost(ptr));
     return 0;
 }
+// 1 when ptr lies in page-locked host memory known to CUDA (asynchronous copies from it do not block), else 0
+SS_EXPORT int ss_host_is_pinned(const void *ptr)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
 
 // float-64 path: the chain of one frame (ss_f64.cuh).
 static int ss64_launch_frame(ss_handle *h, int f)

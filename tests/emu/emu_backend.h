@@ -18,6 +18,11 @@ struct DmHostBackend {
         for (int y = 0; y < rows; ++y) memcpy((char *)dst + y * dpitch, (const char *)src + y * spitch, row_bytes);
         return 0;
     }
+    int upload_frame_behind(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows)
+    {
+        return upload_frame(dst, dpitch, src, spitch, row_bytes, rows, 0);
+    }
+    int wait_uploads() { return 0; }
     int download(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
     int download2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, int rows)
     {

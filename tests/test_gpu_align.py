@@ -183,6 +183,82 @@ def test_fused_align_and_stack_pipeline_recovers_the_undisplaced_result():
     assert np.corrcoef(a, b)[0, 1] > 0.8
 
 
+def test_pipeline_gives_the_same_image_from_pageable_and_from_pinned_frames():
+    # pageable frames are staged by worker threads into a ring of pinned slots, pinned frames upload from where they
+    # are; both are prefetched one frame ahead (ssal_prefetch) -- same transforms, same image
+    import ctypes
+    from shinestacker_b200 import _native
+    from shinestacker_b200.pipeline import align_and_stack_arrays
+    from tools.time_pipeline import displaced_stack
+    lib = _native.load()
+    frames = synthetic.make_stack(11, 300, 400, np.uint8, 29)
+    moved, _, _ = displaced_stack(frames)
+    pin_moved, _, pin = displaced_stack(frames, lib)
+    assert lib.ss_host_is_pinned(ctypes.c_void_p(pin_moved[0].ctypes.data)) == 1
+    assert lib.ss_host_is_pinned(ctypes.c_void_p(moved[0].ctypes.data)) == 0
+    try:
+        a, ma = align_and_stack_arrays(list(moved), return_transforms=True)
+        b, mb = align_and_stack_arrays(list(pin_moved), return_transforms=True)
+        c, mc = align_and_stack_arrays(list(moved), ref_idx=0, return_transforms=True)      # reference frame first
+    finally:
+        _check(lib.ss_host_free(pin))
+    # (the ECC sums are accumulated with atomics: the transforms agree to rounding, not necessarily to the bit)
+    assert all(np.allclose(x, y, rtol=0, atol=1e-6) for x, y in zip(ma, mb))
+    assert np.mean(a != b) < 1e-3
+    assert c.shape == a.shape and np.array_equal(mc[0], np.array([[1.0, 0, 0], [0, 1.0, 0]]))
+
+
+def test_prefetched_frames_and_double_buffered_results():
+    import ctypes
+    from shinestacker_b200 import _native, NativeLibraryError
+    lib = _native.load()
+    frames = synthetic.make_noise_stack(3, 240, 320, np.uint8, 43)
+    ref = frames[0]
+    moving = [au.cv2_warp_stage(ref, au.rigid(0.3, 1.0, 2.5, -1.5), "BORDER_REPLICATE"),
+              au.cv2_warp_stage(ref, au.rigid(-0.2, 1.0, -3.0, 2.0), "BORDER_REPLICATE")]
+    pin = ctypes.c_void_p()
+    _check(lib.ss_host_alloc(ctypes.byref(pin), 2 * ref.nbytes))
+    buf = np.frombuffer((ctypes.c_uint8 * (2 * ref.nbytes)).from_address(pin.value), np.uint8).reshape((2,) + ref.shape)
+    buf[:] = moving
+    wp, plain = al.Warper(ref.shape[:2], np.uint8), al.Warper(ref.shape[:2], np.uint8)
+    try:
+        wp.ecc_set_reference(ref)
+        plain.ecc_set_reference(ref)
+        with pytest.raises(NativeLibraryError):
+            wp.use_prefetched()                     # nothing prefetched yet
+        wp.prefetch(buf[0])
+        with pytest.raises(NativeLibraryError):
+            wp.prefetch(buf[1])                     # one outstanding frame at most
+        results, ms = [], []
+        for k in range(2):
+            wp.use_prefetched()
+            if k == 0:
+                wp.prefetch(buf[1])                 # uploads while frame 0 is fitted and warped
+            m, _ = wp.ecc_estimate(None)
+            m_plain, _ = plain.ecc_estimate(moving[k])
+            assert np.allclose(m, m_plain, rtol=0, atol=1e-6)
+            ms.append(m)
+            wp.warp(None, m, al.ALIGN_RIGID, "BORDER_REPLICATE", download=False)
+            results.append(wp.result_device())
+            assert np.array_equal(plain.warp(moving[k], m, al.ALIGN_RIGID, "BORDER_REPLICATE"),
+                                  au.cv2_warp_stage(moving[k], m, "BORDER_REPLICATE"))
+        # both results are still in device memory (double-buffered outputs): feed them to a stacker and compare
+        assert results[0][0].value != results[1][0].value
+        algo = PyramidStack()
+        algo._set_metadata(ref)
+        algo._ensure_handle(ref.shape, ref.dtype, 2)
+        for ptr, pitch in results:
+            _check(lib.ss_push_frame_device(algo._h, ptr, pitch))
+        fused = algo._finish(2, ref.shape[:2])
+        expect = PyramidStack().focus_stack_arrays([plain.warp(moving[k], ms[k], al.ALIGN_RIGID, "BORDER_REPLICATE")
+                                                    for k in range(2)])
+        assert np.array_equal(fused, expect)
+    finally:
+        wp.close()
+        plain.close()
+        _check(lib.ss_host_free(pin))
+
+
 def test_device_resident_sources():
     # ssal_warp_device / ssdm_push_frame_device: frames that already live in HBM (here: the output of another warp)
     import ctypes

@@ -37,6 +37,8 @@ struct DmCudaBackend {
         if (ev_end) cudaEventDestroy(ev_end);
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr; h_pinned_n = 0;
+        if (d_params) cudaFree(d_params);
+        d_params = nullptr; d_params_n = 0;
     }
     int alloc(void **p, size_t bytes)
     {
@@ -138,6 +140,8 @@ struct DmCudaBackend {
     // download through pinned memory and ONE synchronisation for all of them
     double *h_pinned = nullptr;
     size_t h_pinned_n = 0;
+    EccParams *d_params = nullptr;
+    int d_params_n = 0;
     int ecc_accumulate_batch(const EccParams *p, int count, double *d_sums, double *host_sums)
     {
         static int n_sm = 0;
@@ -147,19 +151,32 @@ struct DmCudaBackend {
             DM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         }
         const size_t n_d = (size_t)count * ECC_NSUMS;
-        if (h_pinned_n < n_d) {
+        const size_t pin_doubles = n_d + ((size_t)count * sizeof(EccParams) + 7) / 8;   // sums, then the parameter sets
+        if (h_pinned_n < pin_doubles) {
             if (h_pinned) cudaFreeHost(h_pinned);
             h_pinned = nullptr; h_pinned_n = 0;
-            DM_CUDA(cudaHostAlloc((void **)&h_pinned, sizeof(double) * n_d, cudaHostAllocDefault));
-            h_pinned_n = n_d;
+            DM_CUDA(cudaHostAlloc((void **)&h_pinned, sizeof(double) * pin_doubles, cudaHostAllocDefault));
+            h_pinned_n = pin_doubles;
         }
+        if (d_params_n < count) {
+            if (d_params) cudaFree(d_params);
+            d_params = nullptr; d_params_n = 0;
+            DM_CUDA(cudaMalloc((void **)&d_params, sizeof(EccParams) * (size_t)count));
+            d_params_n = count;
+        }
+        memcpy(h_pinned + n_d, p, sizeof(EccParams) * (size_t)count);
+        DM_CUDA(cudaMemcpyAsync(d_params, h_pinned + n_d, sizeof(EccParams) * (size_t)count, cudaMemcpyHostToDevice, s_comp));
         DM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * n_d, s_comp));
-        for (int i = 0; i < count; ++i) {
+        // sets of equal geometry go out as one launch (grid.y = set); the coarse search is 81 such sets
+        for (int i = 0; i < count;) {
+            int j = i + 1;
+            while (j < count && p[j].h == p[i].h && p[j].w == p[i].w && j - i < 65535) ++j;
             const long long n = (long long)p[i].h * p[i].w;
             long long blocks = (n + 255) / 256;
             if (blocks > 4LL * n_sm) blocks = 4LL * n_sm;     // 4 resident CTAs of 256 threads per SM
-            ecc_accumulate_kernel<<<(int)blocks, 256, 0, s_comp>>>(p[i], d_sums + (size_t)i * ECC_NSUMS);
+            ecc_accumulate_kernel<<<dim3((unsigned)blocks, (unsigned)(j - i)), 256, 0, s_comp>>>(d_params + i, d_sums + (size_t)i * ECC_NSUMS);
             ++launches;
+            i = j;
         }
         DM_CUDA(cudaGetLastError());
         DM_CUDA(cudaMemcpyAsync(h_pinned, d_sums, sizeof(double) * n_d, cudaMemcpyDeviceToHost, s_comp));

@@ -308,8 +308,11 @@ __global__ void __launch_bounds__(256) ecc_level_kernel(const __grid_constant__ 
 
 // One ECC iteration over a level: grid-stride over the pixels, per-thread float partial sums, shuffle
 // reduction per warp, shared-memory reduction per CTA, one double atomicAdd per sum and CTA.
-__global__ void __launch_bounds__(256) ecc_accumulate_kernel(const __grid_constant__ EccParams p, double *sums)
+// blockIdx.y selects one of several parameter sets (the candidates of the coarse search: one launch for all).
+__global__ void __launch_bounds__(256) ecc_accumulate_kernel(const EccParams *pp, double *all_sums)
 {
+    const EccParams p = pp[blockIdx.y];
+    double *sums = all_sums + (size_t)blockIdx.y * ECC_NSUMS;
     float acc[ECC_NSUMS];
 #pragma unroll
     for (int i = 0; i < ECC_NSUMS; ++i) acc[i] = 0.f;

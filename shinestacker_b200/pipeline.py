@@ -66,7 +66,7 @@ class _Sources:
 
 
 def align_and_stack_arrays(frames, ref_idx=None, stack_algo=None, border_mode=BORDER_REPLICATE_BLUR,
-                           border_value=(0, 0, 0, 0), border_blur=50, ecc_finest_level=0, ecc_max_iters=30,
+                           border_value=(0, 0, 0, 0), border_blur=50, ecc_finest_level=None, ecc_max_iters=30,
                            ecc_eps=1e-3, device=0, warper=None, return_transforms=False):
     """Aligns every frame onto ``frames[ref_idx]`` (ECC similarity fit + warp, all on the GPU) and fuses the
     aligned stack with ``stack_algo`` (default ``PyramidStack()``); returns the fused image (and the list of
@@ -74,12 +74,19 @@ def align_and_stack_arrays(frames, ref_idx=None, stack_algo=None, border_mode=BO
 
     Pipelined per frame: while frame i is fitted and warped, frame i+1 uploads into the warper's second source
     buffer (``ssal_prefetch``) and the aligned frame i-1 is copied into the stack by the stacker's own stream (the
-    warper's outputs are double-buffered, so nothing waits for that copy)."""
+    warper's outputs are double-buffered, so nothing waits for that copy).
+
+    ``ecc_finest_level``: pyramid level the fit stops at; default (None) = 1 for frames of at least 2048 pixels on the
+    short side, else 0.  The reference estimates on a subsampled image by default as well (align.py:167-173,
+    ``subsample``); on the 4096x3072 stack the two full-resolution iterations cost 0.73 ms of the 1.6 ms fit and
+    change the error against the known transform from 0.0025 to 0.0023 px (tools/pipe_once.py)."""
     frames = list(frames)
     if not frames:
         raise ImageLoadError("", "empty frame list")
     n = len(frames)
     ref_idx = n // 2 if ref_idx is None else int(ref_idx)
+    if ecc_finest_level is None:
+        ecc_finest_level = 1 if min(frames[0].shape[:2]) >= 2048 else 0
     algo = stack_algo or PyramidStack(device=device)
     first = frames[0]
     algo._set_metadata(first)                                  # pylint: disable=protected-access

@@ -204,7 +204,8 @@ class PyramidStack(PyramidBase):
         self.keep_depth_maps = keep_depth_maps
         self.frame_index_base = int(frame_index_base)
         self.decode_threads = int(decode_threads)   # files decoded ahead of the upload (0 = inline)
-        self.depth_maps = None     # dict(best=[level 0..L-1], best_e, best_d) after focus_stack
+        self._depth_maps = None    # dict(best=[level 0..L-1], best_e, best_d) after focus_stack, fetched on first use
+        self._depth_maps_ready = False
         self.last_kernel_ms = None
         self.last_launches = None
         self._lib = _native.load()
@@ -226,6 +227,7 @@ class PyramidStack(PyramidBase):
                 64 if self.float_type == np.float64 else 32, self.device, self.batch_frames, self.frame_index_base)
         if self._h is not None and self._geom == geom and n_frames <= self._max_frames and \
                 (not resident or self._resident >= n_frames):
+            self._depth_maps_ready = False       # maps not fetched by now belong to the stack being replaced
             _check(self._lib.ss_reset(self._h))
             return
         self.close()
@@ -254,6 +256,12 @@ class PyramidStack(PyramidBase):
 
     def close(self):
         if getattr(self, "_h", None) is not None:
+            if getattr(self, "_depth_maps_ready", False) and self._depth_maps is None:
+                try:
+                    self._depth_maps = self.get_depth_maps()      # keep the last stack's maps readable after close
+                except Exception:  # pylint: disable=broad-except
+                    pass
+            self._depth_maps_ready = False
             self._lib.ss_destroy(self._h)
             self._h = None
         for ptr, _ in getattr(self, "_stage", []):
@@ -392,9 +400,17 @@ class PyramidStack(PyramidBase):
         nl = ctypes.c_int64()
         _check(lib.ss_launch_count(h, ctypes.byref(nl)))
         self.last_launches = nl.value
-        if self.keep_depth_maps:
-            self.depth_maps = self.get_depth_maps()
+        # the integer arg-max maps stay in HBM until the next stack; `depth_maps` downloads them on first access
+        self._depth_maps, self._depth_maps_ready = None, bool(self.keep_depth_maps)
         return out
+
+    @property
+    def depth_maps(self):
+        """dict(best=[level 0 .. L-1], best_e, best_d) of the last stack (``keep_depth_maps``), else None.  Downloaded
+        from the device on first access, so stacks whose maps nobody looks at do not pay for the transfer."""
+        if self._depth_maps is None and self._depth_maps_ready and self._h is not None:
+            self._depth_maps = self.get_depth_maps()
+        return self._depth_maps
 
     def get_depth_maps(self):
         """Integer arg-max maps of the last stack (np.argmax results of reference pyramid.py:51 and

@@ -37,8 +37,6 @@ struct DmCudaBackend {
         if (ev_end) cudaEventDestroy(ev_end);
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr; h_pinned_n = 0;
-        if (d_params) cudaFree(d_params);
-        d_params = nullptr; d_params_n = 0;
     }
     int alloc(void **p, size_t bytes)
     {
@@ -140,9 +138,9 @@ struct DmCudaBackend {
     // download through pinned memory and ONE synchronisation for all of them
     double *h_pinned = nullptr;
     size_t h_pinned_n = 0;
-    EccParams *d_params = nullptr;
-    int d_params_n = 0;
-    int ecc_accumulate_batch(const EccParams *p, int count, double *d_sums, double *host_sums)
+    // Coarse search: the (2 radius + 1)^2 shifted copies of `base` are evaluated by ONE launch (grid.y = candidate,
+    // parameters by value: no host-to-device copy), one download through pinned memory, one synchronisation.
+    int ecc_search(const EccParams &base, double tx, double ty, int radius, double *d_sums, double *host_sums)
     {
         static int n_sm = 0;
         if (!n_sm) {
@@ -150,38 +148,31 @@ struct DmCudaBackend {
             DM_CUDA(cudaGetDevice(&dev));
             DM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         }
+        const int count = (2 * radius + 1) * (2 * radius + 1);
         const size_t n_d = (size_t)count * ECC_NSUMS;
-        const size_t pin_doubles = n_d + ((size_t)count * sizeof(EccParams) + 7) / 8;   // sums, then the parameter sets
-        if (h_pinned_n < pin_doubles) {
+        if (h_pinned_n < n_d) {
             if (h_pinned) cudaFreeHost(h_pinned);
             h_pinned = nullptr; h_pinned_n = 0;
-            DM_CUDA(cudaHostAlloc((void **)&h_pinned, sizeof(double) * pin_doubles, cudaHostAllocDefault));
-            h_pinned_n = pin_doubles;
+            DM_CUDA(cudaHostAlloc((void **)&h_pinned, sizeof(double) * n_d, cudaHostAllocDefault));
+            h_pinned_n = n_d;
         }
-        if (d_params_n < count) {
-            if (d_params) cudaFree(d_params);
-            d_params = nullptr; d_params_n = 0;
-            DM_CUDA(cudaMalloc((void **)&d_params, sizeof(EccParams) * (size_t)count));
-            d_params_n = count;
-        }
-        memcpy(h_pinned + n_d, p, sizeof(EccParams) * (size_t)count);
-        DM_CUDA(cudaMemcpyAsync(d_params, h_pinned + n_d, sizeof(EccParams) * (size_t)count, cudaMemcpyHostToDevice, s_comp));
         DM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * n_d, s_comp));
-        // sets of equal geometry go out as one launch (grid.y = set); the coarse search is 81 such sets
-        for (int i = 0; i < count;) {
-            int j = i + 1;
-            while (j < count && p[j].h == p[i].h && p[j].w == p[i].w && j - i < 65535) ++j;
-            const long long n = (long long)p[i].h * p[i].w;
-            long long blocks = (n + 255) / 256;
-            if (blocks > 4LL * n_sm) blocks = 4LL * n_sm;     // 4 resident CTAs of 256 threads per SM
-            ecc_accumulate_kernel<<<dim3((unsigned)blocks, (unsigned)(j - i)), 256, 0, s_comp>>>(d_params + i, d_sums + (size_t)i * ECC_NSUMS);
-            ++launches;
-            i = j;
-        }
+        const long long n = (long long)base.h * base.w;
+        long long blocks = (n + 255) / 256;
+        if (blocks > 4LL * n_sm) blocks = 4LL * n_sm;     // 4 resident CTAs of 256 threads per SM
+        ecc_accumulate_kernel<<<dim3((unsigned)blocks, (unsigned)count), 256, 0, s_comp>>>(base, tx, ty, radius, d_sums);
+        ++launches;
         DM_CUDA(cudaGetLastError());
         DM_CUDA(cudaMemcpyAsync(h_pinned, d_sums, sizeof(double) * n_d, cudaMemcpyDeviceToHost, s_comp));
         DM_CUDA(cudaStreamSynchronize(s_comp));
         memcpy(host_sums, h_pinned, sizeof(double) * n_d);
+        return 0;
+    }
+    int ecc_set_state(EccState *d_state, const EccState &st)
+    {
+        ecc_set_state_kernel<<<1, 1, 0, s_comp>>>(st, d_state);
+        DM_CUDA(cudaGetLastError());
+        ++launches;
         return 0;
     }
     // All iterations of one pyramid level on the device (cooperative launch; no host round trip).  d_bar: one
@@ -204,12 +195,6 @@ struct DmCudaBackend {
         void *args[] = {(void *)&g, (void *)&d_state, (void *)&d_sums, (void *)&d_bar};
         DM_CUDA(cudaLaunchCooperativeKernel((const void *)ecc_level_kernel, dim3((unsigned)blocks), dim3(256), args, 0, s_comp));
         ++launches;
-        return 0;
-    }
-    int upload_async(void *dst, const void *src, size_t bytes)
-    {
-        DM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s_comp));
-        DM_CUDA(cudaStreamSynchronize(s_comp));      // src is caller stack memory
         return 0;
     }
     int elapsed_ms(float *ms)

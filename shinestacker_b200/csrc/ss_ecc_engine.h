@@ -128,22 +128,17 @@ struct EccEstimator {
                     // content without low frequencies; all candidates are evaluated with one synchronisation
                     const double cx = 0.5 * (ww - 1), cy = 0.5 * (hh - 1);
                     const double tx = st.dx + st.a * cx - st.b * cy - cx, ty = st.dy + st.b * cx + st.a * cy - cy;
-                    std::vector<EccParams> cand;
                     std::vector<double> sums((size_t)ECC_SEARCH_N * ECC_NSUMS);
-                    for (int sy = -ECC_SEARCH; sy <= ECC_SEARCH; ++sy)
-                        for (int sx = -ECC_SEARCH; sx <= ECC_SEARCH; ++sx) {
-                            EccParams p;
-                            p.ref = ref[l]; p.mov = mov[l]; p.gx = gx; p.gy = gy; p.h = hh; p.w = ww;
-                            p.a = (float)st.a; p.b = (float)st.b; p.tx = (float)(tx + sx); p.ty = (float)(ty + sy);
-                            p.cx = (float)cx; p.cy = (float)cy; p.mean_r = 0.f; p.mean_w = 0.f;
-                            cand.push_back(p);
-                        }
-                    searched = (int)cand.size();
-                    if ((rc = be->ecc_accumulate_batch(cand.data(), (int)cand.size(), d_sums, sums.data())))
+                    EccParams base;
+                    base.ref = ref[l]; base.mov = mov[l]; base.gx = gx; base.gy = gy; base.h = hh; base.w = ww;
+                    base.a = (float)st.a; base.b = (float)st.b; base.tx = (float)tx; base.ty = (float)ty;
+                    base.cx = (float)cx; base.cy = (float)cy; base.mean_r = 0.f; base.mean_w = 0.f;
+                    searched = ECC_SEARCH_N;
+                    if ((rc = be->ecc_search(base, tx, ty, ECC_SEARCH, d_sums, sums.data())))
                         return fail(rc, be->last_error());
                     double best = -3, btx = tx, bty = ty;
-                    for (size_t c = 0; c < cand.size(); ++c) {
-                        const double *Q = sums.data() + c * ECC_NSUMS;
+                    for (int c = 0; c < ECC_SEARCH_N; ++c) {
+                        const double *Q = sums.data() + (size_t)c * ECC_NSUMS;
                         const double n = Q[27];
                         double r = -2.0;
                         if (n >= 64) {
@@ -151,12 +146,15 @@ struct EccEstimator {
                             const double sww = Q[22] - n * mw * mw, srw = Q[23] - n * mw * mr, srr = Q[24] - n * mr * mr;
                             r = sww > 0 && srr > 0 ? srw / sqrt(sww * srr) : -2.0;
                         }
-                        if (r > best) { best = r; btx = cand[c].tx; bty = cand[c].ty; }
+                        if (r > best) {
+                            const EccParams p = ecc_search_candidate(base, tx, ty, ECC_SEARCH, c);
+                            best = r; btx = p.tx; bty = p.ty;
+                        }
                     }
                     st.tx = btx; st.ty = bty;
                     la.use_state_t = 1;
                 }
-                if ((rc = be->upload_async(d_state, &st, sizeof(st)))) return fail(rc, be->last_error());
+                if ((rc = be->ecc_set_state(d_state, st))) return fail(rc, be->last_error());
             }
             if ((rc = be->ecc_run_level(la, d_state, d_sums, d_bar))) return fail(rc, be->last_error());
         }

@@ -113,6 +113,21 @@ struct EccState {
 };
 enum { ECC_FAIL_NO_OVERLAP = 1, ECC_FAIL_FLAT = 2, ECC_FAIL_SINGULAR = 3 };
 
+// candidate c of the coarse search around (tx, ty): c = (sy + radius) * (2 radius + 1) + (sx + radius)
+#ifdef SS_HOST_EMU
+inline
+#else
+__host__ __device__ inline
+#endif
+EccParams ecc_search_candidate(const EccParams &base, double tx, double ty, int radius, int c)
+{
+    const int side = 2 * radius + 1;
+    EccParams p = base;
+    p.tx = (float)(tx + (c % side - radius));
+    p.ty = (float)(ty + (c / side - radius));
+    return p;
+}
+
 struct EccLevelArgs {
     const float *ref, *mov, *gx, *gy;
     int h, w;
@@ -306,12 +321,17 @@ __global__ void __launch_bounds__(256) ecc_level_kernel(const __grid_constant__ 
     // (the barrier counter is zeroed by the host before every launch)
 }
 
+// the state as a kernel argument: no host-to-device copy (which would queue behind the frame uploads of the copy engine)
+__global__ void ecc_set_state_kernel(const __grid_constant__ EccState st, EccState *dst) { *dst = st; }
+
 // One ECC iteration over a level: grid-stride over the pixels, per-thread float partial sums, shuffle
 // reduction per warp, shared-memory reduction per CTA, one double atomicAdd per sum and CTA.
-// blockIdx.y selects one of several parameter sets (the candidates of the coarse search: one launch for all).
-__global__ void __launch_bounds__(256) ecc_accumulate_kernel(const EccParams *pp, double *all_sums)
+// blockIdx.y selects the candidate of the coarse search (one launch for all): whole-pixel shifts (sx, sy) in
+// [-radius, radius]^2 around (tx, ty), sy outermost -- ecc_search_candidate().
+__global__ void __launch_bounds__(256) ecc_accumulate_kernel(const __grid_constant__ EccParams base, double tx, double ty,
+                                                             int radius, double *all_sums)
 {
-    const EccParams p = pp[blockIdx.y];
+    const EccParams p = ecc_search_candidate(base, tx, ty, radius, (int)blockIdx.y);
     double *sums = all_sums + (size_t)blockIdx.y * ECC_NSUMS;
     float acc[ECC_NSUMS];
 #pragma unroll

@@ -30,10 +30,11 @@ struct DmHostBackend {
         return 0;
     }
 #ifdef ECC_NSUMS
-    int ecc_accumulate_batch(const EccParams *pp, int count, double *, double *host_sums)
+    int ecc_search(const EccParams &base, double tx, double ty, int radius, double *, double *host_sums)
     {
+        const int count = (2 * radius + 1) * (2 * radius + 1);
         for (int c = 0; c < count; ++c) {
-            const EccParams &p = pp[c];
+            const EccParams p = ecc_search_candidate(base, tx, ty, radius, c);
             double *out = host_sums + (size_t)c * ECC_NSUMS;
             for (int i = 0; i < ECC_NSUMS; ++i) out[i] = 0;
             float s[ECC_NSUMS];
@@ -41,10 +42,11 @@ struct DmHostBackend {
                 for (int x = 0; x < p.w; ++x)
                     if (ecc_pixel(p, x, y, s))
                         for (int i = 0; i < ECC_NSUMS; ++i) out[i] += s[i];
-            ++launches;
         }
+        ++launches;
         return 0;
     }
+    int ecc_set_state(EccState *dst, const EccState &st) { *dst = st; return 0; }
     int ecc_run_level(const EccLevelArgs &g, EccState *st, double *, unsigned int *)
     {
         if (st->fail) return 0;
@@ -64,7 +66,6 @@ struct DmHostBackend {
         if (!st->fail) ecc_level_end(g, *st);
         return 0;
     }
-    int upload_async(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
 #endif
     int zero(void *p, size_t bytes) { memset(p, 0, bytes); return 0; }
     template <class K>

@@ -22,7 +22,7 @@ algo = PyramidStack(batch_frames=8)
 wp = Warper((3072, 4096), np.uint8)
 pipeline.align_and_stack_arrays(frames, stack_algo=algo, warper=wp)
 
-acc = {}
+acc, extra = {}, {}
 
 
 def timed(name, fn):
@@ -36,7 +36,16 @@ def timed(name, fn):
 
 wp.use_prefetched = timed("use_prefetched", wp.use_prefetched)
 wp.prefetch = timed("prefetch", wp.prefetch)
-wp.ecc_estimate = timed("ecc_estimate", wp.ecc_estimate)
+_ecc = wp.ecc_estimate
+
+
+def ecc_and_kernel_time(*a, **k):
+    r = _ecc(*a, **k)
+    extra["ecc_device_ms_between_events"] = extra.get("ecc_device_ms_between_events", 0.0) + wp.last_kernel_ms
+    return r
+
+
+wp.ecc_estimate = timed("ecc_estimate", ecc_and_kernel_time)
 wp.warp = timed("warp", wp.warp)
 wp.result_device = timed("result_device", wp.result_device)
 wp.ecc_set_reference = timed("ecc_set_reference", wp.ecc_set_reference)
@@ -60,4 +69,5 @@ pipeline.align_and_stack_arrays(frames, stack_algo=algo, warper=wp)
 total = (time.perf_counter() - t0) * 1e3
 acc["total"] = total
 acc["unaccounted"] = total - sum(v for k, v in acc.items() if k != "total")
+acc.update(extra)
 print(json.dumps({k: round(v, 2) for k, v in acc.items()}))

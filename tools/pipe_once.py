@@ -30,3 +30,18 @@ for fl in (0, 1, 2, 3, 4, 5, 6):
     c = np.array([2048.0, 1536.0, 1.0])
     print("finest", fl, "ms", round(min(ts), 3), "kernel_ms", round(wp.last_kernel_ms, 3), "iters", info["iterations"],
           "err_px", float(np.abs(m @ c - truth[0] @ c).max()))
+# does an upload in flight slow the fit down?
+for concurrent in (0, 1):
+    ks, ws = [], []
+    for rep in range(6):
+        wp.prefetch(frames[0]); wp.use_prefetched()
+        lib.ss_sync_copies(algo._h)
+        import ctypes as _c
+        time.sleep(0.003)                       # let the upload of frames[0] finish
+        if concurrent:
+            wp.prefetch(frames[1])
+        t0 = time.perf_counter(); m, info = wp.ecc_estimate(None, 1); ws.append((time.perf_counter() - t0) * 1e3)
+        ks.append(wp.last_kernel_ms)
+        if concurrent:
+            wp.use_prefetched()
+    print("concurrent upload", concurrent, "wall ms", round(min(ws), 3), "device ms", round(min(ks), 3), round(float(np.median(ks)), 3))

@@ -873,37 +873,47 @@ struct DmPyrDownTile {
         float *out = out0 + z * zs_out;
         const int h = src.h, w = src.w, x0 = tx * DM_PD_X, y0 = ty * DM_PD_Y, sx0 = 2 * x0 - 2, sy0 = 2 * y0 - 2;
         float *S = sm, *R = sm + 4 * DM_PD_SH * DM_PD_SW;
-        const int NS = DM_PD_SH * (DM_PD_SW - 1);       // 35 rows x 67 columns
         const bool inside = sx0 >= 0 && sy0 >= 0 && sx0 + DM_PD_SW - 1 <= w && sy0 + DM_PD_SH <= h;
-        for (int base = 0; base < NS; base += 4 * nthreads) {
-            float t[4][4];
+        const int lanes = nthreads < 32 ? nthreads : 32, lane = tid % lanes, warp = tid / lanes, nwarps = nthreads / lanes;
+        for (int i = warp; i < DM_PD_SH; i += nwarps) {         // 35 rows x 67 columns, a warp per row
+            const int yy = inside ? sy0 + i : dm_reflect101(sy0 + i, h);
+            float t[3][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int s = base + u * nthreads + tid;
-                if (s < NS) {
-                    const int i = s / (DM_PD_SW - 1), j = s % (DM_PD_SW - 1);
-                    const int yy = inside ? sy0 + i : dm_reflect101(sy0 + i, h), xx = inside ? sx0 + j : dm_reflect101(sx0 + j, w);
+            for (int u = 0; u < 3; ++u) {
+                const int j = lane + u * lanes;
+                if (j < DM_PD_SW - 1) {
+                    const int xx = inside ? sx0 + j : dm_reflect101(sx0 + j, w);
 #pragma unroll
                     for (int p = 0; p < 4; ++p) t[u][p] = src.at(p, xx, yy);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int s = base + u * nthreads + tid;
-                if (s < NS) {
-                    const int i = s / (DM_PD_SW - 1), j = s % (DM_PD_SW - 1);
+            for (int u = 0; u < 3; ++u) {
+                const int j = lane + u * lanes;
+                if (j < DM_PD_SW - 1) {
 #pragma unroll
                     for (int p = 0; p < 4; ++p) S[(p * DM_PD_SH + i) * DM_PD_SW + j] = t[u][p];
                 }
             }
+            for (int j = lane + 3 * lanes; j < DM_PD_SW - 1; j += lanes) {      // fewer than 32 lanes (host build)
+                const int xx = inside ? sx0 + j : dm_reflect101(sx0 + j, w);
+                for (int p = 0; p < 4; ++p) S[(p * DM_PD_SH + i) * DM_PD_SW + j] = src.at(p, xx, yy);
+            }
         }
         DM_SYNC();
-        for (int item = tid; item < 4 * DM_PD_SH * DM_PD_X; item += nthreads) {         // rows
-            const int x = item % DM_PD_X, pi = item / DM_PD_X;                          // pi = plane * SH + row
+        // rows: two neighbouring outputs per item share their taps
+        for (int item = tid; item < 4 * DM_PD_SH * (DM_PD_X / 2); item += nthreads) {
+            const int x = 2 * (item % (DM_PD_X / 2)), pi = item / (DM_PD_X / 2);        // pi = plane * SH + row
             const float *s = S + pi * DM_PD_SW + 2 * x;
-            float acc = ss_add(ss_mul(s[2], 6.f), ss_mul(ss_add(s[1], s[3]), 4.f));
-            acc = ss_add(acc, s[0]);
-            R[pi * DM_PD_X + x] = ss_add(acc, s[4]);
+            float v[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) v[q] = s[q];
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                float acc = ss_add(ss_mul(v[2 * o + 2], 6.f), ss_mul(ss_add(v[2 * o + 1], v[2 * o + 3]), 4.f));
+                acc = ss_add(acc, v[2 * o]);
+                R[pi * DM_PD_X + x + o] = ss_add(acc, v[2 * o + 4]);
+            }
         }
         DM_SYNC();
         const long long plane2 = (long long)h2 * w2;

@@ -11,6 +11,12 @@
 #define ECC_MAX_LEVELS 12
 #define ECC_SEARCH 4            /* coarse search: whole-pixel shifts in [-4, 4]^2 at the coarsest level */
 #define ECC_SEARCH_N ((2 * ECC_SEARCH + 1) * (2 * ECC_SEARCH + 1))
+/* Step size (pixels of the level) at which a level above the finest one stops: it only has to land inside the basin
+ * of the next level (about a pixel there = half a pixel here).  0.02 kept the 64 x 48 level iterating to max_iters on
+ * its own rounding noise (30 of the 58 iterations of a 4096 x 3072 fit, tools/pipe_once.py). */
+#ifndef ECC_COARSE_EPS
+#define ECC_COARSE_EPS 0.1
+#endif
 
 template <class Backend>
 struct EccEstimator {
@@ -120,7 +126,7 @@ struct EccEstimator {
             la.ref = ref[l]; la.mov = mov[l]; la.gx = gx; la.gy = gy; la.h = hh; la.w = ww;
             la.max_iters = max_iters; la.use_state_t = 0; la.scale_up = l > finest_level ? 1 : 0;
             // coarse levels only have to bring the next level into its basin
-            la.eps = l > finest_level ? (eps_px > 0.02 ? eps_px : 0.02) : eps_px;
+            la.eps = l > finest_level ? (eps_px > ECC_COARSE_EPS ? eps_px : ECC_COARSE_EPS) : eps_px;
             if (l == L - 1) {
                 if (!init_m) {
                     // coarsest level: exhaustive search over whole-pixel shifts (+-4 px here = +-4 * 2^(L-1) px at full

@@ -13,7 +13,6 @@ There is no CPU implementation here: without the library or an sm_100 GPU every 
 ``NativeLibraryError``.
 """
 import ctypes
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -88,6 +87,17 @@ class DepthMapStack:
     print_message = PyramidStack.print_message
     _staging = PyramidStack._staging
     _validate = staticmethod(PyramidStack._validate)
+    _stream = PyramidStack._stream       # worker threads stage frames into the pinned ring, this thread uploads
+
+    def _push_slot(self, _i, slot):
+        _check(self._lib.ssdm_push_frame(self._h, slot[0], self._pitch))
+
+    def _sync_copies(self):
+        _check(self._lib.ssdm_sync_copies(self._h))
+
+    def _callbacks_after_push(self, i):
+        if self._report_steps:
+            self._callbacks(i)
 
     # ---- native handle ------------------------------------------------------------------------------
     def _check_options(self):
@@ -151,6 +161,7 @@ class DepthMapStack:
             raise RunStopException(self.name())
 
     def _push(self, i, img, ring):
+        """One frame through the pinned ring from the calling thread (tests; the stack entry points use _stream)."""
         slot = i % len(ring)
         if i >= len(ring) and slot == 0:
             _check(self._lib.ssdm_sync_copies(self._h))
@@ -186,49 +197,44 @@ class DepthMapStack:
         return out
 
     def focus_stack(self, filenames):
-        """reference depth_map.py:64-123: list of image paths -> fused H x W x 3 BGR array of the input dtype."""
+        """reference depth_map.py:64-123: list of image paths -> fused H x W x 3 BGR array of the input dtype.
+        Files are decoded and copied into pinned memory by ``decode_threads`` workers while this thread uploads."""
+        filenames = list(filenames)
         n = len(filenames)
-        metadata = None
-        ring = None
-        pool = ThreadPoolExecutor(max_workers=self.decode_threads) if self.decode_threads > 0 and n > 1 else None
-        pending = {}
-
-        def fetch(i):
-            if pool is None:
-                return fastio.read_frame(filenames[i], read_img)
-            for j in range(i, min(n, i + self.decode_threads + 1)):
-                if j not in pending:
-                    pending[j] = pool.submit(fastio.read_frame, filenames[j], read_img)
-            return pending.pop(i).result()
-
+        if n == 0:
+            raise ImageLoadError("", "empty file list")
         try:
-            for i, img_path in enumerate(filenames):
-                self.print_message(f": reading file (1/2) {img_path.split('/')[-1]}")
-                img = fetch(i)
+            self.print_message(f": reading file (1/2) {filenames[0].split('/')[-1]}")
+            first = fastio.read_frame(filenames[0], read_img)
+            if first is None:
+                raise ImageLoadError(filenames[0])
+            if first.ndim != 3 or first.shape[2] != 3 or first.dtype not in (np.uint8, np.uint16):
+                raise ImageLoadError(filenames[0], "expected a 3-channel 8 or 16 bit image")
+            shape, dtype = tuple(first.shape), np.dtype(first.dtype)
+            self._ensure_handle(shape, dtype, n)
+            self._pitch = shape[1] * 3 * dtype.itemsize
+            self._report_steps = True
+            ring = self._staging(shape[0] * shape[1] * 3 * dtype.itemsize, 2 * max(self.decode_threads, 2))
+
+            def load_into(i, view):
+                img = first if i == 0 else fastio.read_frame(filenames[i], read_img)
+                if img is not None and tuple(img.shape) == shape and img.dtype == dtype:
+                    stage_frame(img, view)
+                return img
+
+            def on_frame(i, img):
+                if i:
+                    self.print_message(f": reading file (1/2) {filenames[i].split('/')[-1]}")
                 if img is None:
-                    raise ImageLoadError(img_path)
-                if metadata is None:
-                    metadata = (img.shape[:2], img.dtype)
-                    if img.ndim != 3 or img.shape[2] != 3 or img.dtype not in (np.uint8, np.uint16):
-                        raise ImageLoadError(img_path, "expected a 3-channel 8 or 16 bit image")
-                    self._ensure_handle(img.shape, img.dtype, n)
-                    ring = self._staging(img.nbytes, 4)
-                else:
-                    self._validate(img, *metadata)
-                self._push(i, img, ring)
-                self._callbacks(i)
-            if metadata is None:
-                raise ImageLoadError("", "empty file list")
-            return self._blend_and_finish(n, metadata[0], metadata[1], filenames)
+                    raise ImageLoadError(filenames[i])
+                self._validate(img, shape[:2], dtype)
+
+            self._stream(n, load_into, ring, on_frame)
+            return self._blend_and_finish(n, shape[:2], dtype, filenames)
         except BaseException:
             if self._h is not None:
                 self._lib.ssdm_reset(self._h)
             raise
-        finally:
-            if pool is not None:
-                for fut in pending.values():
-                    fut.cancel()
-                pool.shutdown(wait=True)
 
     def focus_stack_arrays(self, frames, stage=True):
         """In-memory entry point: iterable of H x W x 3 BGR uint8/uint16 arrays -> fused image.
@@ -241,13 +247,23 @@ class DepthMapStack:
         if img0.ndim != 3 or img0.shape[2] != 3 or img0.dtype not in (np.uint8, np.uint16):
             raise ImageLoadError("<array>", "expected a 3-channel 8 or 16 bit image")
         self._ensure_handle(img0.shape, img0.dtype, len(frames))
-        ring = self._staging(img0.nbytes, 4) if stage else None
+        self._pitch = img0.shape[1] * 3 * img0.dtype.itemsize
+        self._report_steps = False
+        shape2, dtype = img0.shape[:2], img0.dtype
+
+        def load_into(i, view):
+            img = frames[i]
+            if img is not None and img.shape == img0.shape and img.dtype == dtype:
+                stage_frame(img, view)         # pageable -> pinned on a worker thread (numpy releases the GIL)
+            return img
+
         try:
-            for i, img in enumerate(frames):
-                self._validate(img, img0.shape[:2], img0.dtype)
-                if stage:
-                    self._push(i, img, ring)
-                else:
+            if stage:
+                ring = self._staging(img0.nbytes, 2 * max(self.decode_threads, 2))
+                self._stream(len(frames), load_into, ring, lambda _i, img: self._validate(img, shape2, dtype))
+            else:
+                for img in frames:
+                    self._validate(img, shape2, dtype)
                     if not img.flags.c_contiguous:
                         raise ValueError("stage=False needs C-contiguous frames")
                     _check(self._lib.ssdm_push_frame(self._h, img.ctypes.data_as(ctypes.c_void_p), img.strides[0]))

@@ -233,8 +233,9 @@ SS_DEV DmF4 dm_col4(const float *p, int stride, const DmTaps &t)
 // (slots outside a stage's valid window are computed from whatever lies there and never consumed).
 // RB / RD: radii of the blur and derivative kernels when known at compile time (-1: read from the taps).
 // Patch: ph = 32 + 2 (rb + rd) rows of pw = 64 + 2 hx floats, hx = rb + rd rounded up to 4; three planes behind a
-// 4-float pad: DM_ET_FLOATS(pw, ph).
-#define DM_ET_FLOATS(pw, ph) (3 * (pw) * (ph) + 8)
+// 4-float pad each (the 128-bit row accesses of `fast` reach one group past either end of a plane; those slots are
+// never written and what is read there is never used): DM_ET_FLOATS(pw, ph).
+#define DM_ET_FLOATS(pw, ph) (3 * ((pw) * (ph) + 4) + 4)
 template <typename InT, int RB, int RD>
 struct DmEnergyTile {
     const void *frame; long long pitch; int h, w; DmTaps tblur, ta, tb; int sobel; float *out; unsigned *stats;
@@ -253,7 +254,7 @@ struct DmEnergyTile {
         const int bx0 = x0 - rd > 0 ? x0 - rd : 0, bx1 = x0 + DM_ET_X + rd < w ? x0 + DM_ET_X + rd : w;
         const int by0 = y0 - rd > 0 ? y0 - rd : 0, by1 = y0 + DM_ET_Y + rd < h ? y0 + DM_ET_Y + rd : h;
         const int ex1 = x0 + DM_ET_X < w ? x0 + DM_ET_X : w, ey1 = y0 + DM_ET_Y < h ? y0 + DM_ET_Y : h;
-        float *P0 = sm + 4, *P1 = P0 + pw * ph, *P2 = P1 + pw * ph;
+        float *P0 = sm + 4, *P1 = P0 + pw * ph + 4, *P2 = P1 + pw * ph + 4;
 #define DM_AT(P, y, x) ((P) + ((y) - oy) * pw + ((x) - ox))
         // G: gray of the window
         for (int y = gy0 + warp; y < gy1; y += nwarps)
@@ -296,7 +297,7 @@ struct DmEnergyTile {
     {
         enum { RBc = RB > 0 ? RB : 0, RDc = RD > 0 ? RD : 0, H = RBc + RDc, HX = (H + 3) / 4 * 4, PW = DM_ET_X + 2 * HX,
                PH = DM_ET_Y + 2 * H, G = PW / 4 };
-        float *P0 = sm + 4, *P1 = P0 + PW * PH, *P2 = P1 + PW * PH;
+        float *P0 = sm + 4, *P1 = P0 + PW * PH + 4, *P2 = P1 + PW * PH + 4;
         const int ox = x0 - HX, oy = y0 - H;
         // G: gray, four pixels (12 samples) per item
         for (int item = tid; item < PH * G; item += nthreads) {

@@ -19,7 +19,7 @@ import numpy as np
 from . import _native
 from .exceptions import InvalidOptionError, ImageLoadError, RunStopException
 from . import fastio
-from .pyramid import read_img, _check, stage_frame, PyramidStack, FLOAT_32, FLOAT_64
+from .pyramid import read_img, _check, stage_frame, default_decode_threads, PyramidStack, FLOAT_32, FLOAT_64
 
 # reference src/shinestacker/config/constants.py:144-157
 DM_ENERGY_LAPLACIAN = "laplacian"
@@ -47,7 +47,7 @@ class DepthMapStack:
     def __init__(self, map_type=DEFAULT_DM_MAP, energy=DEFAULT_DM_ENERGY,
                  kernel_size=DEFAULT_DM_KERNEL_SIZE, blur_size=DEFAULT_DM_BLUR_SIZE,
                  smooth_size=DEFAULT_DM_SMOOTH_SIZE, temperature=DEFAULT_DM_TEMPERATURE,
-                 levels=DEFAULT_DM_LEVELS, float_type=DEFAULT_DM_FLOAT, device=0, decode_threads=4):
+                 levels=DEFAULT_DM_LEVELS, float_type=DEFAULT_DM_FLOAT, device=0, decode_threads=None):
         # reference base_stack_algo.py:10-22
         self._name = "depth map"
         self._steps_per_frame = 2
@@ -68,7 +68,7 @@ class DepthMapStack:
         self.temperature = temperature
         self.levels = levels
         self.device = int(device)
-        self.decode_threads = int(decode_threads)
+        self.decode_threads = default_decode_threads() if decode_threads is None else int(decode_threads)
         self.last_kernel_ms = None
         self.last_launches = None
         self._lib = _native.load()

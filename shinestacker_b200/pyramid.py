@@ -119,6 +119,10 @@ def select_base(lib, h, n_frames, num_values, float_type=np.float32):
             _check(lib.ss_finish_select_base_px(h, table.ctypes.data_as(ctypes.c_void_p)))
 
 
+def default_decode_threads():
+    return max(1, min(12, (os.cpu_count() or 4) - 2))
+
+
 def stage_frame(img, view):
     """Copy one decoded frame -- an ndarray from cv2.imread or a mapped plain TIFF (fastio) -- into a pinned
     staging buffer (flat uint8 view)."""
@@ -193,7 +197,7 @@ class PyramidStack(PyramidBase):
 
     def __init__(self, min_size=DEFAULT_PY_MIN_SIZE, kernel_size=DEFAULT_PY_KERNEL_SIZE,
                  gen_kernel=DEFAULT_PY_GEN_KERNEL, float_type=DEFAULT_PY_FLOAT,
-                 device=0, batch_frames=8, keep_depth_maps=True, frame_index_base=0, decode_threads=8):
+                 device=0, batch_frames=8, keep_depth_maps=True, frame_index_base=0, decode_threads=None):
         super().__init__(min_size, kernel_size, gen_kernel, float_type)
         self.offset = np.arange(-self.pad_amount, self.pad_amount + 1)
         self.dtype = None
@@ -203,7 +207,9 @@ class PyramidStack(PyramidBase):
         self.batch_frames = int(batch_frames)
         self.keep_depth_maps = keep_depth_maps
         self.frame_index_base = int(frame_index_base)
-        self.decode_threads = int(decode_threads)   # files decoded ahead of the upload (0 = inline)
+        # workers that decode / copy frames into the pinned ring ahead of the upload (0 = inline); default: the host's
+        # cores minus two, at most 12 (B200 box, 16 cores, 64 x 37.7 MB TIFFs: 6 -> 100 ms, 8 -> 87 ms, 12 -> 85 ms)
+        self.decode_threads = default_decode_threads() if decode_threads is None else int(decode_threads)
         self._depth_maps = None    # dict(best=[level 0..L-1], best_e, best_d) after focus_stack, fetched on first use
         self._depth_maps_ready = False
         self.last_kernel_ms = None
@@ -319,6 +325,10 @@ class PyramidStack(PyramidBase):
         ptr, view = ring[slot]
         stage_frame(img, view)
         _check(self._lib.ss_push_frame(self._h, ptr, img.shape[1] * 3 * img.dtype.itemsize))
+
+    def _ring_slots(self):
+        """Pinned slots: two per frame of a kernel-chain batch and two per worker, so that neither waits for the other."""
+        return 2 * max(self.batch_frames, min(self.decode_threads, 12), 1)
 
     def _stream(self, n, load_into, ring, on_frame):
         """Decode / convert on worker threads straight into the pinned ring, upload from the calling thread.
@@ -521,7 +531,7 @@ class PyramidStack(PyramidBase):
 
         try:
             self._ensure_handle(shape2, dtype, n)
-            ring = self._staging(frame_bytes, 2 * max(self.batch_frames, 1))
+            ring = self._staging(frame_bytes, self._ring_slots())
             self._callbacks_after_push = lambda i: self._callbacks(i + n)
             self._stream(n, load_into, ring, on_frame)
             self.print_message(': pyramids fusion completed')
@@ -543,7 +553,7 @@ class PyramidStack(PyramidBase):
             raise ImageLoadError("<array>", "expected a 3-channel 8 or 16 bit image")
         self._set_metadata(img0)
         self._ensure_handle(img0.shape, img0.dtype, len(frames))
-        ring = self._staging(img0.nbytes, 2 * max(self.batch_frames, 1))
+        ring = self._staging(img0.nbytes, self._ring_slots())
         self._frame_shape = tuple(img0.shape)
         self._rgb_frames = set()
         shape2, dtype = img0.shape[:2], img0.dtype

@@ -37,11 +37,20 @@ def stubbed(monkeypatch):
     def ensure(self, shape, dtype, n):
         self._check_options()
         self._geom = (int(shape[0]), int(shape[1]))
+        self._frame = (tuple(int(v) for v in shape), np.dtype(dtype))
         self._h = 1
 
+    def push_slot(self, i, slot):
+        # what the upload would read from the pinned slot a worker thread staged the frame in
+        shape, dtype = self._frame
+        n = int(np.prod(shape)) * dtype.itemsize
+        pushed.append((i, slot[1][:n].view(dtype).reshape(shape).copy()))
+
     monkeypatch.setattr(DepthMapStack, "_ensure_handle", ensure)
-    monkeypatch.setattr(DepthMapStack, "_staging", lambda self, nbytes, count: [])
-    monkeypatch.setattr(DepthMapStack, "_push", lambda self, i, img, ring: pushed.append((i, img.copy())))
+    monkeypatch.setattr(DepthMapStack, "_staging",
+                        lambda self, nbytes, count: [(None, np.zeros(nbytes, np.uint8)) for _ in range(4)])
+    monkeypatch.setattr(DepthMapStack, "_push_slot", push_slot)
+    monkeypatch.setattr(DepthMapStack, "_sync_copies", lambda self: None)
     monkeypatch.setattr(DepthMapStack, "close", lambda self: None)
     return pushed
 

@@ -14,9 +14,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def measure(host, steps=2, threads=6):
+def measure(host, steps=2, threads=None, sweep=()):
     import cv2
     from shinestacker_b200 import PyramidStack, fastio
+    from shinestacker_b200.pyramid import default_decode_threads
+    threads = default_decode_threads() if threads is None else threads
     need = int(sum(f.nbytes for f in host) * 1.1) + (64 << 20)
     root = None
     for cand in ("/dev/shm", tempfile.gettempdir()):
@@ -54,6 +56,18 @@ def measure(host, steps=2, threads=6):
             res[label] = {"ms_per_stack": t * 1e3, "mp_per_s": n * h * w / 1e6 / t}
         fastio.ENABLED = True
         res["same_result"] = bool(np.array_equal(outs["mapped_tiff"], outs["cv2_imread"]))
+        if sweep:       # worker threads / frames per kernel-chain launch (the pinned ring has 2 x batch slots)
+            res["sweep_mapped_tiff_ms"] = {}
+            for th, batch in sweep:
+                algo = PyramidStack(decode_threads=th, batch_frames=batch)
+                algo.focus_stack(paths)
+                ts = []
+                for _ in range(steps):
+                    t0 = time.perf_counter()
+                    algo.focus_stack(paths)
+                    ts.append(time.perf_counter() - t0)
+                algo.close()
+                res["sweep_mapped_tiff_ms"][f"{th} threads, batch {batch}"] = float(np.median(ts)) * 1e3
         # the in-memory entry point: pageable numpy frames -> fused image (worker threads stage them into pinned memory)
         algo = PyramidStack(decode_threads=threads)
         frames = [np.array(f) for f in host]

@@ -72,46 +72,39 @@ def test_stackers_stage_mapped_frames_in_order(tmp_path, monkeypatch, algo_cls, 
         def __getattr__(self, name):
             return lambda *a: 0
 
-    def push(self, i, img, ring):
-        kinds.append(type(img).__name__)
-        view = np.zeros(frames[0].nbytes, np.uint8)
-        stage_frame(img, view)
-        staged.append(view.view(np.uint16).reshape(frames[0].shape).copy())
-
     monkeypatch.setattr(algo_cls, "_ensure_handle", lambda self, *a, **k: setattr(self, "_h", None))
+    # worker threads stage every frame straight into a pinned slot; the upload reads the slot
+    by_path = {}
+    real_read = fastio.read_frame
+
+    def spy(path, fallback):
+        img = real_read(path, fallback)
+        by_path[path] = type(img).__name__
+        return img
+
+    def push_slot(self, i, slot):
+        img = slot[1][:frames[0].nbytes].view(np.uint16).reshape(frames[0].shape).copy()
+        # PyramidStack stages mapped TIFFs as their raw R, G, B payload (ss_push_frame_rgb swaps on the device);
+        # DepthMapStack converts to BGR while staging
+        rgb = i in getattr(self, "_rgb_frames", ())
+        staged.append(img[..., ::-1] if rgb else img)
+        swapped.append(rgb)
+
+    monkeypatch.setattr(fastio, "read_frame", spy)
+    monkeypatch.setattr(algo_cls, "_staging",
+                        lambda self, nbytes, count: [(None, np.zeros(nbytes, np.uint8)) for _ in range(2)])
+    monkeypatch.setattr(algo_cls, "_push_slot", push_slot)
+    monkeypatch.setattr(algo_cls, "_sync_copies", lambda self: None)
     if algo_cls is PyramidStack:
-        # worker threads stage every frame straight into a pinned slot; the upload reads the slot
-        by_path = {}
-        real_read = fastio.read_frame
-
-        def spy(path, fallback):
-            img = real_read(path, fallback)
-            by_path[path] = type(img).__name__
-            return img
-
-        def push_slot(self, i, slot):
-            img = slot[1][:frames[0].nbytes].view(np.uint16).reshape(frames[0].shape).copy()
-            # mapped TIFFs are staged as their raw R, G, B payload (ss_push_frame_rgb swaps on the device)
-            staged.append(img[..., ::-1] if i in self._rgb_frames else img)
-            swapped.append(i in self._rgb_frames)
-
-        monkeypatch.setattr(fastio, "read_frame", spy)
-        monkeypatch.setattr(algo_cls, "_staging",
-                            lambda self, nbytes, count: [(None, np.zeros(nbytes, np.uint8)) for _ in range(2)])
-        monkeypatch.setattr(algo_cls, "_push_slot", push_slot)
-        monkeypatch.setattr(algo_cls, "_sync_copies", lambda self: None)
         monkeypatch.setattr(algo_cls, "_finish", lambda self, n, shape: np.zeros(tuple(shape) + (3,), self.dtype))
     else:
-        monkeypatch.setattr(algo_cls, "_staging", lambda self, nbytes, count: [])
-        monkeypatch.setattr(algo_cls, "_push", push)
         monkeypatch.setattr(algo_cls, "_blend_and_finish", lambda self, n, shape, dtype, names=None: np.zeros(shape + (3,), dtype))
     algo = algo_cls(decode_threads=threads)
     algo._lib = Lib()
     out = algo.focus_stack(paths)
     assert out.shape == frames[0].shape
-    if algo_cls is PyramidStack:
-        kinds = [by_path[p] for p in paths]
-        assert swapped == [True, True, False, True, True]
+    kinds = [by_path[p] for p in paths]
+    assert swapped == ([True, True, False, True, True] if algo_cls is PyramidStack else [False] * 5)
     assert kinds == ["PlainTiff", "PlainTiff", "ndarray", "PlainTiff", "PlainTiff"]
     for got, f in zip(staged, frames):
         assert np.array_equal(got, f)

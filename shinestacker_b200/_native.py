@@ -131,6 +131,16 @@ SIGNATURES_DEPTHMAP = {
     "ssdm_finish": (_i, [_vp, _vp, _sz]),
     "ssdm_rerun_resident": (_i, [_vp]),
     "ssdm_get_plane": (_i, [_vp, _i, _i, _vp]),
+    "ssdm_sync": (_i, [_vp]),
+    "ssdm_shard_local_max": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "ssdm_shard_finish_local": (_i, [_vp, ctypes.c_float]),
+    "ssdm_shard_buffer_count": (_i, [_vp]),
+    "ssdm_shard_export": (_i, [_vp, _vp]),
+    "ssdm_shard_connect": (_i, [_vp, _vp, _i, _i, _i]),
+    "ssdm_shard_ptrs": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "ssdm_shard_connect_ptrs": (_i, [_vp, ctypes.POINTER(_vp), _i, _i, _i]),
+    "ssdm_shard_finish_weights": (_i, [_vp]),
+    "ssdm_shard_finish_end": (_i, [_vp, _vp, _sz]),
     "ssdm_kernel_time_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "ssdm_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),
 }

@@ -92,6 +92,12 @@ struct DmEngine {
     float gmax = 0.f;
     int batch = DM_BLEND_BATCH_MAX, launched_blend = 0;   // frames per blend launch (SSDM_BLEND_BATCH=1..8)
     int fold_norm = 0, moments = 3, tiled_pyrdown = 1;
+    // frames of one stack sharded over ranks (shard_* below): this rank holds a contiguous run of the frames
+    int world = 1, rank = 0, root = 0, stats_folded = 0;
+    float local_max = 0.f;
+    float *d_psum = nullptr;
+    const float *peer_psum[DM_MAX_RANKS] = {};
+    const float *peer_acc[DM_MAX_RANKS][16] = {};
     int fused_energy = 1;          // SSDM_ENERGY_FUSED=0: the four streaming passes instead of the tiled kernel
 
     int fail(int code, const char *msg) { snprintf(err, sizeof(err), "%s", msg); return code; }
@@ -178,11 +184,11 @@ struct DmEngine {
     void destroy()
     {
         be.sync();
-        void *ptrs[] = {d_frames, d_out, d_energy, d_smooth, d_t1, d_t2, d_t3, d_stats, d_slots, d_sw};
+        void *ptrs[] = {d_frames, d_out, d_energy, d_smooth, d_t1, d_t2, d_t3, d_stats, d_slots, d_sw, d_psum};
         for (void *p : ptrs) if (p) be.free(p);
         for (float *p : gp) if (p) be.free(p);
         for (float *p : acc) if (p) be.free(p);
-        d_frames = d_out = nullptr; d_energy = d_smooth = d_t1 = d_t2 = d_t3 = d_sw = nullptr; d_stats = d_slots = nullptr;
+        d_frames = d_out = nullptr; d_energy = d_smooth = d_t1 = d_t2 = d_t3 = d_sw = d_psum = nullptr; d_stats = d_slots = nullptr;
         gp.clear(); acc.clear();
     }
 
@@ -191,6 +197,7 @@ struct DmEngine {
         int rc = be.sync();
         if (rc) return fail(rc, be.last_error());
         n = 0; finished = 0; blended = 0; launched_blend = 0; collapsed = 0; weights = nullptr; gmax = 0.f;
+        stats_folded = 0; local_max = 0.f;
         be.reset_counters();
         std::vector<unsigned> init(2 * (size_t)o.max_frames * DM_STAT_SLOTS);
         for (size_t i = 0; i < init.size(); i += 2) { init[i] = 0x7f800000u; init[i + 1] = 0u; }  // min = +inf, max = 0
@@ -271,8 +278,8 @@ struct DmEngine {
         return DM_OK;
     }
 
-    // depth_map.py:88-93: global normalisation, bilateral smoothing, focus map
-    int finish_begin()
+    // per-frame (min, max) of the raw energies out of the slots the energy kernels updated; the largest is local_max
+    int fold_stats()
     {
         if (n == 0) return fail(DM_ERR_STATE, "no frames");
         if (finished) return fail(DM_ERR_STATE, "already finished");
@@ -290,7 +297,16 @@ struct DmEngine {
             mx = hi > mx ? hi : mx;
         }
         if ((rc = be.upload_small(d_stats, st.data(), st.size() * sizeof(unsigned)))) return fail(rc, be.last_error());
-        memcpy(&gmax, &mx, 4);
+        memcpy(&local_max, &mx, 4);
+        stats_folded = 1;
+        return DM_OK;
+    }
+
+    // depth_map.py:88-92: division by the maximum over the whole stack, bilateral smoothing (frames of this handle)
+    int smooth(float global_max)
+    {
+        int rc;
+        gmax = global_max;
         const char *pair_env = getenv("SSDM_BILATERAL_PAIR");     // A/B knob: "1" / "0" = the direct kernels
         const char *mom_env = getenv("SSDM_BILATERAL_MOMENTS");
         moments = mom_env && atoi(mom_env) == 5 ? 5 : 3;
@@ -324,11 +340,99 @@ struct DmEngine {
             }
             weights = d_smooth;
         }
+        return DM_OK;
+    }
+
+    // depth_map.py:88-93: global normalisation, bilateral smoothing, focus map
+    int finish_begin()
+    {
+        int rc = fold_stats();
+        if (rc) return rc;
+        if ((rc = smooth(local_max))) return rc;
         DmFocusMap f{weights, h, w, n, o.map_type, (float)o.temperature};
         if ((rc = be.launch(f, w, h, 1))) return fail(rc, be.last_error());
         finished = 1;
         blended = 0; launched_blend = 0;
         return DM_OK;
+    }
+
+    // ---- frames of one stack sharded over ranks ------------------------------------------------------------------
+    // Every rank pushes its own contiguous run of the frames.  Three values cross the ranks: the maximum energy (a
+    // float, through the host), the per-pixel sum of the smoothed energies (each rank's partial sum, read from the
+    // peers' memory) and the blended pyramid (summed on the root out of the peers' memory).  The sums are taken
+    // rank by rank, i.e. in stack order but associated differently from one long chain: float32 rounding, covered by
+    // the 1-LSB contract of this stacker.  map_type 'average' only.
+    int shard_local_max(float *out)
+    {
+        const int rc = fold_stats();
+        if (rc) return rc;
+        *out = local_max;
+        return DM_OK;
+    }
+    int shard_finish_local(float global_max)
+    {
+        if (!stats_folded) return fail(DM_ERR_STATE, "shard_local_max first");
+        if (o.map_type != 0) return fail(DM_ERR_INVALID_OPTION, "sharded stacks implement map_type average only");
+        int rc = smooth(global_max);
+        if (rc) return rc;
+        if (!d_psum && (rc = be.alloc((void **)&d_psum, plane * sizeof(float)))) return fail(rc, be.last_error());
+        DmPartialSum k{weights, h, w, n, d_psum};
+        if ((rc = be.launch(k, w, h, 1))) return fail(rc, be.last_error());
+        return DM_OK;
+    }
+    // exchangeable buffers of this rank: ptrs[0] = partial sum plane, ptrs[1 + l] = blended level l; count = 1 + L
+    int shard_ptrs(void **ptrs)
+    {
+        int rc;
+        if (!d_psum && (rc = be.alloc((void **)&d_psum, plane * sizeof(float)))) return fail(rc, be.last_error());
+        ptrs[0] = d_psum;
+        for (int l = 0; l < L; ++l) ptrs[1 + l] = acc[l];
+        return DM_OK;
+    }
+    // all[r * (1 + L) + k]: buffer k of rank r, mapped into this process (the own entries may be anything)
+    int shard_connect(void *const *all, int world_, int rank_, int root_)
+    {
+        if (world_ < 1 || world_ > DM_MAX_RANKS || rank_ < 0 || rank_ >= world_ || root_ < 0 || root_ >= world_)
+            return fail(DM_ERR_INVALID_OPTION, "world / rank / root out of range");
+        void *own[17];
+        const int rc = shard_ptrs(own);
+        if (rc) return rc;
+        world = world_; rank = rank_; root = root_;
+        for (int r = 0; r < world; ++r)
+            for (int k = 0; k < 1 + L; ++k) {
+                const float *p = (const float *)(r == rank ? own[k] : all[(size_t)r * (1 + L) + k]);
+                if (k == 0) peer_psum[r] = p; else peer_acc[r][k - 1] = p;
+            }
+        return DM_OK;
+    }
+    // after every rank has finished shard_finish_local (barrier): the focus maps of the own frames
+    int shard_finish_weights()
+    {
+        if (!weights || finished) return fail(DM_ERR_STATE, "shard_finish_local first");
+        DmFocusMapShared k;
+        k.e = weights; k.h = h; k.w = w; k.n = n; k.world = world;
+        for (int r = 0; r < DM_MAX_RANKS; ++r) k.psum[r] = r < world ? peer_psum[r] : nullptr;
+        const int rc = be.launch(k, w, h, 1);
+        if (rc) return fail(rc, be.last_error());
+        finished = 1;
+        blended = 0; launched_blend = 0;
+        return DM_OK;
+    }
+    // after every rank has blended its frames (barrier): the root sums the pyramids and collapses; others return
+    int shard_finish_end(void *out_bgr, size_t out_pitch)
+    {
+        if (!finished || blended != n) return fail(DM_ERR_STATE, "finish_end before every frame was blended");
+        if (rank != root) { const int rc = be.sync(); return rc ? fail(rc, be.last_error()) : DM_OK; }
+        if (!collapsed && world > 1) {
+            for (int l = 0; l < L; ++l) {
+                DmPeerAccSum k;
+                for (int r = 0; r < DM_MAX_RANKS; ++r) k.acc[r] = r < world ? peer_acc[r][l] : nullptr;
+                k.world = world; k.out = acc[l]; k.count = 3LL * lh[l] * lw[l]; k.row = lw[l];
+                const int rc = be.launch(k, lw[l], 3 * lh[l], 1);
+                if (rc) return fail(rc, be.last_error());
+            }
+        }
+        return finish_end(out_bgr, out_pitch);
     }
 
     // pass 2 of the nb frames i0 .. i0 + nb - 1: Gaussian pyramids of the batch (one launch per level, z = frame),

@@ -764,6 +764,46 @@ struct DmFocusMap {
     }
 };
 
+// ---- frames sharded over ranks (one process per GPU): the sums over the stack are taken rank by rank ----------
+#define DM_MAX_RANKS 16
+// sum of this rank's n planes, frames in stack order (get_focus_map 'average', depth_map.py:55-57)
+struct DmPartialSum {
+    const float *e; int h, w, n; float *out;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        const long long plane = (long long)h * w, o = (long long)y * w + x;
+        float s = e[o];
+        for (int i = 1; i < n; ++i) s = ss_add(s, e[i * plane + o]);
+        out[o] = s;
+    }
+};
+// sum of every rank's partial sum, ranks in stack order, then e_i / sum for the own n planes, in place
+struct DmFocusMapShared {
+    float *e; int h, w, n; const float *psum[DM_MAX_RANKS]; int world;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        const long long plane = (long long)h * w, o = (long long)y * w + x;
+        float s = psum[0][o];
+        for (int r = 1; r < world; ++r) s = ss_add(s, psum[r][o]);
+        for (int i = 0; i < n; ++i) {
+            float *q = e + i * plane + o;
+            *q = s != 0.f ? ss_div(*q, s) : 0.f;
+        }
+    }
+};
+// one level of the blended pyramid: sum of every rank's share, ranks in stack order (one call = one float)
+struct DmPeerAccSum {
+    const float *acc[DM_MAX_RANKS]; int world; float *out; long long count; int row;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        const long long o = (long long)y * row + x;
+        if (o >= count) return;
+        float s = acc[0][o];
+        for (int r = 1; r < world; ++r) s = ss_add(s, acc[r][o]);
+        out[o] = s;
+    }
+};
+
 // ---- pass 2, per frame: Gaussian pyramids of the image and of its weight map, Laplacian blend -----------
 // Source of one pyramid level: planes 0..2 = B, G, R (level 0: the interleaved integer frame, converted
 // on the fly = img.astype(float32), depth_map.py:96; deeper levels: float planes), plane 3 = weight map.

@@ -210,6 +210,7 @@ struct DmCudaBackend {
 struct ssdm_handle {
     DmEngine<DmCudaBackend> eng;
     int device = 0;
+    void *peer_open[DM_MAX_RANKS][17] = {};     // IPC mappings of the peers' exchangeable buffers (ssdm_shard_connect)
 };
 
 #define SSDM_ENTER(h)                                                       \
@@ -252,10 +253,18 @@ SS_EXPORT int ssdm_create(const ssdm_config *cfg, ssdm_handle **out)
     return SS_OK;
 }
 
+static void ssdm_close_peers(ssdm_handle *h)
+{
+    for (int r = 0; r < DM_MAX_RANKS; ++r)
+        for (int k = 0; k < 17; ++k)
+            if (h->peer_open[r][k]) { cudaIpcCloseMemHandle(h->peer_open[r][k]); h->peer_open[r][k] = nullptr; }
+}
+
 SS_EXPORT void ssdm_destroy(ssdm_handle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    ssdm_close_peers(h);
     h->eng.destroy();
     h->eng.be.shutdown();
     delete h;
@@ -281,6 +290,70 @@ SS_EXPORT int ssdm_finish(ssdm_handle *h, void *out_bgr, size_t pitch)
     if (!rc) rc = h->eng.finish_end(out_bgr, pitch);
     SSDM_RET(h, rc);
 }
+SS_EXPORT int ssdm_sync(ssdm_handle *h)
+{
+    SSDM_ENTER(h);
+    const int rc = h->eng.be.sync();
+    return rc ? ss_fail(rc, "%s", h->eng.be.last_error()) : SS_OK;
+}
+// ---- frames of one stack sharded over the GPUs of a box (one process per GPU) -------------------------------------
+SS_EXPORT int ssdm_shard_local_max(ssdm_handle *h, float *max_out)
+{
+    SSDM_ENTER(h);
+    if (!max_out) return ss_fail(SS_ERR_STATE, "null argument");
+    SSDM_RET(h, h->eng.shard_local_max(max_out));
+}
+SS_EXPORT int ssdm_shard_finish_local(ssdm_handle *h, float global_max) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_finish_local(global_max)); }
+SS_EXPORT int ssdm_shard_buffer_count(ssdm_handle *h) { return h ? 1 + h->eng.L : 0; }
+SS_EXPORT int ssdm_shard_ptrs(ssdm_handle *h, void **ptrs)
+{
+    SSDM_ENTER(h);
+    if (!ptrs) return ss_fail(SS_ERR_STATE, "null argument");
+    SSDM_RET(h, h->eng.shard_ptrs(ptrs));
+}
+// blob: ssdm_shard_buffer_count() x 64 bytes, the CUDA IPC handles of this rank's exchangeable buffers
+SS_EXPORT int ssdm_shard_export(ssdm_handle *h, void *blob)
+{
+    SSDM_ENTER(h);
+    if (!blob) return ss_fail(SS_ERR_STATE, "null argument");
+    void *own[17];
+    const int rc = h->eng.shard_ptrs(own);
+    if (rc) return ss_fail(rc, "%s", h->eng.err);
+    for (int k = 0; k < 1 + h->eng.L; ++k) {
+        cudaIpcMemHandle_t mh;
+        SS_CUDA(cudaIpcGetMemHandle(&mh, own[k]));
+        memcpy((char *)blob + 64 * k, &mh, 64);
+    }
+    return SS_OK;
+}
+// blobs: world x (ssdm_shard_export blob), in rank order (the own entry is ignored)
+SS_EXPORT int ssdm_shard_connect(ssdm_handle *h, const void *blobs, int world, int rank, int root)
+{
+    SSDM_ENTER(h);
+    if (!blobs || world < 1 || world > DM_MAX_RANKS || rank < 0 || rank >= world) return ss_fail(SS_ERR_INVALID_OPTION, "world / rank out of range");
+    const int nb = 1 + h->eng.L;
+    ssdm_close_peers(h);
+    std::vector<void *> all((size_t)world * nb, nullptr);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        for (int k = 0; k < nb; ++k) {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, (const char *)blobs + ((size_t)r * nb + k) * 64, 64);
+            SS_CUDA(cudaIpcOpenMemHandle(&h->peer_open[r][k], mh, cudaIpcMemLazyEnablePeerAccess));
+            all[(size_t)r * nb + k] = h->peer_open[r][k];
+        }
+    }
+    SSDM_RET(h, h->eng.shard_connect(all.data(), world, rank, root));
+}
+// the same with plain device pointers (handles of one process, e.g. tests): ptrs[r * count + k]
+SS_EXPORT int ssdm_shard_connect_ptrs(ssdm_handle *h, void *const *ptrs, int world, int rank, int root)
+{
+    SSDM_ENTER(h);
+    if (!ptrs) return ss_fail(SS_ERR_STATE, "null argument");
+    SSDM_RET(h, h->eng.shard_connect(ptrs, world, rank, root));
+}
+SS_EXPORT int ssdm_shard_finish_weights(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_finish_weights()); }
+SS_EXPORT int ssdm_shard_finish_end(ssdm_handle *h, void *out_bgr, size_t pitch) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_finish_end(out_bgr, pitch)); }
 SS_EXPORT int ssdm_rerun_resident(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.rerun_resident()); }
 SS_EXPORT int ssdm_get_plane(ssdm_handle *h, int what, int frame, float *out) { SSDM_ENTER(h); SSDM_RET(h, h->eng.get_plane(what, frame, out)); }
 SS_EXPORT int ssdm_kernel_time_ms(ssdm_handle *h, float *ms)

@@ -121,7 +121,7 @@ __global__ void ss64_base_gray_hist_kernel(const double *base, int n_px, int32_t
     atomicAdd(&counts[gv], 1u);
 }
 
-__device__ double ss64_np_pairwise_sum(const double *a, int n)
+__device__ __forceinline__ double ss64_np_pairwise_leaf(const double *a, int n)
 {
     if (n < 8) {
         double res = 0.0;
@@ -138,18 +138,31 @@ __device__ double ss64_np_pairwise_sum(const double *a, int n)
     for (; i < n; ++i) res = __dadd_rn(res, a[i]);
     return res;
 }
+// numpy's pairwise add.reduce (see ss_np_pairwise_sum): runs above 128 values are halved, DEPTH levels deep
+template <int DEPTH>
+__device__ double ss64_np_pairwise_sum(const double *a, int n)
+{
+    if (n <= 128) return ss64_np_pairwise_leaf(a, n);
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(ss64_np_pairwise_sum<DEPTH - 1>(a, n2), ss64_np_pairwise_sum<DEPTH - 1>(a + n2, n - n2));
+}
+template <>
+__device__ double ss64_np_pairwise_sum<0>(const double *a, int n) { return ss64_np_pairwise_leaf(a, n); }
 
 // entropy / deviation in float64 (pyramid.py:66-93), blockIdx.y = frame
+template <int MAXSIDE>
 __global__ void ss64_base_metrics_kernel(const int32_t *gray, const double *log_p, int per_px, int h, int w,
                                          int num_values, int side, double *ent_out, double *dev_out)
 {
+    constexpr int DEPTH = MAXSIDE * MAXSIDE <= 128 ? 0 : 3;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
     const int n_px = h * w;
     if (i >= n_px) return;
     const int y = i / w, x = i - y * w;
     const int pad = (side - 1) / 2, n = side * side;
-    double buf[121];
-    int vals[121];
+    double buf[MAXSIDE * MAXSIDE];
+    int vals[MAXSIDE * MAXSIDE];
     const int32_t *g = gray + (size_t)f * n_px;
     const double *lp = log_p + (size_t)f * (per_px ? n_px : num_values);
     int c = 0;
@@ -165,13 +178,13 @@ __global__ void ss64_base_metrics_kernel(const int32_t *gray, const double *log_
             ++c;
         }
     }
-    ent_out[(size_t)f * n_px + i] = __dmul_rn(-1.0, ss64_np_pairwise_sum(buf, n));
+    ent_out[(size_t)f * n_px + i] = __dmul_rn(-1.0, ss64_np_pairwise_sum<DEPTH>(buf, n));
     const double mean = (double)s / (double)n;
     for (int k = 0; k < n; ++k) {
         const double d = __dsub_rn((double)vals[k], mean);
         buf[k] = __dmul_rn(d, d);
     }
-    dev_out[(size_t)f * n_px + i] = __ddiv_rn(ss64_np_pairwise_sum(buf, n), (double)n);
+    dev_out[(size_t)f * n_px + i] = __ddiv_rn(ss64_np_pairwise_sum<DEPTH>(buf, n), (double)n);
 }
 
 // arg-max over frames + blend ((0 + base[best_e]) + base[best_d]) / 2 (pyramid.py:102-111)

@@ -123,9 +123,10 @@ __global__ void ss_base_gray_hist_kernel(const float *base, int n_px, int32_t *g
     atomicAdd(&counts[(size_t)f * num_values + gv], 1u);
 }
 
-// numpy's float32 pairwise add.reduce for n <= 128 contiguous values (reference: ndarray.sum() at
-// pyramid.py:77 and :85).
-__device__ float ss_np_pairwise_sum(const float *a, int n)
+// numpy's float32 pairwise add.reduce over n contiguous values (reference: ndarray.sum() at pyramid.py:77 and :85;
+// SURVEY.md section 9 item 7): up to 128 values eight running sums combined as a fixed tree, above that the run is
+// halved (first half rounded down to a multiple of 8) -- DEPTH levels of halving cover n <= 128 << DEPTH.
+__device__ __forceinline__ float ss_np_pairwise_leaf(const float *a, int n)
 {
     if (n < 8) {
         float res = 0.f;
@@ -142,8 +143,19 @@ __device__ float ss_np_pairwise_sum(const float *a, int n)
     for (; i < n; ++i) res = __fadd_rn(res, a[i]);
     return res;
 }
+template <int DEPTH>
+__device__ float ss_np_pairwise_sum(const float *a, int n)
+{
+    if (n <= 128) return ss_np_pairwise_leaf(a, n);
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(ss_np_pairwise_sum<DEPTH - 1>(a, n2), ss_np_pairwise_sum<DEPTH - 1>(a + n2, n - n2));
+}
+template <>
+__device__ float ss_np_pairwise_sum<0>(const float *a, int n) { return ss_np_pairwise_leaf(a, n); }
 
-#define SS_MAX_WINDOW 11
+#define SS_MAX_WINDOW 31         /* base-level window side: kernel_size up to 32 (the oracle's range) */
+#define SS_SMALL_WINDOW 11       /* sides up to this use the instantiation with the small per-thread window buffers */
 
 // Base level, step 2a (reference pyramid.py:66-93): per (pixel, frame) the window entropy
 // -sum(v*log p[v]) and the window variance, both in numpy's evaluation order.
@@ -151,18 +163,20 @@ __device__ float ss_np_pairwise_sum(const float *a, int n)
 // log-probability of every base pixel's own value, indexed by the pixel; per_px == 2: lut[counts[f][v]], lut being
 // the table log(float32(c) / n_px) for every possible count c = 0 .. n_px (computed once by the host -- with numpy
 // when Python drives the library, so that it is numpy's log -- which removes the host round trip of the histogram).
+template <int MAXSIDE>
 __global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, int per_px, int h, int w,
                                        int num_values, int side, float *ent_out, float *dev_out,
                                        const unsigned int *counts = nullptr)
 {
+    constexpr int DEPTH = MAXSIDE * MAXSIDE <= 128 ? 0 : 3;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
     const int n_px = h * w;
     if (i >= n_px) return;
     const int y = i / w, x = i - y * w;
     const int pad = (side - 1) / 2, n = side * side;
-    float buf[SS_MAX_WINDOW * SS_MAX_WINDOW];
-    int vals[SS_MAX_WINDOW * SS_MAX_WINDOW];
+    float buf[MAXSIDE * MAXSIDE];
+    int vals[MAXSIDE * MAXSIDE];
     const int32_t *g = gray + (size_t)f * n_px;
     // log p[v]: either a per-frame table indexed by the value, or (16-bit stacks) the log-probability of
     // every base pixel's own value, indexed by the pixel
@@ -183,13 +197,13 @@ __global__ void ss_base_metrics_kernel(const int32_t *gray, const float *log_p, 
             ++c;
         }
     }
-    ent_out[(size_t)f * n_px + i] = __fmul_rn(-1.f, ss_np_pairwise_sum(buf, n));
+    ent_out[(size_t)f * n_px + i] = __fmul_rn(-1.f, ss_np_pairwise_sum<DEPTH>(buf, n));
     const float mean = (float)((double)s / (double)n);
     for (int k = 0; k < n; ++k) {
         const float d = __fsub_rn((float)vals[k], mean);
         buf[k] = __fmul_rn(d, d);
     }
-    dev_out[(size_t)f * n_px + i] = __fdiv_rn(ss_np_pairwise_sum(buf, n), (float)n);
+    dev_out[(size_t)f * n_px + i] = __fdiv_rn(ss_np_pairwise_sum<DEPTH>(buf, n), (float)n);
 }
 
 // Base level, step 2b (reference pyramid.py:102-105): running strict-'>' arg-max of entropy and of
@@ -1226,8 +1240,12 @@ static int ss_select_base_impl(ss_handle *h, const float *log_prob, int per_px)
     if ((rc = ss_timer_begin(h))) return rc;
     {
         dim3 g((nb + 63) / 64, h->n_pushed);
-        ss_base_metrics_kernel<<<g, 64, 0, h->s_comp>>>(h->gray, h->log_p, per_px, h->lh[h->L], h->lw[h->L],
-                                                          h->num_values, h->side, h->ent, h->dev);
+        if (h->side <= SS_SMALL_WINDOW)
+            ss_base_metrics_kernel<SS_SMALL_WINDOW><<<g, 64, 0, h->s_comp>>>(h->gray, h->log_p, per_px, h->lh[h->L], h->lw[h->L],
+                                                                             h->num_values, h->side, h->ent, h->dev);
+        else
+            ss_base_metrics_kernel<SS_MAX_WINDOW><<<g, 64, 0, h->s_comp>>>(h->gray, h->log_p, per_px, h->lh[h->L], h->lw[h->L],
+                                                                           h->num_values, h->side, h->ent, h->dev);
         h->launches++;
     }
     ss_base_select_kernel<<<(nb + 127) / 128, 128, 0, h->s_comp>>>(h->ent, h->dev, h->base, nb, h->n_pushed,
@@ -1265,8 +1283,12 @@ SS_EXPORT int ss_finish_base_device(ss_handle *h)
     const int nb = h->lh[h->L] * h->lw[h->L];
     if ((rc = ss_timer_begin(h))) return rc;
     dim3 g((nb + 63) / 64, h->n_pushed);
-    ss_base_metrics_kernel<<<g, 64, 0, h->s_comp>>>(h->gray, h->log_lut, 2, h->lh[h->L], h->lw[h->L], h->num_values,
-                                                      h->side, h->ent, h->dev, h->counts);
+    if (h->side <= SS_SMALL_WINDOW)
+        ss_base_metrics_kernel<SS_SMALL_WINDOW><<<g, 64, 0, h->s_comp>>>(h->gray, h->log_lut, 2, h->lh[h->L], h->lw[h->L],
+                                                                         h->num_values, h->side, h->ent, h->dev, h->counts);
+    else
+        ss_base_metrics_kernel<SS_MAX_WINDOW><<<g, 64, 0, h->s_comp>>>(h->gray, h->log_lut, 2, h->lh[h->L], h->lw[h->L],
+                                                                       h->num_values, h->side, h->ent, h->dev, h->counts);
     ss_base_select_kernel<<<(nb + 127) / 128, 128, 0, h->s_comp>>>(h->ent, h->dev, h->base, nb, h->n_pushed,
         h->cfg.frame_index_base, h->best_ve, h->best_ie, h->best_vd, h->best_id, h->pix_e, h->pix_d);
     h->launches += 2;
@@ -1320,8 +1342,12 @@ SS_EXPORT int ss_finish_select_base_f64(ss_handle *h, const double *log_prob, in
     int rc;
     if ((rc = ss_timer_begin(h))) return rc;
     dim3 g((nb + 63) / 64, h->n_pushed);
-    ss64_base_metrics_kernel<<<g, 64, 0, h->s_comp>>>(h->gray, h->logp64, per_px, h->lh[h->L], h->lw[h->L], h->num_values,
-                                                        h->side, h->ent64, h->dev64);
+    if (h->side <= SS_SMALL_WINDOW)
+        ss64_base_metrics_kernel<SS_SMALL_WINDOW><<<g, 64, 0, h->s_comp>>>(h->gray, h->logp64, per_px, h->lh[h->L], h->lw[h->L],
+                                                                           h->num_values, h->side, h->ent64, h->dev64);
+    else
+        ss64_base_metrics_kernel<SS_MAX_WINDOW><<<g, 64, 0, h->s_comp>>>(h->gray, h->logp64, per_px, h->lh[h->L], h->lw[h->L],
+                                                                         h->num_values, h->side, h->ent64, h->dev64);
     ss64_base_select_fuse_kernel<<<(nb + 127) / 128, 128, 0, h->s_comp>>>(h->ent64, h->dev64, h->base64, nb, h->n_pushed,
         h->cfg.frame_index_base, h->best_ie, h->best_id, h->fusedbase64);
     h->launches += 2;

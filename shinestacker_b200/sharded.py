@@ -140,3 +140,94 @@ class ShardedPyramidStack:
             a._push(i, img, ring)
         res = self.finish(len(local_frames), img0.shape[:2])
         return res if self.rank == self.root else None
+
+
+class ShardedDepthMapStack:
+    """``DepthMapStack`` with the frames of one stack sharded over the GPUs of a box, one per rank (SURVEY.md section 8f
+    rank 1 + 8e).  Every rank runs the energy, smoothing and blend kernels on its own contiguous run of the frames; the
+    three reductions over the stack (depth_map.py:88-115) cross the ranks: the maximum energy as one float through the
+    rendezvous, the per-pixel sum of the smoothed energies and the blended pyramid out of the peers' device memory
+    (include/shinestack_b200_depthmap.h, ssdm_shard_*).  ``focus_stack_arrays(local_frames, n_total)`` returns the
+    fused image on the root and None elsewhere.  Sums are associated rank by rank, so the image equals the single-GPU
+    one within float32 rounding (the stacker's 1-LSB contract); ``map_type='average'`` only."""
+
+    def __init__(self, rank, world, device=0, root=0, rendezvous=None, **kwargs):
+        from .depth_map import DepthMapStack      # pylint: disable=import-outside-toplevel
+        self.rank, self.world, self.device, self.root = rank, world, device, root
+        self.algo = DepthMapStack(device=device, **kwargs)
+        self._rdv = rendezvous
+        self._connected_handle = None
+        self.last_kernel_ms = None
+
+    def _rendezvous(self):
+        if self._rdv is None:
+            self._rdv = _rdv.TcpRendezvous.from_env() if self.world > 1 else _rdv.Single()
+        return self._rdv
+
+    def _connect(self):
+        a = self.algo
+        if self._connected_handle == a._h.value:
+            return
+        lib, rdv = a._lib, self._rendezvous()
+        count = lib.ssdm_shard_buffer_count(a._h)
+        blob = (ctypes.c_uint8 * (64 * count))()
+        _check(lib.ssdm_shard_export(a._h, blob))
+        blobs = b"".join(rdv.all_gather(bytes(blob)))
+        _check(lib.ssdm_shard_connect(a._h, blobs, self.world, self.rank, self.root))
+        self._connected_handle = a._h.value
+
+    def finish(self, n_local, shape, dtype, out=None):
+        """Everything after the pushes; all ranks must call it."""
+        a = self.algo
+        lib, h, rdv = a._lib, a._h, self._rendezvous()
+        local = ctypes.c_float()
+        _check(lib.ssdm_shard_local_max(h, ctypes.byref(local)))
+        gmax = max(np.frombuffer(b, np.float32)[0] for b in rdv.all_gather(np.float32(local.value).tobytes()))
+        self._connect()
+        _check(lib.ssdm_shard_finish_local(h, ctypes.c_float(gmax)))
+        _check(lib.ssdm_sync(h))
+        rdv.barrier()                       # every partial sum plane is complete
+        _check(lib.ssdm_shard_finish_weights(h))
+        for i in range(n_local):
+            _check(lib.ssdm_blend_frame(h, i))
+        _check(lib.ssdm_sync(h))
+        rdv.barrier()                       # every rank's share of the blended pyramid is complete
+        res = None
+        if self.rank == self.root:
+            res = out if out is not None else np.empty((shape[0], shape[1], 3), dtype=dtype)
+            _check(lib.ssdm_shard_finish_end(h, res.ctypes.data_as(ctypes.c_void_p), res.strides[0]))
+        else:
+            _check(lib.ssdm_shard_finish_end(h, None, 0))
+        rdv.barrier()                       # the root has read the peers' pyramids: they may be overwritten again
+        ms = ctypes.c_float()
+        _check(lib.ssdm_kernel_time_ms(h, ctypes.byref(ms)))
+        self.last_kernel_ms = ms.value
+        return res
+
+    def focus_stack_arrays(self, local_frames, n_total=None):
+        a = self.algo
+        local_frames = list(local_frames)
+        img0 = local_frames[0]
+        a._ensure_handle(img0.shape, img0.dtype, len(local_frames))
+        a._pitch = img0.shape[1] * 3 * img0.dtype.itemsize
+        a._report_steps = False
+        shape2, dtype = img0.shape[:2], img0.dtype
+
+        def load_into(i, view):
+            from .pyramid import stage_frame      # pylint: disable=import-outside-toplevel
+            img = local_frames[i]
+            if img is not None and img.shape == img0.shape and img.dtype == dtype:
+                stage_frame(img, view)
+            return img
+
+        try:
+            ring = a._staging(img0.nbytes, 2 * max(a.decode_threads, 2))
+            a._stream(len(local_frames), load_into, ring, lambda _i, img: a._validate(img, shape2, dtype))
+            return self.finish(len(local_frames), shape2, dtype)
+        except BaseException:
+            if a._h is not None:
+                a._lib.ssdm_reset(a._h)
+            raise
+
+    def close(self):
+        self.algo.close()

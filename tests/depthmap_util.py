@@ -74,6 +74,13 @@ class Emu:
             lib.emu_dm_blend.argtypes = [vp, i]
             lib.emu_dm_finish_end.argtypes = [vp, vp, sz]
             lib.emu_dm_get_plane.argtypes = [vp, i, i, vp]
+            lib.emu_dm_shard_local_max.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+            lib.emu_dm_shard_finish_local.argtypes = [vp, ctypes.c_float]
+            lib.emu_dm_shard_count.argtypes = [vp]
+            lib.emu_dm_shard_ptrs.argtypes = [vp, ctypes.POINTER(vp)]
+            lib.emu_dm_shard_connect.argtypes = [vp, ctypes.POINTER(vp), i, i, i]
+            lib.emu_dm_shard_finish_weights.argtypes = [vp]
+            lib.emu_dm_shard_finish_end.argtypes = [vp, vp, sz]
             cls._lib = lib
         return cls._lib
 
@@ -132,3 +139,51 @@ def emu_focus_stack(frames, stages=None, **kwargs):
         return e.finish(stages)
     finally:
         e.close()
+
+
+def emu_sharded_focus_stack(frames, world, root=0, stages=None, **kwargs):
+    """The sharded call sequence of include/shinestack_b200_depthmap.h with `world` handles of the host build in one
+    process (contiguous runs of the frames, plain pointers instead of IPC handles); returns the root's image."""
+    from shinestacker_b200.sharded import shard_range
+    h, w = frames[0].shape[:2]
+    lib = Emu.lib()
+    ranks = []
+    for r in range(world):
+        a, b = shard_range(len(frames), r, world)
+        e = Emu(h, w, frames[0].dtype, max(b - a, 1), **kwargs)
+        for f in frames[a:b]:
+            assert e.push(f) == 0, e.error()
+        ranks.append((e, a, b))
+    try:
+        maxima = []
+        for e, _, _ in ranks:
+            m = ctypes.c_float()
+            assert lib.emu_dm_shard_local_max(e.p, ctypes.byref(m)) == 0, e.error()
+            maxima.append(m.value)
+        gmax = max(maxima)
+        count = lib.emu_dm_shard_count(ranks[0][0].p)
+        table = (ctypes.c_void_p * (world * count))()
+        for r, (e, _, _) in enumerate(ranks):
+            own = (ctypes.c_void_p * count)()
+            assert lib.emu_dm_shard_ptrs(e.p, own) == 0, e.error()
+            table[r * count:(r + 1) * count] = list(own)
+        for r, (e, _, _) in enumerate(ranks):
+            assert lib.emu_dm_shard_connect(e.p, table, world, r, root) == 0, e.error()
+            assert lib.emu_dm_shard_finish_local(e.p, ctypes.c_float(gmax)) == 0, e.error()
+        for e, _, _ in ranks:                                   # "barrier": every partial sum exists
+            assert lib.emu_dm_shard_finish_weights(e.p) == 0, e.error()
+        if stages is not None:
+            stages["weights"] = np.array([e.plane("weights", i) for e, a, b in ranks for i in range(b - a)])
+        for e, a, b in ranks:
+            for i in range(b - a):
+                assert lib.emu_dm_blend(e.p, i) == 0, e.error()
+        out = np.empty((h, w, 3), frames[0].dtype)
+        for r, (e, _, _) in enumerate(ranks):
+            if r != root:
+                assert lib.emu_dm_shard_finish_end(e.p, None, 0) == 0, e.error()
+        e = ranks[root][0]
+        assert lib.emu_dm_shard_finish_end(e.p, out.ctypes.data, out.strides[0]) == 0, e.error()
+        return out
+    finally:
+        for e, _, _ in ranks:
+            e.close()

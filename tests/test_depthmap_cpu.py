@@ -268,3 +268,28 @@ def test_bilateral_forms_agree_with_the_oracle(monkeypatch):
         out = du.emu_focus_stack(frames, stages=st)
         assert np.abs(st["weights"] - ost["weights"]).max() < 1e-6, env
         du.assert_within_1lsb(out, ref, str(env), max_frac=0.2)
+
+
+@pytest.mark.parametrize("world,root,n,dtype,kwargs", [
+    (2, 0, 5, np.uint8, {}),
+    (3, 2, 7, np.uint16, {"levels": 4}),
+    (4, 1, 4, np.uint8, {"energy": "sobel", "smooth_size": 0}),       # one frame per rank, no smoothing
+    (1, 0, 3, np.uint8, {}),                                          # a "box" of one GPU goes the same way
+])
+def test_frames_sharded_over_ranks_give_the_single_handle_result_within_rounding(world, root, n, dtype, kwargs):
+    frames = synthetic.make_stack(n, 60, 90, np.dtype(dtype), seed=world + n)
+    st, sst = {}, {}
+    single = du.emu_focus_stack(frames, stages=st, **kwargs)
+    sharded = du.emu_sharded_focus_stack(frames, world, root, stages=sst, **kwargs)
+    # the sums over the stack are associated rank by rank: float32 rounding only
+    assert np.abs(st["weights"] - sst["weights"]).max() < 1e-6
+    du.assert_within_1lsb(sharded, single, "sharded", max_frac=0.02)
+    du.assert_within_1lsb(sharded, dmo.focus_stack(frames, **kwargs), "sharded vs oracle", max_frac=0.2)
+    if world == 1:
+        assert np.array_equal(sharded, single)
+
+
+def test_sharded_stacks_implement_the_average_map_only():
+    frames = synthetic.make_stack(2, 40, 50, np.dtype(np.uint8), seed=1)
+    with pytest.raises(AssertionError, match="average"):
+        du.emu_sharded_focus_stack(frames, 2, map_type="max")

@@ -108,3 +108,113 @@ def test_full_size_identity_property():
     img = synthetic.make_noise_stack(1, 3072, 4096, np.uint8, 81)[0]
     out = DepthMapStack().focus_stack_arrays([img] * 3)
     du.assert_within_1lsb(out, img, "identical frames", max_frac=0.5)
+
+
+def _sharded_on_one_gpu(frames, world, root, **kwargs):
+    """The sharded call sequence with `world` handles on ONE device in one process (plain device pointers instead of
+    IPC handles) -- the kernels and the order of the phases are those of a multi-GPU run."""
+    import ctypes
+    from shinestacker_b200.sharded import shard_range
+    from shinestacker_b200.pyramid import _check
+    algos = []
+    for r in range(world):
+        a, b = shard_range(len(frames), r, world)
+        algo = DepthMapStack(**kwargs)
+        algo._ensure_handle(frames[0].shape, frames[0].dtype, b - a)
+        ring = algo._staging(frames[0].nbytes, 4)
+        for i, f in enumerate(frames[a:b]):
+            algo._push(i, f, ring)
+        algos.append((algo, b - a))
+    lib = algos[0][0]._lib
+    maxima = []
+    for algo, _ in algos:
+        m = ctypes.c_float()
+        _check(lib.ssdm_shard_local_max(algo._h, ctypes.byref(m)))
+        maxima.append(m.value)
+    count = lib.ssdm_shard_buffer_count(algos[0][0]._h)
+    table = (ctypes.c_void_p * (world * count))()
+    for r, (algo, _) in enumerate(algos):
+        own = (ctypes.c_void_p * count)()
+        _check(lib.ssdm_shard_ptrs(algo._h, own))
+        table[r * count:(r + 1) * count] = list(own)
+    for r, (algo, _) in enumerate(algos):
+        _check(lib.ssdm_shard_connect_ptrs(algo._h, table, world, r, root))
+        _check(lib.ssdm_shard_finish_local(algo._h, ctypes.c_float(max(maxima))))
+    for algo, _ in algos:
+        _check(lib.ssdm_sync(algo._h))
+    for algo, _ in algos:
+        _check(lib.ssdm_shard_finish_weights(algo._h))
+    weights = np.array([algo.get_plane("weights", i) for algo, n in algos for i in range(n)])
+    for algo, n in algos:
+        for i in range(n):
+            _check(lib.ssdm_blend_frame(algo._h, i))
+        _check(lib.ssdm_sync(algo._h))
+    out = np.empty_like(frames[0])
+    for r, (algo, _) in enumerate(algos):
+        if r != root:
+            _check(lib.ssdm_shard_finish_end(algo._h, None, 0))
+    _check(lib.ssdm_shard_finish_end(algos[root][0]._h, out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+    for algo, _ in algos:
+        algo.close()
+    return out, weights
+
+
+@pytest.mark.parametrize("world,root,n,h,w,dtype,kwargs", [
+    (2, 0, 5, 150, 203, np.uint8, {}),
+    (3, 2, 8, 130, 260, np.uint16, {"levels": 4}),
+    (4, 1, 9, 100, 136, np.uint8, {"energy": "sobel"}),
+])
+def test_sharded_phases_equal_the_host_build_and_the_single_handle_result(world, root, n, h, w, dtype, kwargs):
+    frames = synthetic.make_stack(n, h, w, np.dtype(dtype), seed=90 + world)
+    out, weights = _sharded_on_one_gpu(frames, world, root, **kwargs)
+    st = {}
+    emu = du.emu_sharded_focus_stack(frames, world, root, stages=st, **kwargs)
+    assert np.array_equal(out, emu) and np.array_equal(weights, st["weights"])      # same code, same order
+    single = DepthMapStack(**kwargs)
+    ref = single.focus_stack_arrays(frames)
+    ref_w = np.array([single.get_plane("weights", i) for i in range(n)])
+    assert np.abs(weights - ref_w).max() < 1e-6
+    du.assert_within_1lsb(out, ref, "sharded vs one handle", max_frac=0.02)
+
+
+def test_sharded_stack_of_one_rank_is_the_plain_stack():
+    from shinestacker_b200.sharded import ShardedDepthMapStack
+    frames = synthetic.make_stack(4, 120, 168, np.dtype(np.uint8), seed=95)
+    algo = ShardedDepthMapStack(0, 1)
+    assert np.array_equal(algo.focus_stack_arrays(frames, 4), DepthMapStack().focus_stack_arrays(frames))
+    assert np.array_equal(algo.focus_stack_arrays(frames[:3], 3), DepthMapStack().focus_stack_arrays(frames[:3]))
+    algo.close()
+
+
+def test_two_processes_share_one_stack_through_cuda_ipc():
+    # two ranks (both on device 0 when the box has one GPU) run the real multi-process path: TCP rendezvous, CUDA IPC
+    # handles of the partial-sum plane and the blended pyramid, barriers between the phases
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port - 36))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(root, "tools", "time_depthmap_sharded.py"), "--frames", "7",
+                                       "--height", "240", "--width", "320", "--steps", "1", "--check"],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, e = p.communicate(timeout=180)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        assert p.returncode == 0, e[-2000:]
+        outs.append(o)
+    line = json.loads(outs[0].strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["vs_one_handle"]["max_abs_diff_lsb"] <= 1
+    assert line["vs_one_handle"]["fraction_differing"] < 0.02

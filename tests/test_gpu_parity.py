@@ -48,6 +48,27 @@ def test_cuda_matches_oracle(oracle, gen, n, h, w, dtype, seed, batch):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("n,h,w,dtype,seed,kwargs", [
+    (3, 150, 200, np.uint8, 61, {"kernel_size": 13}),         # 169 values per window: one halving of numpy's pairwise sum
+    (3, 300, 260, np.uint16, 62, {"kernel_size": 20}),        # 361
+    (2, 280, 300, np.uint8, 63, {"kernel_size": 32}),         # 961: the widest window (side 31)
+    (2, 150, 200, np.uint8, 64, {"kernel_size": 17, "float_type": "float-64"}),
+    (2, 150, 200, np.uint8, 65, {"kernel_size": 12}),         # the widest window of the small instantiation
+])
+def test_wide_base_windows(oracle, n, h, w, dtype, seed, kwargs):
+    frames = synthetic.make_noise_stack(n, h, w, dtype, seed)
+    ref, info = oracle.focus_stack(frames, **kwargs)
+    out, maps, _ = run_gpu(frames, **kwargs)
+    assert np.array_equal(out, ref)
+    assert np.array_equal(maps["best_e"], info["best_e"]) and np.array_equal(maps["best_d"], info["best_d"])
+
+
+def test_window_wider_than_the_oracle_range_is_rejected():
+    from shinestacker_b200 import InvalidOptionError
+    with pytest.raises(InvalidOptionError):
+        run_gpu(synthetic.make_noise_stack(2, 100, 100, np.uint8, 66), kernel_size=34)
+
+
 def test_batch_size_does_not_change_the_result():
     frames = synthetic.make_noise_stack(11, 200, 264, np.uint8, 41)
     base, maps0, _ = run_gpu(frames, batch_frames=11)

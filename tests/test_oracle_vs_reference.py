@@ -57,6 +57,11 @@ CASES = [
     ("noise", 3, 131, 200, np.uint8, 29, {"float_type": "float-64"}),
     ("stack", 4, 260, 376, np.uint16, 30, {"float_type": "float-64"}),
     ("noise", 3, 140, 133, np.uint16, 31, {"float_type": "float-64", "gen_kernel": 0.3, "kernel_size": 3}),
+    # base windows above 128 values: numpy's pairwise sum halves the run (13 -> 169, 20 -> 361, 32 -> 961 values)
+    ("noise", 3, 150, 200, np.uint8, 32, {"kernel_size": 13}),
+    ("stack", 3, 300, 260, np.uint16, 33, {"kernel_size": 20}),
+    ("noise", 2, 280, 300, np.uint8, 34, {"kernel_size": 32}),
+    ("noise", 2, 150, 200, np.uint8, 35, {"kernel_size": 17, "float_type": "float-64"}),
 ]
 
 

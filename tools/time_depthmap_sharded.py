@@ -50,13 +50,18 @@ def main():
         (n_local,) + frames[0].shape)
     host[:] = frames[f0:f1]
     pitch = a.width * 3 * dt.itemsize
-    out = None
+    out, out_pin = None, ctypes.c_void_p()
+    if rank == 0:                               # the root's result lands in pinned memory
+        _check(lib.ss_host_alloc(ctypes.byref(out_pin), frames[0].nbytes))
+        out_buf = np.frombuffer((ctypes.c_uint8 * frames[0].nbytes).from_address(out_pin.value), dt).reshape(frames[0].shape)
+    else:
+        out_buf = None
 
     def step():
         dm._ensure_handle(frames[0].shape, dt, n_local)        # resets the handle
         for i in range(n_local):
             _check(lib.ssdm_push_frame(dm._h, host[i].ctypes.data_as(ctypes.c_void_p), pitch))
-        return algo.finish(n_local, frames[0].shape[:2], dt)
+        return algo.finish(n_local, frames[0].shape[:2], dt, out=out_buf)
 
     step()
     times, dev = [], []
@@ -83,6 +88,8 @@ def main():
     rdv.barrier()
     algo.close()
     lib.ss_host_free(pin)
+    if out_pin.value:
+        lib.ss_host_free(out_pin)
     rdv.close()
 
 

@@ -83,28 +83,56 @@ def source_coords(m, h, w):
     return np.rint(fX).astype(np.int64), np.rint(fY).astype(np.int64)
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 values is exact in float64."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
 def _float_perspective_u16(img, m, border, bval):
+    """cv2 4.13 warpPerspective of uint16 images (found by probing cv2, tests/test_align_cpu.py pins it): quotient
+    X/W and its fractional part in float64, the fraction as float32, vertical interpolation first, every step one
+    fused multiply-add, round half to even.  Where one of the four taps lies outside the image cv2 writes the border
+    value (BORDER_CONSTANT) or leaves the destination untouched (BORDER_REPLICATE); the latter is modelled as
+    replication of the edge pixel."""
     h, w = img.shape[:2]
     f32 = np.float32
     Mi = invert_homography(m)
     xs = np.arange(w, dtype=np.float64)
     ys = np.arange(h, dtype=np.float64)[:, None]
-    W = Mi[6] * xs + (Mi[7] * ys + Mi[8])
-    X = ((Mi[0] * xs + (Mi[1] * ys + Mi[2])) / W).astype(f32)
-    Y = ((Mi[3] * xs + (Mi[4] * ys + Mi[5])) / W).astype(f32)
-    sx, sy = np.floor(X).astype(np.int64), np.floor(Y).astype(np.int64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        W = Mi[6] * xs + (Mi[7] * ys + Mi[8])
+        X = (Mi[0] * xs + (Mi[1] * ys + Mi[2])) / W
+        Y = (Mi[3] * xs + (Mi[4] * ys + Mi[5])) / W
+    X = np.where(X > -1e9, np.where(X < 1e9, X, 1e9), -1e9)
+    Y = np.where(Y > -1e9, np.where(Y < 1e9, Y, 1e9), -1e9)
+    sx = np.clip(np.floor(X), -32768, 32767).astype(np.int64)
+    sy = np.clip(np.floor(Y), -32768, 32767).astype(np.int64)
     fx = (X - np.floor(X)).astype(f32)[..., None]
     fy = (Y - np.floor(Y)).astype(f32)[..., None]
 
     def px(yy, xx):
-        v = img[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)].astype(f32)
-        if border == BORDER_CONSTANT:
-            v[~((yy >= 0) & (yy < h) & (xx >= 0) & (xx < w))] = bval
-        return v
+        return img[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)].astype(f32)
     p00, p01, p10, p11 = px(sy, sx), px(sy, sx + 1), px(sy + 1, sx), px(sy + 1, sx + 1)
-    top = p00 + fx * (p01 - p00)
-    bot = p10 + fx * (p11 - p10)
-    return np.clip(np.rint(top + fy * (bot - top)), 0, 65535).astype(np.uint16)
+    fyb, fxb = np.broadcast_to(fy, p00.shape), np.broadcast_to(fx, p00.shape)
+    left = _fma32(fyb, p10 - p00, p00)
+    right = _fma32(fyb, p11 - p01, p01)
+    out = np.clip(np.rint(_fma32(fxb, right - left, left)), 0, 65535).astype(np.uint16)
+    if border == BORDER_CONSTANT:
+        all_in = (sx >= 0) & (sx + 1 < w) & (sy >= 0) & (sy + 1 < h)
+        out[~all_in] = bval.astype(np.uint16)
+    return out
+
+
+def float_perspective_all_taps_inside(m, h, w):
+    """Mask of the destination pixels whose four taps lie in the image (where cv2's uint16 warpPerspective is defined
+    for every border mode)."""
+    Mi = invert_homography(m)
+    xs = np.arange(w, dtype=np.float64)
+    ys = np.arange(h, dtype=np.float64)[:, None]
+    W = Mi[6] * xs + (Mi[7] * ys + Mi[8])
+    sx = np.floor((Mi[0] * xs + (Mi[1] * ys + Mi[2])) / W)
+    sy = np.floor((Mi[3] * xs + (Mi[4] * ys + Mi[5])) / W)
+    return (sx >= 0) & (sx + 1 < w) & (sy >= 0) & (sy + 1 < h)
 
 
 def warp(img, m, border=BORDER_REPLICATE, border_value=(0, 0, 0, 0), return_mask=False):

@@ -63,6 +63,7 @@ struct AlWarp {
     {
         long long X, Y;
         float ffx = 0.f, ffy = 0.f;
+        long long isx = 0, isy = 0;             // float path: integer source position (floor of the exact quotient)
         if (!persp) {
             X = ((long long)x0[y] + adelta[x]) >> 5;
             Y = ((long long)y0[y] + bdelta[x]) >> 5;
@@ -72,17 +73,19 @@ struct AlWarp {
             const double Y0 = m[3] * dx + (m[4] * dy + m[5]);
             double W = m[6] * dx + (m[7] * dy + m[8]);
             if (float_persp) {
-                const float fX = (float)(X0 / W), fY = (float)(Y0 / W);
-                const float flx = floorf(fX), fly = floorf(fY);
-                ffx = fX - flx; ffy = fY - fly;
-                X = (long long)flx * 32; Y = (long long)fly * 32;
-            } else {
-                W = W != 0.0 ? 32.0 / W : 0.0;
-                double fX = X0 * W, fY = Y0 * W;
-                fX = fX < -2147483648.0 ? -2147483648.0 : (fX > 2147483647.0 ? 2147483647.0 : fX);
-                fY = fY < -2147483648.0 ? -2147483648.0 : (fY > 2147483647.0 ? 2147483647.0 : fY);
-                X = al_rint_ll(fX); Y = al_rint_ll(fY);
+                // cv2 4.13, uint16 + warpPerspective: quotient and its fraction in float64, the fraction then as float32
+                double qx = X0 / W, qy = Y0 / W;
+                qx = qx > -1e9 ? (qx < 1e9 ? qx : 1e9) : -1e9;       // also catches NaN (W = 0)
+                qy = qy > -1e9 ? (qy < 1e9 ? qy : 1e9) : -1e9;
+                const double flx = floor(qx), fly = floor(qy);
+                ffx = (float)(qx - flx); ffy = (float)(qy - fly);
+                isx = (long long)flx; isy = (long long)fly;
             }
+            W = W != 0.0 ? 32.0 / W : 0.0;      // the 1/32-pixel coordinates: every other type, and the mask of this one
+            double fX = X0 * W, fY = Y0 * W;
+            fX = fX < -2147483648.0 ? -2147483648.0 : (fX > 2147483647.0 ? 2147483647.0 : fX);
+            fY = fY < -2147483648.0 ? -2147483648.0 : (fY > 2147483647.0 ? 2147483647.0 : fY);
+            X = al_rint_ll(fX); Y = al_rint_ll(fY);
         }
         if (!float_persp) {
             // interior fast path: all four taps inside the image (the overwhelming majority of the pixels)
@@ -126,13 +129,38 @@ struct AlWarp {
         const int inside[4] = {in_x0 && in_y0, in_x1 && in_y0, in_x0 && in_y1, in_x1 && in_y1};
         const int cx0 = sx < 0 ? 0 : (sx > w - 1 ? w - 1 : sx), cx1 = sx + 1 < 0 ? 0 : (sx + 1 > w - 1 ? w - 1 : sx + 1);
         const int cy0 = sy < 0 ? 0 : (sy > h - 1 ? h - 1 : sy), cy1 = sy + 1 < 0 ? 0 : (sy + 1 > h - 1 ? h - 1 : sy + 1);
-        const T *r0 = row(cy0), *r1 = row(cy1);
         T *o = (T *)((char *)dst + (long long)y * dpitch) + 3 * x;
         if (fill_list) {
             int s = 0;
             for (int i = 0; i < 4; ++i) s += inside[i] ? wt[i] : 0;
             if (s < 512) al_append(fill_count, fill_list, y * w + x);
         }
+        if (float_persp) {
+            // vertical interpolation first, each step one fma, round half to even: bit-identical to cv2 4.13 wherever all
+            // four taps lie in the image.  With a tap outside, cv2 writes the border VALUE (BORDER_CONSTANT) or nothing at
+            // all (BORDER_REPLICATE: the destination keeps what it held); here REPLICATE replicates the edge pixel.
+            const long long lx = isx < -32768 ? -32768 : (isx > 32767 ? 32767 : isx), ly = isy < -32768 ? -32768 : (isy > 32767 ? 32767 : isy);
+            const int tx = (int)lx, ty = (int)ly;
+            const bool all_in = tx >= 0 && tx + 1 < w && ty >= 0 && ty + 1 < h;
+            const int ax0 = tx < 0 ? 0 : (tx > w - 1 ? w - 1 : tx), ax1 = tx + 1 < 0 ? 0 : (tx + 1 > w - 1 ? w - 1 : tx + 1);
+            const int ay0 = ty < 0 ? 0 : (ty > h - 1 ? h - 1 : ty), ay1 = ty + 1 < 0 ? 0 : (ty + 1 > h - 1 ? h - 1 : ty + 1);
+            const T *q0 = row(ay0), *q1 = row(ay1);
+            for (int c = 0; c < 3; ++c) {
+                if (border_const && !all_in) { o[c] = (T)bval[c]; continue; }
+                const float v00 = (float)q0[3 * ax0 + c], v01 = (float)q0[3 * ax1 + c];
+                const float v10 = (float)q1[3 * ax0 + c], v11 = (float)q1[3 * ax1 + c];
+                const float l = ss_fma(ffy, ss_add(v10, -v00), v00), r = ss_fma(ffy, ss_add(v11, -v01), v01);
+                float t = al_rintf(ss_fma(ffx, ss_add(r, -l), l));
+                t = t < 0.f ? 0.f : (t > 65535.f ? 65535.f : t);
+                o[c] = (T)(int)t;
+            }
+            if (dst2) {
+                T *o2 = (T *)((char *)dst2 + (long long)y * dpitch) + 3 * x;
+                o2[0] = o[0]; o2[1] = o[1]; o2[2] = o[2];
+            }
+            return;
+        }
+        const T *r0 = row(cy0), *r1 = row(cy1);
         for (int c = 0; c < 3; ++c) {
             int v[4] = {(int)r0[3 * cx0 + c], (int)r0[3 * cx1 + c], (int)r1[3 * cx0 + c], (int)r1[3 * cx1 + c]};
             if (border_const)
@@ -140,12 +168,6 @@ struct AlWarp {
             if (sizeof(T) == 1) {
                 const int t = ((v[0] * wt[0] + v[1] * wt[1] + v[2] * wt[2] + v[3] * wt[3]) * 32 + 16384) >> 15;
                 o[c] = (T)(t > 255 ? 255 : t);
-            } else if (float_persp) {
-                const float top = ss_add((float)v[0], ss_mul(ffx, ss_add((float)v[1], -(float)v[0])));
-                const float bot = ss_add((float)v[2], ss_mul(ffx, ss_add((float)v[3], -(float)v[2])));
-                float t = al_rintf(ss_add(top, ss_mul(ffy, ss_add(bot, -top))));
-                t = t < 0.f ? 0.f : (t > 65535.f ? 65535.f : t);
-                o[c] = (T)(int)t;
             } else {
                 float t = ss_mul((float)v[0], ss_mul((float)wt[0], 0.0009765625f));
                 t = ss_add(t, ss_mul((float)v[1], ss_mul((float)wt[1], 0.0009765625f)));

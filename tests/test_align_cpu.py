@@ -33,18 +33,32 @@ def test_oracle_and_host_build_of_the_kernels_match_cv2(dtype, name, mode):
     emu.close()
 
 
-def test_uint16_homography_is_close_on_in_image_pixels():
-    # cv2 4.13 routes uint16 warpPerspective through float kernels (and leaves out-of-image pixels unwritten
-    # with BORDER_REPLICATE): not bit-pinned; the float model agrees to 1 LSB where the source is in the image
-    yy, xx = np.mgrid[0:160, 0:220]
-    img = np.stack([xx * 250 + yy * 17, xx * 5 + yy * 300, xx * 111 + yy * 122], -1).astype(np.uint16)
-    m = au.homography(0.7, 1.01, 5.5, -8.25)
-    ref = cv2.warpPerspective(img, m, (220, 160), borderMode=cv2.BORDER_REPLICATE)
-    emu = au.EmuWarper(160, 220, np.uint16)
-    out = emu.warp(img, m, "BORDER_REPLICATE")
-    assert np.array_equal(out, ao.warp(img, m, ao.BORDER_REPLICATE))
-    inner = (slice(20, 140), slice(20, 200))
-    assert np.abs(out[inner].astype(int) - ref[inner].astype(int)).max() <= 1
+def test_uint16_homography_is_pinned_where_cv2_defines_it():
+    # cv2 4.13 routes uint16 warpPerspective through float kernels: bit-exact wherever the four taps lie in the image
+    # (every border mode) and everywhere with BORDER_CONSTANT (a tap outside -> the border value).  With
+    # BORDER_REPLICATE cv2 leaves the other pixels of the destination UNWRITTEN (checked with a sentinel): there the
+    # model replicates the edge pixel.
+    rng = np.random.default_rng(11)
+    for trial in range(5):
+        h, w = int(rng.integers(60, 200)), int(rng.integers(60, 260))
+        img = rng.integers(0, 65536, (h, w, 3)).astype(np.uint16)
+        m = au.homography(rng.uniform(-10, 10), rng.uniform(0.9, 1.1), rng.uniform(-15, 15), rng.uniform(-15, 15),
+                          rng.uniform(-3e-5, 3e-5), rng.uniform(-3e-5, 3e-5))
+        inside = ao.float_perspective_all_taps_inside(m, h, w)
+        assert inside.mean() > 0.5
+        emu = au.EmuWarper(h, w, np.uint16)
+        bval = (1000.0, 20000.0, 65535.0, 0.0)
+        ref = cv2.warpPerspective(img, m, (w, h), borderMode=cv2.BORDER_CONSTANT, borderValue=bval)
+        out = emu.warp(img, m, "BORDER_CONSTANT", bval)
+        assert np.array_equal(out, ref)
+        assert np.array_equal(out, ao.warp(img, m, ao.BORDER_CONSTANT, bval))
+        sentinel = np.full((h, w, 3), 12345, np.uint16)
+        ref = cv2.warpPerspective(img, m, (w, h), dst=sentinel.copy(), borderMode=cv2.BORDER_REPLICATE)
+        out = emu.warp(img, m, "BORDER_REPLICATE")
+        assert np.array_equal(out, ao.warp(img, m, ao.BORDER_REPLICATE))
+        assert np.array_equal(out[inside], ref[inside])
+        assert (ref[~inside] == 12345).all()                     # cv2 does not write them
+        emu.close()
 
 
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16])

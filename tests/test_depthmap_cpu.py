@@ -293,3 +293,91 @@ def test_sharded_stacks_implement_the_average_map_only():
     frames = synthetic.make_stack(2, 40, 50, np.dtype(np.uint8), seed=1)
     with pytest.raises(AssertionError, match="average"):
         du.emu_sharded_focus_stack(frames, 2, map_type="max")
+
+
+class _EmuNative:
+    """The ssdm_* entry points ShardedDepthMapStack.finish uses, served by the host build of the kernels: the real host
+    orchestration (rendezvous, barriers, phase order) runs on a CPU-only box.  'IPC handles' are plain pointers, valid
+    because the ranks are threads of one process."""
+
+    def __init__(self):
+        self.emu = du.Emu.lib()
+
+    def ssdm_shard_local_max(self, h, ref):
+        return self.emu.emu_dm_shard_local_max(h, ref)
+
+    def ssdm_shard_finish_local(self, h, gmax):
+        return self.emu.emu_dm_shard_finish_local(h, gmax)
+
+    def ssdm_shard_buffer_count(self, h):
+        return self.emu.emu_dm_shard_count(h)
+
+    def ssdm_shard_export(self, h, blob):
+        import ctypes
+        count = self.emu.emu_dm_shard_count(h)
+        ptrs = (ctypes.c_void_p * count)()
+        rc = self.emu.emu_dm_shard_ptrs(h, ptrs)
+        for k in range(count):
+            blob[64 * k:64 * k + 8] = list((ptrs[k] or 0).to_bytes(8, "little"))
+        return rc
+
+    def ssdm_shard_connect(self, h, blobs, world, rank, root):
+        import ctypes
+        count = self.emu.emu_dm_shard_count(h)
+        table = (ctypes.c_void_p * (world * count))()
+        for i in range(world * count):
+            table[i] = int.from_bytes(blobs[64 * i:64 * i + 8], "little")
+        return self.emu.emu_dm_shard_connect(h, table, world, rank, root)
+
+    def ssdm_sync(self, h):
+        return 0
+
+    def ssdm_shard_finish_weights(self, h):
+        return self.emu.emu_dm_shard_finish_weights(h)
+
+    def ssdm_blend_frame(self, h, i):
+        return self.emu.emu_dm_blend(h, i)
+
+    def ssdm_shard_finish_end(self, h, out, pitch):
+        return self.emu.emu_dm_shard_finish_end(h, out, pitch)
+
+    def ssdm_kernel_time_ms(self, h, ref):
+        return 0
+
+
+def test_sharded_host_orchestration_with_two_ranks_over_tcp():
+    import ctypes
+    import socket
+    import threading
+    from shinestacker_b200 import rendezvous
+    from shinestacker_b200.sharded import ShardedDepthMapStack, shard_range
+    frames = synthetic.make_stack(5, 50, 70, np.dtype(np.uint8), seed=12)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    results, errors = {}, []
+
+    def rank_main(rank):
+        try:
+            rdv = rendezvous.TcpRendezvous(rank, 2, "127.0.0.1", port, timeout=30)
+            a, b = shard_range(len(frames), rank, 2)
+            emu = du.Emu(50, 70, np.uint8, b - a)
+            for f in frames[a:b]:
+                assert emu.push(f) == 0
+            st = ShardedDepthMapStack(rank, 2, rendezvous=rdv, root=1)
+            st.algo._lib, st.algo._h = _EmuNative(), ctypes.c_void_p(emu.p)
+            results[rank] = st.finish(b - a, (50, 70), np.dtype(np.uint8))
+            st.algo._h = None
+            rdv.close()
+            emu.close()
+        except Exception as e:  # pylint: disable=broad-except
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    assert not errors, errors
+    assert results[0] is None                                 # rank 1 is the root
+    assert np.array_equal(results[1], du.emu_sharded_focus_stack(frames, 2, root=1))

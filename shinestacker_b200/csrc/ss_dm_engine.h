@@ -359,7 +359,8 @@ struct DmEngine {
     // ---- frames of one stack sharded over ranks ------------------------------------------------------------------
     // Every rank pushes its own contiguous run of the frames.  Three values cross the ranks: the maximum energy (a
     // float, through the host), the per-pixel sum of the smoothed energies (each rank's partial sum, read from the
-    // peers' memory) and the blended pyramid (summed on the root out of the peers' memory).  The sums are taken
+    // peers' memory) and the blended pyramid (every rank sums one band of rows out of the peers' memory, the root then
+    // collects the bands).  The sums are taken
     // rank by rank, i.e. in stack order but associated differently from one long chain: float32 rounding, covered by
     // the 1-LSB contract of this stacker.  map_type 'average' only.
     int shard_local_max(float *out)
@@ -418,16 +419,32 @@ struct DmEngine {
         blended = 0; launched_blend = 0;
         return DM_OK;
     }
-    // after every rank has blended its frames (barrier): the root sums the pyramids and collapses; others return
+    // after every rank has blended its frames (barrier): every rank reduces its band of rows of every level
+    int shard_reduce_band()
+    {
+        if (!finished || blended != n) return fail(DM_ERR_STATE, "reduce before every frame was blended");
+        if (world == 1) return DM_OK;
+        for (int l = 0; l < L; ++l) {
+            const int y0 = (int)((long long)rank * lh[l] / world), y1 = (int)((long long)(rank + 1) * lh[l] / world);
+            if (y1 <= y0) continue;
+            DmPeerBandSum k;
+            for (int r = 0; r < DM_MAX_RANKS; ++r) k.acc[r] = r < world ? peer_acc[r][l] : nullptr;
+            k.world = world; k.out = acc[l]; k.h = lh[l]; k.w = lw[l]; k.y0 = y0; k.y1 = y1;
+            const int rc = be.launch(k, lw[l], 3 * (y1 - y0), 1);
+            if (rc) return fail(rc, be.last_error());
+        }
+        return DM_OK;
+    }
+    // after every rank has reduced its band (barrier): the root collects the bands, collapses and stores; others return
     int shard_finish_end(void *out_bgr, size_t out_pitch)
     {
         if (!finished || blended != n) return fail(DM_ERR_STATE, "finish_end before every frame was blended");
         if (rank != root) { const int rc = be.sync(); return rc ? fail(rc, be.last_error()) : DM_OK; }
         if (!collapsed && world > 1) {
             for (int l = 0; l < L; ++l) {
-                DmPeerAccSum k;
+                DmPeerBandGather k;
                 for (int r = 0; r < DM_MAX_RANKS; ++r) k.acc[r] = r < world ? peer_acc[r][l] : nullptr;
-                k.world = world; k.out = acc[l]; k.count = 3LL * lh[l] * lw[l]; k.row = lw[l];
+                k.world = world; k.root = root; k.out = acc[l]; k.h = lh[l]; k.w = lw[l];
                 const int rc = be.launch(k, lw[l], 3 * lh[l], 1);
                 if (rc) return fail(rc, be.last_error());
             }

@@ -791,16 +791,31 @@ struct DmFocusMapShared {
         }
     }
 };
-// one level of the blended pyramid: sum of every rank's share, ranks in stack order (one call = one float)
-struct DmPeerAccSum {
-    const float *acc[DM_MAX_RANKS]; int world; float *out; long long count; int row;
-    SS_MDEV void operator()(int x, int y, int) const
+// One level of the blended pyramid, reduced in two steps.  Rows [rank h / world, (rank + 1) h / world) are this rank's
+// band: DmPeerBandSum adds every rank's share of the band, ranks in stack order, into the own pyramid (in place: the
+// other ranks read other rows of it); DmPeerBandGather then copies the finished bands of the other ranks into the
+// root's pyramid.  One call = one float of one of the three planes.
+struct DmPeerBandSum {
+    const float *acc[DM_MAX_RANKS]; int world; float *out; int h, w, y0, y1;
+    SS_MDEV void operator()(int x, int yy, int) const
     {
-        const long long o = (long long)y * row + x;
-        if (o >= count) return;
+        const int rows = y1 - y0, plane = yy / rows, y = y0 + yy % rows;
+        const long long o = ((long long)plane * h + y) * w + x;
         float s = acc[0][o];
         for (int r = 1; r < world; ++r) s = ss_add(s, acc[r][o]);
         out[o] = s;
+    }
+};
+struct DmPeerBandGather {
+    const float *acc[DM_MAX_RANKS]; int world, root; float *out; int h, w;
+    SS_MDEV void operator()(int x, int yy, int) const
+    {
+        const int plane = yy / h, y = yy % h;
+        int q = 0;
+        while (q + 1 < world && y >= (int)((long long)(q + 1) * h / world)) ++q;
+        if (q == root) return;
+        const long long o = ((long long)plane * h + y) * w + x;
+        out[o] = acc[q][o];
     }
 };
 

@@ -353,6 +353,7 @@ SS_EXPORT int ssdm_shard_connect_ptrs(ssdm_handle *h, void *const *ptrs, int wor
     SSDM_RET(h, h->eng.shard_connect(ptrs, world, rank, root));
 }
 SS_EXPORT int ssdm_shard_finish_weights(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_finish_weights()); }
+SS_EXPORT int ssdm_shard_reduce_band(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_reduce_band()); }
 SS_EXPORT int ssdm_shard_finish_end(ssdm_handle *h, void *out_bgr, size_t pitch) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_finish_end(out_bgr, pitch)); }
 SS_EXPORT int ssdm_rerun_resident(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.rerun_resident()); }
 SS_EXPORT int ssdm_get_plane(ssdm_handle *h, int what, int frame, float *out) { SSDM_ENTER(h); SSDM_RET(h, h->eng.get_plane(what, frame, out)); }

@@ -192,6 +192,9 @@ class ShardedDepthMapStack:
             _check(lib.ssdm_blend_frame(h, i))
         _check(lib.ssdm_sync(h))
         rdv.barrier()                       # every rank's share of the blended pyramid is complete
+        _check(lib.ssdm_shard_reduce_band(h))
+        _check(lib.ssdm_sync(h))
+        rdv.barrier()                       # every band of rows is summed
         res = None
         if self.rank == self.root:
             res = out if out is not None else np.empty((shape[0], shape[1], 3), dtype=dtype)

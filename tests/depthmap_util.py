@@ -80,6 +80,7 @@ class Emu:
             lib.emu_dm_shard_ptrs.argtypes = [vp, ctypes.POINTER(vp)]
             lib.emu_dm_shard_connect.argtypes = [vp, ctypes.POINTER(vp), i, i, i]
             lib.emu_dm_shard_finish_weights.argtypes = [vp]
+            lib.emu_dm_shard_reduce_band.argtypes = [vp]
             lib.emu_dm_shard_finish_end.argtypes = [vp, vp, sz]
             cls._lib = lib
         return cls._lib
@@ -177,6 +178,8 @@ def emu_sharded_focus_stack(frames, world, root=0, stages=None, **kwargs):
         for e, a, b in ranks:
             for i in range(b - a):
                 assert lib.emu_dm_blend(e.p, i) == 0, e.error()
+        for e, _, _ in ranks:                                   # "barrier", then every rank sums its band of rows
+            assert lib.emu_dm_shard_reduce_band(e.p) == 0, e.error()
         out = np.empty((h, w, 3), frames[0].dtype)
         for r, (e, _, _) in enumerate(ranks):
             if r != root:

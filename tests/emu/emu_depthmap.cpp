@@ -34,6 +34,7 @@ int emu_dm_shard_count(void *p) { return 1 + ((Emu *)p)->L; }
 int emu_dm_shard_ptrs(void *p, void **ptrs) { return ((Emu *)p)->shard_ptrs(ptrs); }
 int emu_dm_shard_connect(void *p, void *const *ptrs, int world, int rank, int root) { return ((Emu *)p)->shard_connect(ptrs, world, rank, root); }
 int emu_dm_shard_finish_weights(void *p) { return ((Emu *)p)->shard_finish_weights(); }
+int emu_dm_shard_reduce_band(void *p) { return ((Emu *)p)->shard_reduce_band(); }
 int emu_dm_shard_finish_end(void *p, void *out, size_t pitch) { return ((Emu *)p)->shard_finish_end(out, pitch); }
 const char *emu_dm_error(void *p) { return ((Emu *)p)->err; }
 long long emu_dm_launches(void *p) { return ((Emu *)p)->be.launches; }

@@ -338,6 +338,9 @@ class _EmuNative:
     def ssdm_blend_frame(self, h, i):
         return self.emu.emu_dm_blend(h, i)
 
+    def ssdm_shard_reduce_band(self, h):
+        return self.emu.emu_dm_shard_reduce_band(h)
+
     def ssdm_shard_finish_end(self, h, out, pitch):
         return self.emu.emu_dm_shard_finish_end(h, out, pitch)
 

@@ -149,6 +149,10 @@ def _sharded_on_one_gpu(frames, world, root, **kwargs):
         for i in range(n):
             _check(lib.ssdm_blend_frame(algo._h, i))
         _check(lib.ssdm_sync(algo._h))
+    for algo, _ in algos:
+        _check(lib.ssdm_shard_reduce_band(algo._h))
+    for algo, _ in algos:
+        _check(lib.ssdm_sync(algo._h))
     out = np.empty_like(frames[0])
     for r, (algo, _) in enumerate(algos):
         if r != root:

@@ -35,6 +35,8 @@ def main():
     from shinestacker_b200 import rendezvous as rdvm
     from shinestacker_b200.sharded import ShardedDepthMapStack, shard_range
     from shinestacker_b200.pyramid import _check
+    from shinestacker_b200.sharded import bind_to_gpu_numa_node
+    bind_to_gpu_numa_node(local)                # pinned buffers and upload traffic on the GPU's own socket
     lib = _native.load()
     rdv = rdvm.TcpRendezvous.from_env(offset=7) if world > 1 else rdvm.Single()
     dt = np.dtype(a.dtype)

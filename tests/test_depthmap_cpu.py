@@ -384,3 +384,22 @@ def test_sharded_host_orchestration_with_two_ranks_over_tcp():
     assert not errors, errors
     assert results[0] is None                                 # rank 1 is the root
     assert np.array_equal(results[1], du.emu_sharded_focus_stack(frames, 2, root=1))
+
+
+def test_randomised_geometries_of_the_tiled_kernels_against_the_oracle():
+    # sizes with interior tiles (four-pixel path of the energy kernel, unreflected patches of the bilateral and of the
+    # tiled pyrDown) next to ragged borders, both sample types, both energies
+    rng = np.random.default_rng(2024)
+    for t in range(8):
+        dtype = [np.uint8, np.uint16][t % 2]
+        h = int(rng.integers(64, 200))
+        w = int(rng.integers(34, 75)) * 4 if t % 4 else int(rng.integers(136, 300))
+        n = int(rng.integers(2, 5))
+        kwargs = dict(energy=["laplacian", "sobel"][(t // 2) % 2], levels=int(rng.integers(2, 5)))
+        frames = synthetic.make_noise_stack(n, h, w, np.dtype(dtype), 500 + t)
+        st = {}
+        out = du.emu_focus_stack(frames, stages=st, **kwargs)
+        ref, ost = dmo.focus_stack(frames, return_stages=True, **kwargs)
+        assert np.array_equal(st["energy"], ost["energy"]), (t, h, w, kwargs)
+        assert np.abs(st["weights"] - ost["weights"]).max() < 5e-6, (t, h, w, kwargs)
+        du.assert_within_1lsb(out, ref, f"case {t} {h}x{w} {kwargs}", max_frac=0.2)

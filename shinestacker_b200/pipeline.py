@@ -129,6 +129,10 @@ def align_and_stack_arrays(frames, ref_idx=None, stack_algo=None, border_mode=BO
         out = algo._finish(n, first.shape[:2])                 # pylint: disable=protected-access
     except BaseException:
         lib.ss_reset(h)
+        try:
+            wp.use_prefetched()         # a frame may still be uploading into the warper's second buffer: retire it
+        except Exception:  # pylint: disable=broad-except
+            pass
         raise
     finally:
         src.close()

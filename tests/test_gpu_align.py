@@ -208,6 +208,26 @@ def test_pipeline_gives_the_same_image_from_pageable_and_from_pinned_frames():
     assert c.shape == a.shape and np.array_equal(mc[0], np.array([[1.0, 0, 0], [0, 1.0, 0]]))
 
 
+def test_pipeline_abort_leaves_a_shared_warper_usable():
+    from shinestacker_b200.pipeline import align_and_stack_arrays
+    from tools.time_pipeline import displaced_stack
+    frames = synthetic.make_stack(5, 240, 320, np.uint8, 31)
+    moved, _, _ = displaced_stack(frames)
+    bad = list(moved)
+    bad[1] = np.random.default_rng(1).integers(0, 256, moved[0].shape).astype(np.uint8)     # unrelated content
+    wp = al.Warper(moved[0].shape[:2], np.uint8)
+    algo = PyramidStack()
+    try:
+        from shinestacker_b200 import NativeLibraryError
+        with pytest.raises((al.AlignmentError, NativeLibraryError)):
+            align_and_stack_arrays(bad, stack_algo=algo, warper=wp)       # fails while frame 2 is being prefetched
+        again = align_and_stack_arrays(list(moved), stack_algo=algo, warper=wp)
+        fresh = align_and_stack_arrays(list(moved))
+        assert np.mean(again != fresh) < 1e-3          # (the ECC sums use atomics: equal up to rounding of the fit)
+    finally:
+        wp.close()
+
+
 def test_prefetched_frames_and_double_buffered_results():
     import ctypes
     from shinestacker_b200 import _native, NativeLibraryError

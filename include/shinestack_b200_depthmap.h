@@ -75,21 +75,24 @@ int ssdm_finish(ssdm_handle *h, void *out_bgr, size_t out_row_pitch_bytes);
  * of the smoothed energies (get_focus_map 'average', :55-57) and the blended pyramid (:104-111) are read out of the
  * peers' device memory (CUDA IPC over NVLink); the pyramid is reduced in bands of rows, one per rank, which the root
  * then collects.  Sums run rank by rank, i.e. in stack order but associated differently
- * from one long chain (float32 rounding; the stacker's contract is 1 LSB).  map_type 'average' only.
+ * from one long chain (float32 rounding; the stacker's contract is 1 LSB).  map_type 'max' (softmax, :58-60) crosses
+ * the ranks twice: the per-pixel maximum (exact in any order), then the sum of the exponentials.
  *
  *   ssdm_push_frame ... ; ssdm_shard_local_max  -> all-gather, max      -> ssdm_shard_finish_local(global max)
  *   ssdm_shard_export -> all-gather -> ssdm_shard_connect (once per handle)
- *   ssdm_sync; barrier; ssdm_shard_finish_weights; ssdm_blend_frame(0..n_local-1); ssdm_sync; barrier
+ *   ssdm_sync; barrier; [map_type max: ssdm_shard_softmax_rel; ssdm_sync; barrier;]
+ *   ssdm_shard_finish_weights; ssdm_blend_frame(0..n_local-1); ssdm_sync; barrier
  *   ssdm_shard_reduce_band; ssdm_sync; barrier
  *   root: ssdm_shard_finish_end(out); others: ssdm_shard_finish_end(NULL); barrier before the next stack.          */
 int ssdm_sync(ssdm_handle *h);
 int ssdm_shard_local_max(ssdm_handle *h, float *max_out);
 int ssdm_shard_finish_local(ssdm_handle *h, float global_max);
-int ssdm_shard_buffer_count(ssdm_handle *h);                      /* 1 + levels */
+int ssdm_shard_buffer_count(ssdm_handle *h);                      /* 2 + levels */
 int ssdm_shard_export(ssdm_handle *h, void *blob /* count x 64 bytes */);
 int ssdm_shard_connect(ssdm_handle *h, const void *blobs /* world x count x 64 */, int world, int rank, int root);
 int ssdm_shard_ptrs(ssdm_handle *h, void **ptrs /* count */);     /* same-process variant of export / connect */
 int ssdm_shard_connect_ptrs(ssdm_handle *h, void *const *ptrs /* world x count */, int world, int rank, int root);
+int ssdm_shard_softmax_rel(ssdm_handle *h);                        /* no-op for map_type average */
 int ssdm_shard_finish_weights(ssdm_handle *h);
 int ssdm_shard_reduce_band(ssdm_handle *h);
 int ssdm_shard_finish_end(ssdm_handle *h, void *out_bgr, size_t out_row_pitch_bytes);

@@ -139,6 +139,7 @@ SIGNATURES_DEPTHMAP = {
     "ssdm_shard_connect": (_i, [_vp, _vp, _i, _i, _i]),
     "ssdm_shard_ptrs": (_i, [_vp, ctypes.POINTER(_vp)]),
     "ssdm_shard_connect_ptrs": (_i, [_vp, ctypes.POINTER(_vp), _i, _i, _i]),
+    "ssdm_shard_softmax_rel": (_i, [_vp]),
     "ssdm_shard_finish_weights": (_i, [_vp]),
     "ssdm_shard_reduce_band": (_i, [_vp]),
     "ssdm_shard_finish_end": (_i, [_vp, _vp, _sz]),

@@ -95,8 +95,10 @@ struct DmEngine {
     // frames of one stack sharded over ranks (shard_* below): this rank holds a contiguous run of the frames
     int world = 1, rank = 0, root = 0, stats_folded = 0;
     float local_max = 0.f;
-    float *d_psum = nullptr;
+    float *d_psum = nullptr, *d_pmax = nullptr;
+    int rel_done = 0;
     const float *peer_psum[DM_MAX_RANKS] = {};
+    const float *peer_pmax[DM_MAX_RANKS] = {};
     const float *peer_acc[DM_MAX_RANKS][16] = {};
     int fused_energy = 1;          // SSDM_ENERGY_FUSED=0: the four streaming passes instead of the tiled kernel
 
@@ -184,11 +186,11 @@ struct DmEngine {
     void destroy()
     {
         be.sync();
-        void *ptrs[] = {d_frames, d_out, d_energy, d_smooth, d_t1, d_t2, d_t3, d_stats, d_slots, d_sw, d_psum};
+        void *ptrs[] = {d_frames, d_out, d_energy, d_smooth, d_t1, d_t2, d_t3, d_stats, d_slots, d_sw, d_psum, d_pmax};
         for (void *p : ptrs) if (p) be.free(p);
         for (float *p : gp) if (p) be.free(p);
         for (float *p : acc) if (p) be.free(p);
-        d_frames = d_out = nullptr; d_energy = d_smooth = d_t1 = d_t2 = d_t3 = d_sw = d_psum = nullptr; d_stats = d_slots = nullptr;
+        d_frames = d_out = nullptr; d_energy = d_smooth = d_t1 = d_t2 = d_t3 = d_sw = d_psum = d_pmax = nullptr; d_stats = d_slots = nullptr;
         gp.clear(); acc.clear();
     }
 
@@ -197,7 +199,7 @@ struct DmEngine {
         int rc = be.sync();
         if (rc) return fail(rc, be.last_error());
         n = 0; finished = 0; blended = 0; launched_blend = 0; collapsed = 0; weights = nullptr; gmax = 0.f;
-        stats_folded = 0; local_max = 0.f;
+        stats_folded = 0; local_max = 0.f; rel_done = 0;
         be.reset_counters();
         std::vector<unsigned> init(2 * (size_t)o.max_frames * DM_STAT_SLOTS);
         for (size_t i = 0; i < init.size(); i += 2) { init[i] = 0x7f800000u; init[i + 1] = 0u; }  // min = +inf, max = 0
@@ -362,7 +364,8 @@ struct DmEngine {
     // peers' memory) and the blended pyramid (every rank sums one band of rows out of the peers' memory, the root then
     // collects the bands).  The sums are taken
     // rank by rank, i.e. in stack order but associated differently from one long chain: float32 rounding, covered by
-    // the 1-LSB contract of this stacker.  map_type 'average' only.
+    // the 1-LSB contract of this stacker.  map_type 'max' (softmax) needs one more plane across the ranks: the per-pixel
+    // maximum (exact in any order), then the sum of the exponentials.
     int shard_local_max(float *out)
     {
         const int rc = fold_stats();
@@ -370,39 +373,65 @@ struct DmEngine {
         *out = local_max;
         return DM_OK;
     }
-    int shard_finish_local(float global_max)
-    {
-        if (!stats_folded) return fail(DM_ERR_STATE, "shard_local_max first");
-        if (o.map_type != 0) return fail(DM_ERR_INVALID_OPTION, "sharded stacks implement map_type average only");
-        int rc = smooth(global_max);
-        if (rc) return rc;
-        if (!d_psum && (rc = be.alloc((void **)&d_psum, plane * sizeof(float)))) return fail(rc, be.last_error());
-        DmPartialSum k{weights, h, w, n, d_psum};
-        if ((rc = be.launch(k, w, h, 1))) return fail(rc, be.last_error());
-        return DM_OK;
-    }
-    // exchangeable buffers of this rank: ptrs[0] = partial sum plane, ptrs[1 + l] = blended level l; count = 1 + L
-    int shard_ptrs(void **ptrs)
+    int shard_alloc()
     {
         int rc;
         if (!d_psum && (rc = be.alloc((void **)&d_psum, plane * sizeof(float)))) return fail(rc, be.last_error());
-        ptrs[0] = d_psum;
-        for (int l = 0; l < L; ++l) ptrs[1 + l] = acc[l];
+        if (!d_pmax && (rc = be.alloc((void **)&d_pmax, plane * sizeof(float)))) return fail(rc, be.last_error());
         return DM_OK;
     }
-    // all[r * (1 + L) + k]: buffer k of rank r, mapped into this process (the own entries may be anything)
+    int shard_finish_local(float global_max)
+    {
+        if (!stats_folded) return fail(DM_ERR_STATE, "shard_local_max first");
+        int rc = smooth(global_max);
+        if (rc) return rc;
+        if ((rc = shard_alloc())) return rc;
+        if (o.map_type == 0) {
+            DmPartialSum k{weights, h, w, n, d_psum};
+            rc = be.launch(k, w, h, 1);
+        } else {
+            DmPartialMax k{weights, h, w, n, d_pmax};
+            rc = be.launch(k, w, h, 1);
+        }
+        return rc ? fail(rc, be.last_error()) : DM_OK;
+    }
+    // map_type 'max' only, after every rank has finished shard_finish_local (barrier): exp((e - max) / temperature)
+    // of the own frames and their partial sum; another barrier, then shard_finish_weights
+    int shard_softmax_rel()
+    {
+        if (!weights || finished) return fail(DM_ERR_STATE, "shard_finish_local first");
+        if (o.map_type != 1) return DM_OK;
+        DmSoftmaxRel k;
+        k.e = weights; k.h = h; k.w = w; k.n = n; k.world = world; k.temperature = (float)o.temperature; k.psum = d_psum;
+        for (int r = 0; r < DM_MAX_RANKS; ++r) k.pmax[r] = r < world ? peer_pmax[r] : nullptr;
+        const int rc = be.launch(k, w, h, 1);
+        if (rc) return fail(rc, be.last_error());
+        rel_done = 1;
+        return DM_OK;
+    }
+    // exchangeable buffers of this rank: ptrs[0] = partial sum plane, ptrs[1] = partial maximum plane,
+    // ptrs[2 + l] = blended level l; count = 2 + L
+    int shard_ptrs(void **ptrs)
+    {
+        const int rc = shard_alloc();
+        if (rc) return rc;
+        ptrs[0] = d_psum; ptrs[1] = d_pmax;
+        for (int l = 0; l < L; ++l) ptrs[2 + l] = acc[l];
+        return DM_OK;
+    }
+    // all[r * (2 + L) + k]: buffer k of rank r, mapped into this process (the own entries may be anything)
     int shard_connect(void *const *all, int world_, int rank_, int root_)
     {
         if (world_ < 1 || world_ > DM_MAX_RANKS || rank_ < 0 || rank_ >= world_ || root_ < 0 || root_ >= world_)
             return fail(DM_ERR_INVALID_OPTION, "world / rank / root out of range");
-        void *own[17];
+        void *own[18];
         const int rc = shard_ptrs(own);
         if (rc) return rc;
         world = world_; rank = rank_; root = root_;
         for (int r = 0; r < world; ++r)
-            for (int k = 0; k < 1 + L; ++k) {
-                const float *p = (const float *)(r == rank ? own[k] : all[(size_t)r * (1 + L) + k]);
-                if (k == 0) peer_psum[r] = p; else peer_acc[r][k - 1] = p;
+            for (int k = 0; k < 2 + L; ++k) {
+                const float *p = (const float *)(r == rank ? own[k] : all[(size_t)r * (2 + L) + k]);
+                if (k == 0) peer_psum[r] = p; else if (k == 1) peer_pmax[r] = p; else peer_acc[r][k - 2] = p;
             }
         return DM_OK;
     }
@@ -410,8 +439,9 @@ struct DmEngine {
     int shard_finish_weights()
     {
         if (!weights || finished) return fail(DM_ERR_STATE, "shard_finish_local first");
+        if (o.map_type == 1 && !rel_done) return fail(DM_ERR_STATE, "map_type max: shard_softmax_rel first");
         DmFocusMapShared k;
-        k.e = weights; k.h = h; k.w = w; k.n = n; k.world = world;
+        k.e = weights; k.h = h; k.w = w; k.n = n; k.world = world; k.softmax = o.map_type;
         for (int r = 0; r < DM_MAX_RANKS; ++r) k.psum[r] = r < world ? peer_psum[r] : nullptr;
         const int rc = be.launch(k, w, h, 1);
         if (rc) return fail(rc, be.last_error());

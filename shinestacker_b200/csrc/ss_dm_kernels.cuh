@@ -777,9 +777,40 @@ struct DmPartialSum {
         out[o] = s;
     }
 };
+// 'max' map (softmax, depth_map.py:58-60): per-pixel maximum of this rank's planes ...
+struct DmPartialMax {
+    const float *e; int h, w, n; float *out;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        const long long plane = (long long)h * w, o = (long long)y * w + x;
+        float m = e[o];
+        for (int i = 1; i < n; ++i) m = fmaxf(m, e[i * plane + o]);
+        out[o] = m;
+    }
+};
+// ... then, with the maximum over every rank's planes (exact, whatever the order): the own planes become
+// exp((e - max) / temperature) in place and their sum in stack order goes to the partial-sum plane
+struct DmSoftmaxRel {
+    float *e; int h, w, n; const float *pmax[DM_MAX_RANKS]; int world; float temperature; float *psum;
+    SS_MDEV void operator()(int x, int y, int) const
+    {
+        const long long plane = (long long)h * w, o = (long long)y * w + x;
+        float m = pmax[0][o];
+        for (int r = 1; r < world; ++r) m = fmaxf(m, pmax[r][o]);
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) {
+            float *q = e + i * plane + o;
+            const float rel = expf(ss_div(ss_add(*q, -m), temperature));
+            *q = rel;
+            s = i ? ss_add(s, rel) : rel;
+        }
+        psum[o] = s;
+    }
+};
 // sum of every rank's partial sum, ranks in stack order, then e_i / sum for the own n planes, in place
+// (softmax: the division is unconditional, as in DmFocusMap)
 struct DmFocusMapShared {
-    float *e; int h, w, n; const float *psum[DM_MAX_RANKS]; int world;
+    float *e; int h, w, n; const float *psum[DM_MAX_RANKS]; int world; int softmax;
     SS_MDEV void operator()(int x, int y, int) const
     {
         const long long plane = (long long)h * w, o = (long long)y * w + x;
@@ -787,7 +818,7 @@ struct DmFocusMapShared {
         for (int r = 1; r < world; ++r) s = ss_add(s, psum[r][o]);
         for (int i = 0; i < n; ++i) {
             float *q = e + i * plane + o;
-            *q = s != 0.f ? ss_div(*q, s) : 0.f;
+            *q = softmax ? ss_div(*q, s) : (s != 0.f ? ss_div(*q, s) : 0.f);
         }
     }
 };

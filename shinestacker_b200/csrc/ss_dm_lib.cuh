@@ -210,7 +210,7 @@ struct DmCudaBackend {
 struct ssdm_handle {
     DmEngine<DmCudaBackend> eng;
     int device = 0;
-    void *peer_open[DM_MAX_RANKS][17] = {};     // IPC mappings of the peers' exchangeable buffers (ssdm_shard_connect)
+    void *peer_open[DM_MAX_RANKS][18] = {};     // IPC mappings of the peers' exchangeable buffers (ssdm_shard_connect)
 };
 
 #define SSDM_ENTER(h)                                                       \
@@ -256,7 +256,7 @@ SS_EXPORT int ssdm_create(const ssdm_config *cfg, ssdm_handle **out)
 static void ssdm_close_peers(ssdm_handle *h)
 {
     for (int r = 0; r < DM_MAX_RANKS; ++r)
-        for (int k = 0; k < 17; ++k)
+        for (int k = 0; k < 18; ++k)
             if (h->peer_open[r][k]) { cudaIpcCloseMemHandle(h->peer_open[r][k]); h->peer_open[r][k] = nullptr; }
 }
 
@@ -304,7 +304,7 @@ SS_EXPORT int ssdm_shard_local_max(ssdm_handle *h, float *max_out)
     SSDM_RET(h, h->eng.shard_local_max(max_out));
 }
 SS_EXPORT int ssdm_shard_finish_local(ssdm_handle *h, float global_max) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_finish_local(global_max)); }
-SS_EXPORT int ssdm_shard_buffer_count(ssdm_handle *h) { return h ? 1 + h->eng.L : 0; }
+SS_EXPORT int ssdm_shard_buffer_count(ssdm_handle *h) { return h ? 2 + h->eng.L : 0; }
 SS_EXPORT int ssdm_shard_ptrs(ssdm_handle *h, void **ptrs)
 {
     SSDM_ENTER(h);
@@ -316,10 +316,10 @@ SS_EXPORT int ssdm_shard_export(ssdm_handle *h, void *blob)
 {
     SSDM_ENTER(h);
     if (!blob) return ss_fail(SS_ERR_STATE, "null argument");
-    void *own[17];
+    void *own[18];
     const int rc = h->eng.shard_ptrs(own);
     if (rc) return ss_fail(rc, "%s", h->eng.err);
-    for (int k = 0; k < 1 + h->eng.L; ++k) {
+    for (int k = 0; k < 2 + h->eng.L; ++k) {
         cudaIpcMemHandle_t mh;
         SS_CUDA(cudaIpcGetMemHandle(&mh, own[k]));
         memcpy((char *)blob + 64 * k, &mh, 64);
@@ -331,7 +331,7 @@ SS_EXPORT int ssdm_shard_connect(ssdm_handle *h, const void *blobs, int world, i
 {
     SSDM_ENTER(h);
     if (!blobs || world < 1 || world > DM_MAX_RANKS || rank < 0 || rank >= world) return ss_fail(SS_ERR_INVALID_OPTION, "world / rank out of range");
-    const int nb = 1 + h->eng.L;
+    const int nb = 2 + h->eng.L;
     ssdm_close_peers(h);
     std::vector<void *> all((size_t)world * nb, nullptr);
     for (int r = 0; r < world; ++r) {
@@ -352,6 +352,7 @@ SS_EXPORT int ssdm_shard_connect_ptrs(ssdm_handle *h, void *const *ptrs, int wor
     if (!ptrs) return ss_fail(SS_ERR_STATE, "null argument");
     SSDM_RET(h, h->eng.shard_connect(ptrs, world, rank, root));
 }
+SS_EXPORT int ssdm_shard_softmax_rel(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_softmax_rel()); }
 SS_EXPORT int ssdm_shard_finish_weights(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_finish_weights()); }
 SS_EXPORT int ssdm_shard_reduce_band(ssdm_handle *h) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_reduce_band()); }
 SS_EXPORT int ssdm_shard_finish_end(ssdm_handle *h, void *out_bgr, size_t pitch) { SSDM_ENTER(h); SSDM_RET(h, h->eng.shard_finish_end(out_bgr, pitch)); }

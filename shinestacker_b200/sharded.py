@@ -149,7 +149,7 @@ class ShardedDepthMapStack:
     rendezvous, the per-pixel sum of the smoothed energies and the blended pyramid out of the peers' device memory
     (include/shinestack_b200_depthmap.h, ssdm_shard_*).  ``focus_stack_arrays(local_frames, n_total)`` returns the
     fused image on the root and None elsewhere.  Sums are associated rank by rank, so the image equals the single-GPU
-    one within float32 rounding (the stacker's 1-LSB contract); ``map_type='average'`` only."""
+    one within float32 rounding (the stacker's 1-LSB contract)."""
 
     def __init__(self, rank, world, device=0, root=0, rendezvous=None, **kwargs):
         from .depth_map import DepthMapStack      # pylint: disable=import-outside-toplevel
@@ -186,7 +186,11 @@ class ShardedDepthMapStack:
         self._connect()
         _check(lib.ssdm_shard_finish_local(h, ctypes.c_float(gmax)))
         _check(lib.ssdm_sync(h))
-        rdv.barrier()                       # every partial sum plane is complete
+        rdv.barrier()                       # every partial sum (average) / partial maximum (max) plane is complete
+        if a.map_type == "max":
+            _check(lib.ssdm_shard_softmax_rel(h))
+            _check(lib.ssdm_sync(h))
+            rdv.barrier()                   # every partial sum of the exponentials is complete
         _check(lib.ssdm_shard_finish_weights(h))
         for i in range(n_local):
             _check(lib.ssdm_blend_frame(h, i))

@@ -79,6 +79,7 @@ class Emu:
             lib.emu_dm_shard_count.argtypes = [vp]
             lib.emu_dm_shard_ptrs.argtypes = [vp, ctypes.POINTER(vp)]
             lib.emu_dm_shard_connect.argtypes = [vp, ctypes.POINTER(vp), i, i, i]
+            lib.emu_dm_shard_softmax_rel.argtypes = [vp]
             lib.emu_dm_shard_finish_weights.argtypes = [vp]
             lib.emu_dm_shard_reduce_band.argtypes = [vp]
             lib.emu_dm_shard_finish_end.argtypes = [vp, vp, sz]
@@ -171,7 +172,9 @@ def emu_sharded_focus_stack(frames, world, root=0, stages=None, **kwargs):
         for r, (e, _, _) in enumerate(ranks):
             assert lib.emu_dm_shard_connect(e.p, table, world, r, root) == 0, e.error()
             assert lib.emu_dm_shard_finish_local(e.p, ctypes.c_float(gmax)) == 0, e.error()
-        for e, _, _ in ranks:                                   # "barrier": every partial sum exists
+        for e, _, _ in ranks:                                   # "barrier": every partial sum / maximum exists
+            assert lib.emu_dm_shard_softmax_rel(e.p) == 0, e.error()        # (no-op for map_type average)
+        for e, _, _ in ranks:                                   # "barrier"
             assert lib.emu_dm_shard_finish_weights(e.p) == 0, e.error()
         if stages is not None:
             stages["weights"] = np.array([e.plane("weights", i) for e, a, b in ranks for i in range(b - a)])

@@ -30,9 +30,10 @@ int emu_dm_rerun(void *p) { return ((Emu *)p)->rerun_resident(); }
 int emu_dm_get_plane(void *p, int what, int frame, float *out) { return ((Emu *)p)->get_plane(what, frame, out); }
 int emu_dm_shard_local_max(void *p, float *out) { return ((Emu *)p)->shard_local_max(out); }
 int emu_dm_shard_finish_local(void *p, float gmax) { return ((Emu *)p)->shard_finish_local(gmax); }
-int emu_dm_shard_count(void *p) { return 1 + ((Emu *)p)->L; }
+int emu_dm_shard_count(void *p) { return 2 + ((Emu *)p)->L; }
 int emu_dm_shard_ptrs(void *p, void **ptrs) { return ((Emu *)p)->shard_ptrs(ptrs); }
 int emu_dm_shard_connect(void *p, void *const *ptrs, int world, int rank, int root) { return ((Emu *)p)->shard_connect(ptrs, world, rank, root); }
+int emu_dm_shard_softmax_rel(void *p) { return ((Emu *)p)->shard_softmax_rel(); }
 int emu_dm_shard_finish_weights(void *p) { return ((Emu *)p)->shard_finish_weights(); }
 int emu_dm_shard_reduce_band(void *p) { return ((Emu *)p)->shard_reduce_band(); }
 int emu_dm_shard_finish_end(void *p, void *out, size_t pitch) { return ((Emu *)p)->shard_finish_end(out, pitch); }

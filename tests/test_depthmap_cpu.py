@@ -275,6 +275,8 @@ def test_bilateral_forms_agree_with_the_oracle(monkeypatch):
     (3, 2, 7, np.uint16, {"levels": 4}),
     (4, 1, 4, np.uint8, {"energy": "sobel", "smooth_size": 0}),       # one frame per rank, no smoothing
     (1, 0, 3, np.uint8, {}),                                          # a "box" of one GPU goes the same way
+    (3, 0, 7, np.uint8, {"map_type": "max"}),                         # softmax: maximum and sum cross the ranks
+    (2, 1, 5, np.uint16, {"map_type": "max", "temperature": 0.05, "levels": 2}),
 ])
 def test_frames_sharded_over_ranks_give_the_single_handle_result_within_rounding(world, root, n, dtype, kwargs):
     frames = synthetic.make_stack(n, 60, 90, np.dtype(dtype), seed=world + n)
@@ -287,12 +289,6 @@ def test_frames_sharded_over_ranks_give_the_single_handle_result_within_rounding
     du.assert_within_1lsb(sharded, dmo.focus_stack(frames, **kwargs), "sharded vs oracle", max_frac=0.2)
     if world == 1:
         assert np.array_equal(sharded, single)
-
-
-def test_sharded_stacks_implement_the_average_map_only():
-    frames = synthetic.make_stack(2, 40, 50, np.dtype(np.uint8), seed=1)
-    with pytest.raises(AssertionError, match="average"):
-        du.emu_sharded_focus_stack(frames, 2, map_type="max")
 
 
 class _EmuNative:
@@ -332,6 +328,9 @@ class _EmuNative:
     def ssdm_sync(self, h):
         return 0
 
+    def ssdm_shard_softmax_rel(self, h):
+        return self.emu.emu_dm_shard_softmax_rel(h)
+
     def ssdm_shard_finish_weights(self, h):
         return self.emu.emu_dm_shard_finish_weights(h)
 
@@ -348,7 +347,8 @@ class _EmuNative:
         return 0
 
 
-def test_sharded_host_orchestration_with_two_ranks_over_tcp():
+@pytest.mark.parametrize("map_type", ["average", "max"])
+def test_sharded_host_orchestration_with_two_ranks_over_tcp(map_type):
     import ctypes
     import socket
     import threading
@@ -364,10 +364,10 @@ def test_sharded_host_orchestration_with_two_ranks_over_tcp():
         try:
             rdv = rendezvous.TcpRendezvous(rank, 2, "127.0.0.1", port, timeout=30)
             a, b = shard_range(len(frames), rank, 2)
-            emu = du.Emu(50, 70, np.uint8, b - a)
+            emu = du.Emu(50, 70, np.uint8, b - a, map_type=map_type)
             for f in frames[a:b]:
                 assert emu.push(f) == 0
-            st = ShardedDepthMapStack(rank, 2, rendezvous=rdv, root=1)
+            st = ShardedDepthMapStack(rank, 2, rendezvous=rdv, root=1, map_type=map_type)
             st.algo._lib, st.algo._h = _EmuNative(), ctypes.c_void_p(emu.p)
             results[rank] = st.finish(b - a, (50, 70), np.dtype(np.uint8))
             st.algo._h = None
@@ -383,7 +383,7 @@ def test_sharded_host_orchestration_with_two_ranks_over_tcp():
         t.join(timeout=60)
     assert not errors, errors
     assert results[0] is None                                 # rank 1 is the root
-    assert np.array_equal(results[1], du.emu_sharded_focus_stack(frames, 2, root=1))
+    assert np.array_equal(results[1], du.emu_sharded_focus_stack(frames, 2, root=1, map_type=map_type))
 
 
 def test_randomised_geometries_of_the_tiled_kernels_against_the_oracle():

@@ -143,6 +143,9 @@ def _sharded_on_one_gpu(frames, world, root, **kwargs):
     for algo, _ in algos:
         _check(lib.ssdm_sync(algo._h))
     for algo, _ in algos:
+        _check(lib.ssdm_shard_softmax_rel(algo._h))
+        _check(lib.ssdm_sync(algo._h))
+    for algo, _ in algos:
         _check(lib.ssdm_shard_finish_weights(algo._h))
     weights = np.array([algo.get_plane("weights", i) for algo, n in algos for i in range(n)])
     for algo, n in algos:
@@ -167,13 +170,18 @@ def _sharded_on_one_gpu(frames, world, root, **kwargs):
     (2, 0, 5, 150, 203, np.uint8, {}),
     (3, 2, 8, 130, 260, np.uint16, {"levels": 4}),
     (4, 1, 9, 100, 136, np.uint8, {"energy": "sobel"}),
+    (3, 0, 7, 120, 168, np.uint8, {"map_type": "max"}),
 ])
 def test_sharded_phases_equal_the_host_build_and_the_single_handle_result(world, root, n, h, w, dtype, kwargs):
     frames = synthetic.make_stack(n, h, w, np.dtype(dtype), seed=90 + world)
     out, weights = _sharded_on_one_gpu(frames, world, root, **kwargs)
     st = {}
     emu = du.emu_sharded_focus_stack(frames, world, root, stages=st, **kwargs)
-    assert np.array_equal(out, emu) and np.array_equal(weights, st["weights"])      # same code, same order
+    if kwargs.get("map_type") == "max":         # expf of the device and of the host's libm differ in the last bits
+        assert np.abs(weights - st["weights"]).max() < 2e-6
+        du.assert_within_1lsb(out, emu, "sharded softmax vs host build", max_frac=0.02)
+    else:
+        assert np.array_equal(out, emu) and np.array_equal(weights, st["weights"])      # same code, same order
     single = DepthMapStack(**kwargs)
     ref = single.focus_stack_arrays(frames)
     ref_w = np.array([single.get_plane("weights", i) for i in range(n)])

@@ -70,6 +70,8 @@ int ssal_ecc_estimate(ssal_handle *h, const void *mov_bgr, size_t pitch_bytes, i
  * source pointer.  At most one prefetched frame can be outstanding. */
 int ssal_prefetch(ssal_handle *h, const void *next_bgr, size_t pitch_bytes);
 int ssal_use_prefetched(ssal_handle *h);
+/* Waits for everything queued on this handle (uploads included): the host buffers handed to ssal_prefetch may then go. */
+int ssal_sync(ssal_handle *h);
 
 /* Device address and row pitch of the last aligned frame (outputs are double-buffered: valid until the SECOND next ssal_warp on this handle). */
 int ssal_result_device(ssal_handle *h, const void **d_bgr, size_t *pitch_bytes);

@@ -159,6 +159,7 @@ SIGNATURES_ALIGN = {
     "ssal_ecc_estimate": (_i, [_vp, _vp, _sz, _i, _i, ctypes.c_double, _dp, _dp, _dp]),
     "ssal_prefetch": (_i, [_vp, _vp, _sz]),
     "ssal_use_prefetched": (_i, [_vp]),
+    "ssal_sync": (_i, [_vp]),
     "ssal_result_device": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "ssal_kernel_time_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "ssal_launch_count": (_i, [_vp, ctypes.POINTER(ctypes.c_int64)]),

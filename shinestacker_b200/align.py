@@ -302,6 +302,10 @@ class Warper:
         """Makes the prefetched frame the current one: ``ecc_estimate(None)`` / ``warp(None, ...)`` then work on it."""
         _check(self._lib.ssal_use_prefetched(self._h))
 
+    def sync(self):
+        """Waits for everything queued on this warper, uploads of prefetched frames included."""
+        _check(self._lib.ssal_sync(self._h))
+
     def _check_frame(self, img):
         if img.shape[:2] != self.shape or img.ndim != 3 or img.shape[2] != 3:
             raise ShapeError(self.shape, img.shape[:2])

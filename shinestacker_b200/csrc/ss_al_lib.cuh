@@ -95,6 +95,12 @@ SS_EXPORT int ssal_use_prefetched(ssal_handle *h)
     const int rc = h->eng.use_prefetched();
     return rc ? ss_fail(rc, "%s", h->eng.err) : SS_OK;
 }
+SS_EXPORT int ssal_sync(ssal_handle *h)
+{
+    SSAL_ENTER(h);
+    const int rc = h->eng.be.sync();
+    return rc ? ss_fail(rc, "%s", h->eng.be.last_error()) : SS_OK;
+}
 SS_EXPORT int ssal_result_device(ssal_handle *h, const void **d_bgr, size_t *pitch)
 {
     if (!h || !d_bgr || !pitch) return ss_fail(SS_ERR_STATE, "null argument");

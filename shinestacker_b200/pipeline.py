@@ -129,10 +129,11 @@ def align_and_stack_arrays(frames, ref_idx=None, stack_algo=None, border_mode=BO
         out = algo._finish(n, first.shape[:2])                 # pylint: disable=protected-access
     except BaseException:
         lib.ss_reset(h)
-        try:
-            wp.use_prefetched()         # a frame may still be uploading into the warper's second buffer: retire it
-        except Exception:  # pylint: disable=broad-except
-            pass
+        for retire in (wp.use_prefetched, wp.sync):     # a frame may still be uploading out of a pinned slot that
+            try:                                        # src.close() is about to free: retire it and wait
+                retire()
+            except Exception:  # pylint: disable=broad-except
+                pass
         raise
     finally:
         src.close()

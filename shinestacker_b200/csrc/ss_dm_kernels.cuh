@@ -621,21 +621,28 @@ struct DmBilateralTile {
         for (int item = tid; item < DM_BT_PH * (DM_BT_X / 4); item += nthreads) {
             const int i = item / (DM_BT_X / 4), x4 = 4 * (item % (DM_BT_X / 4));
             const float *src = V + i * DM_BT_PP + x4;
-            float m[18];
+            float m[20];
 #pragma unroll
-            for (int j = 0; j < 18; ++j) m[j] = dm_pow<K>(src[j]);
+            for (int q = 0; q < 5; ++q) {                                   // 128-bit loads (x4 and the pitch are multiples of 4)
+                const DmF4 t = dm_ld4(src + 4 * q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[4 * q + j] = dm_pow<K>(t.v[j]);
+            }
             float *dst = H + i * DM_BT_X + x4;
+            DmF4 hv[6];                                                     // planes H_0, H_3, H_4, H_5, H_6, H_7
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
                 const int c = o + 7;
-                dst[o] = m[c];
+                hv[0].v[o] = m[c];
                 float a = m[c];
 #pragma unroll
                 for (int d = 1; d <= 7; ++d) {
                     a = ss_fma(g[d], ss_add(m[c - d], m[c + d]), a);
-                    if (d >= 3) dst[(d - 2) * DM_BT_PH * DM_BT_X + o] = a;     // planes H_0, H_3, H_4, H_5, H_6, H_7
+                    if (d >= 3) hv[d - 2].v[o] = a;
                 }
             }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dm_st4(dst + q * DM_BT_PH * DM_BT_X, hv[q]);    // 128-bit stores
         }
     }
 

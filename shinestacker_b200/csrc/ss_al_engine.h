@@ -21,7 +21,6 @@ struct AlEngine {
     bool next_pending = false;
     int *d_tab = nullptr, *d_fill = nullptr;      // d_fill[0] = number of pixels to fill, d_fill[1..] = their indices
     const uint8_t *result = nullptr;
-    std::vector<int> tab;
     char err[256];
     EccEstimator<Backend> ecc;          // allocated on first use
     bool ecc_ready = false, src_valid = false;
@@ -45,7 +44,6 @@ struct AlEngine {
         if ((rc = be.alloc((void **)&d_out_b, frame_bytes))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_fill, sizeof(int) * ((size_t)w * h + 1)))) return fail(rc, be.last_error());
         if ((rc = be.alloc((void **)&d_tab, sizeof(int) * 2 * ((size_t)w + h)))) return fail(rc, be.last_error());
-        tab.resize(2 * ((size_t)w + h));
         return DM_OK;
     }
 
@@ -87,16 +85,10 @@ struct AlEngine {
             M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
             const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
             M[2] = b1; M[5] = b2;
-            int *ad = tab.data(), *bd = ad + w, *x0 = bd + w, *y0 = x0 + h;
-            for (int x = 0; x < w; ++x) {
-                ad[x] = (int)nearbyint(M[0] * x * 1024);
-                bd[x] = (int)nearbyint(M[3] * x * 1024);
-            }
-            for (int y = 0; y < h; ++y) {
-                x0[y] = (int)nearbyint((M[1] * y + M[2]) * 1024) + 16;
-                y0[y] = (int)nearbyint((M[4] * y + M[5]) * 1024) + 16;
-            }
-            if ((rc = be.upload_small(d_tab, tab.data(), tab.size() * sizeof(int)))) return rc;
+            AlAffineTables t;
+            for (int i = 0; i < 6; ++i) t.M[i] = M[i];
+            t.w = w; t.h = h; t.ad = d_tab; t.bd = d_tab + w; t.x0 = d_tab + 2 * w; t.y0 = d_tab + 2 * w + h;
+            if ((rc = be.launch(t, w > h ? w : h, 1, 1))) return rc;
             k.persp = 0;
             k.adelta = d_tab; k.bdelta = d_tab + w; k.x0 = d_tab + 2 * w; k.y0 = d_tab + 2 * w + h;
         } else {

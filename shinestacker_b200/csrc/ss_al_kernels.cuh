@@ -184,6 +184,26 @@ struct AlWarp {
     }
 };
 
+// cv2.warpAffine's fixed-point coordinate tables (AB_BITS = 10) for the inverted 2x3 matrix M, built on the device
+// (a host-built table would need a host-to-device copy that queues behind the frame uploads): one call = entry i of
+// the column tables (i < w) and of the row tables (i < h).  Float64 products and sums unfused, round half to even:
+// the values of cv2's saturate_cast<int>(M * x * 1024).
+struct AlAffineTables {
+    double M[6]; int w, h; int *ad, *bd, *x0, *y0;
+    SS_MDEV void operator()(int i, int, int) const
+    {
+        const double v = (double)i;
+        if (i < w) {
+            ad[i] = (int)al_rint_ll(M[0] * v * 1024);
+            bd[i] = (int)al_rint_ll(M[3] * v * 1024);
+        }
+        if (i < h) {
+            x0[i] = (int)al_rint_ll((M[1] * v + M[2]) * 1024) + 16;
+            y0[i] = (int)al_rint_ll((M[4] * v + M[5]) * 1024) + 16;
+        }
+    }
+};
+
 // img_warp[mask == 0] = GaussianBlur(img_warp)[mask == 0] (align.py:249-251).  `out` already holds a copy of
 // the warped frame (AlWarp's second destination); the listed pixels (thin border strips) are replaced by the
 // full 2-D fixed-point sum (sum_ij k_i k_j p_ij + half) >> shift -- exact integers, so the order of the taps

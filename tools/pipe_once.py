@@ -1,3 +1,9 @@
+#!/usr/bin/env python
+"""Probes of the ECC fit inside the align + stack pipeline (config 5) on a few 4096x3072 frames:
+  1. host time of one fit + warp,
+  2. cost and accuracy of the fit stopped at each pyramid level (finest_level = 0 .. 6),
+  3. device time of the fit with and without an upload of the next frame in flight.
+usage: python tools/pipe_once.py [n_frames]      (the numbers quoted in DESIGN.md section 11)"""
 import sys, time, json
 sys.path.insert(0, ".")
 import numpy as np

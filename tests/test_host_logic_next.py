@@ -150,3 +150,46 @@ def test_reference_combined_actions_drive_our_align_frames(tmp_path, monkeypatch
     for name in ("img00.tif", "img02.tif"):
         got = cv2.imread(str(out_dir / name), cv2.IMREAD_UNCHANGED)
         assert np.abs(got[inner].astype(int) - img[inner].astype(int)).mean() < 3.0
+
+
+def test_pipeline_sources_stage_pageable_frames_ahead_in_a_small_ring():
+    # align_and_stack_arrays takes pinned frames as they are and copies pageable ones into a ring of pinned slots a few
+    # positions ahead on worker threads; the ring is shorter than the stack, so slots are reused
+    import ctypes
+    from shinestacker_b200 import pipeline
+
+    class Lib:
+        def __init__(self, pinned_ids):
+            self.pinned_ids, self.bufs, self.freed = pinned_ids, {}, 0
+
+        def ss_host_is_pinned(self, ptr):
+            return 1 if ptr.value in self.pinned_ids else 0
+
+        def ss_host_alloc(self, ref, nbytes):
+            buf = (ctypes.c_uint8 * nbytes)()
+            addr = ctypes.addressof(buf)
+            self.bufs[addr] = buf
+            ctypes.cast(ref, ctypes.POINTER(ctypes.c_void_p))[0] = addr
+            return 0
+
+        def ss_host_free(self, ptr):
+            self.freed += 1
+            return 0
+
+    frames = synthetic.make_noise_stack(11, 24, 40, np.uint16, 9)
+    order = [i for i in range(11) if i != 5]                    # the moving frames (5 is the reference)
+    lib = Lib({frames[2].ctypes.data, frames[7].ctypes.data})   # two of them already sit in page-locked memory
+    src = pipeline._Sources(lib, frames)
+    assert len(src.ring) == pipeline.STAGE_SLOTS
+    try:
+        for k, i in enumerate(order):
+            got = src.get(order, k)
+            assert np.array_equal(got, frames[i])
+            assert (got is frames[i]) == (i in (2, 7))          # pinned frames are handed through, others are copies
+            assert all(j <= k + pipeline.STAGE_SLOTS - 2 for j in src.pending)      # never further ahead than the ring allows
+    finally:
+        src.close()
+    assert lib.freed == pipeline.STAGE_SLOTS and not src.ring
+    all_pinned = pipeline._Sources(Lib({f.ctypes.data for f in frames}), frames)
+    assert all_pinned.pool is None and not all_pinned.ring       # nothing to stage: no threads, no pinned ring
+    all_pinned.close()

@@ -30,6 +30,8 @@ def test_cuda_matches_golden(name):
     (3, 600, 800, np.uint8, 74, {"smooth_size": 0, "levels": 4}),
     (2, 1025, 1537, np.uint16, 75, {"kernel_size": 7, "blur_size": 7, "smooth_size": 9}),
     (12, 96, 136, np.uint8, 76, {"map_type": "max", "temperature": 0.03}),
+    (2, 150, 260, np.uint8, 77, {"kernel_size": 9, "blur_size": 15, "smooth_size": 5}),     # halo 11: > 48 KB of shared memory
+    (2, 140, 200, np.uint16, 78, {"kernel_size": 31, "blur_size": 31, "smooth_size": 0, "levels": 2}),   # the widest kernels
 ])
 def test_cuda_matches_oracle(n, h, w, dtype, seed, kwargs):
     frames = synthetic.make_noise_stack(n, h, w, np.dtype(dtype), seed)
